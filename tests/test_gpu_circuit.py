@@ -1,0 +1,137 @@
+"""Parity of the CUDA circuit kernels (through the C-ABI) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): world/query probabilities 1e-5 relative, gradients
+1e-4 relative, fp32.  The forward is in fact required to be BIT-exact against the fp32
+sequential interpreter (same IEEE ops in the same order); the documented 1e-5 bound is
+checked against the fp64 interpreter.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fp_interp
+from tests.util import rel_err, synthetic_facts
+
+pytestmark = pytest.mark.gpu
+
+BATCHES = [1, 31, 32, 33, 100, 1000, 4096 + 7]
+
+
+@pytest.fixture(scope="module")
+def dc(addition_family, cuda_device):
+    from vael_b200.ops import DeviceCircuit
+    d = DeviceCircuit(addition_family.circuit, cuda_device)
+    assert d.fast_kind == 2, "2-digit addition must take the two-AD fast path"
+    assert d.hash == addition_family.circuit.fnv1a64()
+    return d
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+@pytest.mark.parametrize("B", BATCHES)
+def test_forward_query_scalar_bit_exact(dc, addition_family, B, force_generic):
+    from vael_b200 import _lib
+    from vael_b200.ops import circuit_forward
+    circ = addition_family.circuit
+    facts = synthetic_facts(B, seed=B)
+    for q in (0, 9, 18):
+        w_ref, q_ref = fp_interp.forward(circ, facts, query=q)
+        w, qq = circuit_forward(dc, torch.from_numpy(facts).cuda(), q, force_generic=force_generic)
+        assert _lib.last_kernel() == ("generic-csr" if force_generic else "ad2-tma")
+        np.testing.assert_array_equal(w.cpu().numpy(), w_ref)
+        np.testing.assert_array_equal(qq.cpu().numpy()[:, 0], q_ref)
+        w64, q64 = fp_interp.forward(circ, facts, query=q, dtype=np.float64)
+        assert rel_err(w.cpu().numpy(), w64) < 1e-5 and rel_err(qq.cpu().numpy()[:, 0], q64) < 1e-5
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+@pytest.mark.parametrize("normalize", [False, True])
+def test_forward_query_per_row(dc, addition_family, force_generic, normalize):
+    from vael_b200.ops import circuit_forward
+    circ = addition_family.circuit
+    B = 777
+    facts = synthetic_facts(B, seed=5)
+    qi = np.random.default_rng(1).integers(0, 19, size=B)
+    w_ref, q_ref = fp_interp.forward(circ, facts, query=qi, normalize=normalize)
+    w, q = circuit_forward(dc, torch.from_numpy(facts).cuda(), torch.from_numpy(qi).cuda(),
+                           normalize=normalize, force_generic=force_generic)
+    np.testing.assert_array_equal(w.cpu().numpy(), w_ref)
+    np.testing.assert_array_equal(q.cpu().numpy()[:, 0], q_ref)
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+def test_forward_evidence(dc, addition_family, force_generic):
+    from vael_b200.ops import circuit_forward
+    circ = addition_family.circuit
+    B = 130
+    facts = synthetic_facts(B, seed=6)
+    for e in (0, 7, 18):
+        w_ref, _ = fp_interp.forward(circ, facts, query=e, evidence=True)
+        with torch.no_grad():
+            w, _ = circuit_forward(dc, torch.from_numpy(facts).cuda(), e, evidence=True, force_generic=force_generic)
+        np.testing.assert_array_equal(w.cpu().numpy(), w_ref)
+        np.testing.assert_allclose(w.cpu().numpy().sum(1), 1.0, rtol=1e-5)
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+@pytest.mark.parametrize("normalize", [False, True])
+@pytest.mark.parametrize("B", [1, 33, 1000])
+def test_backward(dc, addition_family, B, normalize, force_generic):
+    from vael_b200.ops import circuit_forward
+    circ = addition_family.circuit
+    rng = np.random.default_rng(B)
+    facts = synthetic_facts(B, seed=B + 1)
+    qi = rng.integers(0, 19, size=B)
+    gw = rng.standard_normal((B, 100)).astype(np.float32)
+    gq = rng.standard_normal((B,)).astype(np.float32)
+    g_ref = fp_interp.backward(circ, facts, gw, gq, qi, normalize=normalize)
+    f = torch.from_numpy(facts).cuda().requires_grad_(True)
+    w, q = circuit_forward(dc, f, torch.from_numpy(qi).cuda(), normalize=normalize, force_generic=force_generic)
+    (w * torch.from_numpy(gw).cuda()).sum().add((q[:, 0] * torch.from_numpy(gq).cuda()).sum()).backward()
+    scale = np.abs(g_ref).max()
+    assert rel_err(f.grad.cpu().numpy(), g_ref, floor=1e-3 * scale) < 1e-4
+    # scalar query, only one of the two upstream gradients present
+    f2 = torch.from_numpy(facts).cuda().requires_grad_(True)
+    w2, q2 = circuit_forward(dc, f2, 9, normalize=normalize, force_generic=force_generic)
+    q2.sum().backward()
+    g2 = fp_interp.backward(circ, facts, None, np.ones(B), 9, normalize=normalize)
+    assert rel_err(f2.grad.cpu().numpy(), g2, floor=1e-3 * np.abs(g2).max()) < 1e-4
+
+
+def test_queries_all(dc, addition_family):
+    from vael_b200.ops import circuit_queries_all
+    circ = addition_family.circuit
+    facts = synthetic_facts(257, seed=3)
+    ref = fp_interp.queries_all(circ, facts)
+    out = circuit_queries_all(dc, torch.from_numpy(facts).cuda())
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
+
+
+def test_empty_batch_and_errors(dc):
+    from vael_b200._lib import VaelError
+    from vael_b200.ops import circuit_forward
+    w, q = circuit_forward(dc, torch.zeros(0, 20, device="cuda"), 3)
+    assert w.shape == (0, 100) and q.shape == (0, 1)
+    with pytest.raises(KeyError):
+        circuit_forward(dc, torch.zeros(4, 20, device="cuda"), 19)
+    with pytest.raises(RuntimeError):
+        circuit_forward(dc, torch.zeros(4, 20), 3)            # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        circuit_forward(dc, torch.zeros(4, 21, device="cuda"), 3)
+    with pytest.raises(RuntimeError):
+        circuit_forward(dc, torch.zeros(4, 20, device="cuda", dtype=torch.float64), 3)
+
+
+def test_unaligned_views_take_the_plain_copy_path(dc, addition_family):
+    """Bulk copies need 16-byte aligned spans; a buffer offset by one float must still work."""
+    from vael_b200.ops import circuit_forward
+    circ = addition_family.circuit
+    B = 70
+    facts = synthetic_facts(B, seed=11)
+    buf = torch.zeros(B * 20 + 1, device="cuda")
+    buf[1:] = torch.from_numpy(facts).cuda().reshape(-1)
+    view = buf[1:].reshape(B, 20)
+    assert view.data_ptr() % 16 != 0
+    w, q = circuit_forward(dc, view, 5)
+    w_ref, q_ref = fp_interp.forward(circ, facts, query=5)
+    np.testing.assert_array_equal(w.cpu().numpy(), w_ref)
+    np.testing.assert_array_equal(q.cpu().numpy()[:, 0], q_ref)

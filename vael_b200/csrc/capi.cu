@@ -1,0 +1,586 @@
+// C-ABI of libvael_b200.so (include/vael_b200.h): circuit upload + validation,
+// kernel dispatch, host-buffer (e2e) variants.  No torch types anywhere.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "params.cuh"
+
+using namespace vael;
+
+// ---------------------------------------------------------------------------
+// error / bookkeeping
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static thread_local const char* g_last_kernel = "";
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+  return fail(VAEL_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                        \
+  do {                                                  \
+    cudaError_t _e = (call);                            \
+    if (_e != cudaSuccess) return cuda_fail(_e, #call); \
+  } while (0)
+
+static int device_sms(int* out) {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev < 64 && cached[dev]) { *out = cached[dev]; return VAEL_OK; }
+  int n = 0;
+  e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+  if (dev < 64) cached[dev] = n;
+  *out = n;
+  return VAEL_OK;
+}
+
+extern "C" int vael_abi_version(void) { return VAEL_B200_ABI_VERSION; }
+extern "C" const char* vael_last_error(void) { return g_err.c_str(); }
+extern "C" int64_t vael_launch_count(void) { return g_launches.load(); }
+extern "C" const char* vael_last_kernel(void) { return g_last_kernel; }
+
+// ---------------------------------------------------------------------------
+// circuit creation
+// ---------------------------------------------------------------------------
+template <typename T>
+static cudaError_t upload(T** dptr, const std::vector<T>& h) {
+  *dptr = nullptr;
+  if (h.empty()) return cudaSuccess;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dptr), h.size() * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+static void fnv(uint64_t& h, const void* data, size_t n) {
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+}
+
+// Is `z` the ProbLog normaliser of two annotated disjunctions over fact columns [0,na) and
+// [na,na+nb):  PROD( SUM(leaves of AD a..., COMPL(leaves of AD a...)), SUM(... b ...) ) ?
+static bool norm_is_ad2(const vael_circuit_desc_t* d, int z, int na, int nb) {
+  auto kind = [&](int n) { return (int)d->node_kind[n]; };
+  auto nch = [&](int n) { return d->child_ptr[n + 1] - d->child_ptr[n]; };
+  auto ch = [&](int n, int i) { return d->child_idx[d->child_ptr[n] + i]; };
+  auto leaves_are = [&](int n, int first, int count, int off) {
+    for (int i = 0; i < count; ++i) {
+      const int c = ch(n, first + i);
+      if (kind(c) != VAEL_NODE_LEAF_POS || d->node_arg[c] != off + i) return false;
+    }
+    return true;
+  };
+  if (kind(z) != VAEL_NODE_PROD || nch(z) != 2) return false;
+  const int sizes[2] = {na, nb}, offs[2] = {0, na};
+  for (int a = 0; a < 2; ++a) {
+    const int s = ch(z, a);
+    if (kind(s) != VAEL_NODE_SUM || nch(s) != sizes[a] + 1) return false;
+    if (!leaves_are(s, 0, sizes[a], offs[a])) return false;
+    const int c = ch(s, sizes[a]);
+    if (kind(c) != VAEL_NODE_COMPL || nch(c) != sizes[a]) return false;
+    if (!leaves_are(c, 0, sizes[a], offs[a])) return false;
+  }
+  return true;
+}
+
+extern "C" void vael_circuit_destroy(vael_circuit_t* c) {
+  if (!c) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(c->device);
+  cudaFree(c->d_nodes); cudaFree(c->d_edges); cudaFree(c->d_world_node); cudaFree(c->d_query_node);
+  cudaFree(c->d_qmask); cudaFree(c->d_par_ptr); cudaFree(c->d_par_rec); cudaFree(c->d_bslot);
+  cudaFree(c->d_fact_leaf_ptr); cudaFree(c->d_fact_leaf);
+  for (auto& S : c->slot) {
+    cudaFree(S.facts); cudaFree(S.worlds); cudaFree(S.query); cudaFree(S.gw); cudaFree(S.gq); cudaFree(S.gf);
+    cudaFree(S.qidx);
+    if (S.stream) cudaStreamDestroy(S.stream);
+  }
+  cudaSetDevice(prev);
+  free(c->h_level_ptr);
+  delete c;
+}
+
+extern "C" int vael_circuit_create(const vael_circuit_desc_t* d, vael_circuit_t** out) {
+  if (!d || !out) return fail(VAEL_E_INVALID, "null argument");
+  *out = nullptr;
+  if (d->n_facts <= 0 || d->n_nodes <= 0 || d->n_levels <= 0 || d->n_edges < 0 || d->n_worlds < 0 ||
+      d->n_queries < 0)
+    return fail(VAEL_E_INVALID, "non-positive circuit dimension");
+  if (d->n_levels > kMaxLevels) return fail(VAEL_E_UNSUPPORTED, "too many levels (max 24)");
+  if (d->semiring != VAEL_SEMIRING_PROB && d->semiring != VAEL_SEMIRING_LOG)
+    return fail(VAEL_E_INVALID, "unknown semiring");
+  if (!d->node_kind || !d->node_arg || !d->level_ptr || !d->child_ptr || (d->n_edges && !d->child_idx) ||
+      (d->n_worlds && !d->world_node) || (d->n_queries && !d->query_node))
+    return fail(VAEL_E_INVALID, "null circuit array");
+  if (d->level_ptr[0] != 0 || d->level_ptr[d->n_levels] != d->n_nodes)
+    return fail(VAEL_E_INVALID, "level_ptr does not cover the nodes");
+  if (d->child_ptr[0] != 0 || d->child_ptr[d->n_nodes] != d->n_edges)
+    return fail(VAEL_E_INVALID, "child_ptr does not cover the edges");
+  std::vector<int> level_of(d->n_nodes, 0);
+  for (int L = 0; L < d->n_levels; ++L) {
+    if (d->level_ptr[L + 1] < d->level_ptr[L]) return fail(VAEL_E_INVALID, "level_ptr not monotone");
+    for (int n = d->level_ptr[L]; n < d->level_ptr[L + 1]; ++n) level_of[n] = L;
+  }
+  for (int n = 0; n < d->n_nodes; ++n) {
+    const int k = d->node_kind[n];
+    const int nc = d->child_ptr[n + 1] - d->child_ptr[n];
+    if (nc < 0) return fail(VAEL_E_INVALID, "child_ptr not monotone");
+    if (k == VAEL_NODE_LEAF_POS || k == VAEL_NODE_LEAF_NEG) {
+      if (d->node_arg[n] < 0 || d->node_arg[n] >= d->n_facts) return fail(VAEL_E_INVALID, "leaf fact column out of range");
+      if (nc != 0 || level_of[n] != 0) return fail(VAEL_E_INVALID, "leaves must be childless level-0 nodes");
+    } else if (k == VAEL_NODE_CONST) {
+      if (d->node_arg[n] < 0 || d->node_arg[n] >= d->n_consts || !d->const_val) return fail(VAEL_E_INVALID, "const index out of range");
+      if (nc != 0) return fail(VAEL_E_INVALID, "const node with children");
+    } else if (k == VAEL_NODE_PROD || k == VAEL_NODE_SUM || k == VAEL_NODE_COMPL) {
+      if (k == VAEL_NODE_COMPL && d->semiring == VAEL_SEMIRING_LOG)
+        return fail(VAEL_E_UNSUPPORTED, "COMPL nodes are not defined for the log semiring");
+      if (nc > 0xffffff) return fail(VAEL_E_UNSUPPORTED, "fan-in too large");
+      for (int e = d->child_ptr[n]; e < d->child_ptr[n + 1]; ++e) {
+        const int c = d->child_idx[e];
+        if (c < 0 || c >= d->n_nodes) return fail(VAEL_E_INVALID, "child index out of range");
+        if (level_of[c] >= level_of[n]) return fail(VAEL_E_INVALID, "child is not in a strictly lower level");
+      }
+    } else {
+      return fail(VAEL_E_INVALID, "unknown node kind");
+    }
+  }
+  std::vector<int> world_pos(d->n_nodes, -1);
+  for (int w = 0; w < d->n_worlds; ++w) {
+    const int n = d->world_node[w];
+    if (n < 0 || n >= d->n_nodes) return fail(VAEL_E_INVALID, "world node out of range");
+    if (world_pos[n] >= 0 && d->node_kind[n] != VAEL_NODE_CONST)
+      return fail(VAEL_E_INVALID, "world nodes must be distinct (constants excepted)");
+    world_pos[n] = w;
+  }
+  for (int q = 0; q < d->n_queries; ++q)
+    if (d->query_node[q] < 0 || d->query_node[q] >= d->n_nodes) return fail(VAEL_E_INVALID, "query node out of range");
+  if (d->norm_node >= d->n_nodes) return fail(VAEL_E_INVALID, "norm node out of range");
+
+  int dev = 0, sms = 0;
+  CK(cudaGetDevice(&dev));
+  if (int rc = device_sms(&sms)) return rc;
+
+  vael_circuit_t* c = new vael_circuit_t();
+  memset(c, 0, sizeof(*c));
+  c->device = dev; c->num_sms = sms;
+  c->n_facts = d->n_facts; c->n_nodes = d->n_nodes; c->n_levels = d->n_levels; c->n_edges = d->n_edges;
+  c->n_worlds = d->n_worlds; c->n_queries = d->n_queries; c->semiring = d->semiring;
+  c->norm_node = d->norm_node < 0 ? -1 : d->norm_node;
+  c->h_level_ptr = static_cast<int32_t*>(malloc(sizeof(int32_t) * (d->n_levels + 1)));
+  memcpy(c->h_level_ptr, d->level_ptr, sizeof(int32_t) * (d->n_levels + 1));
+
+  // identity hash of the arrays as given
+  uint64_t h = 1469598103934665603ull;
+  const int32_t hdr[9] = {d->n_facts, d->n_nodes, d->n_levels, d->n_edges, d->n_worlds, d->n_queries, d->n_consts, d->semiring, c->norm_node};
+  fnv(h, hdr, sizeof(hdr));
+  fnv(h, d->node_kind, d->n_nodes);
+  fnv(h, d->node_arg, sizeof(int32_t) * d->n_nodes);
+  fnv(h, d->level_ptr, sizeof(int32_t) * (d->n_levels + 1));
+  fnv(h, d->child_ptr, sizeof(int32_t) * (d->n_nodes + 1));
+  if (d->n_edges) fnv(h, d->child_idx, sizeof(int32_t) * d->n_edges);
+  if (d->n_consts) fnv(h, d->const_val, sizeof(float) * d->n_consts);
+  if (d->n_worlds) fnv(h, d->world_node, sizeof(int32_t) * d->n_worlds);
+  if (d->n_queries) fnv(h, d->query_node, sizeof(int32_t) * d->n_queries);
+  c->hash = h;
+
+  // node descriptors
+  std::vector<NodeDesc> nodes(d->n_nodes);
+  for (int n = 0; n < d->n_nodes; ++n) {
+    const int k = d->node_kind[n];
+    const int nc = d->child_ptr[n + 1] - d->child_ptr[n];
+    NodeDesc nd{};
+    nd.kind_n = k | (nc << 8);
+    nd.slot = n;
+    if (k == VAEL_NODE_LEAF_POS || k == VAEL_NODE_LEAF_NEG) {
+      nd.a = d->node_arg[n];
+    } else if (k == VAEL_NODE_CONST) {
+      float v = d->const_val[d->node_arg[n]];
+      memcpy(&nd.a, &v, 4);
+    } else if (nc <= 2) {
+      nd.a = nc >= 1 ? d->child_idx[d->child_ptr[n]] : 0;
+      nd.b = nc == 2 ? d->child_idx[d->child_ptr[n] + 1] : 0;
+    } else {
+      nd.a = d->child_ptr[n];  // offset into the edge array
+    }
+    nodes[n] = nd;
+  }
+  std::vector<int32_t> edges(d->child_idx, d->child_idx + d->n_edges);
+  std::vector<int32_t> wn(d->world_node, d->world_node + d->n_worlds), qn(d->query_node, d->query_node + d->n_queries);
+
+  // query -> world membership bit masks (only if every query is a SUM over world nodes)
+  c->mask_words = (d->n_worlds + 31) / 32;
+  std::vector<uint32_t> qmask((size_t)d->n_queries * c->mask_words, 0u);
+  bool masks_ok = d->n_queries > 0 && d->n_worlds > 0 && d->semiring == VAEL_SEMIRING_PROB;
+  for (int q = 0; q < d->n_queries && masks_ok; ++q) {
+    const int n = d->query_node[q];
+    if (d->node_kind[n] == VAEL_NODE_CONST) continue;  // an unsatisfiable query: empty mask (const must be 0)
+    if (world_pos[n] >= 0) {  // a query that holds in exactly one world is that world's node
+      qmask[(size_t)q * c->mask_words + (world_pos[n] >> 5)] |= 1u << (world_pos[n] & 31);
+      continue;
+    }
+    if (d->node_kind[n] != VAEL_NODE_SUM) { masks_ok = false; break; }
+    for (int e = d->child_ptr[n]; e < d->child_ptr[n + 1]; ++e) {
+      const int w = world_pos[d->child_idx[e]];
+      if (w < 0 || d->node_kind[d->child_idx[e]] == VAEL_NODE_CONST) { masks_ok = false; break; }
+      qmask[(size_t)q * c->mask_words + (w >> 5)] |= 1u << (w & 31);
+    }
+  }
+  // the fast path sums members in world order; the CSR children must be listed in that order too
+  bool members_in_world_order = masks_ok;
+  for (int q = 0; q < d->n_queries && members_in_world_order; ++q) {
+    const int n = d->query_node[q];
+    if (d->node_kind[n] != VAEL_NODE_SUM) continue;
+    int prev = -1;
+    for (int e = d->child_ptr[n]; e < d->child_ptr[n + 1]; ++e) {
+      const int w = world_pos[d->child_idx[e]];
+      if (w <= prev) { members_in_world_order = false; break; }
+      prev = w;
+    }
+  }
+
+  // parent lists (transposed CSR) for the gather-form adjoint
+  std::vector<int32_t> par_ptr(d->n_nodes + 1, 0);
+  for (int e = 0; e < d->n_edges; ++e) par_ptr[d->child_idx[e] + 1]++;
+  for (int n = 0; n < d->n_nodes; ++n) par_ptr[n + 1] += par_ptr[n];
+  std::vector<int2> par_rec(d->n_edges);
+  {
+    std::vector<int32_t> fill(par_ptr.begin(), par_ptr.end() - 1);
+    for (int p = 0; p < d->n_nodes; ++p)
+      for (int e = d->child_ptr[p]; e < d->child_ptr[p + 1]; ++e) {
+        const int ch = d->child_idx[e];
+        par_rec[fill[ch]++] = make_int2(p, e - d->child_ptr[p]);
+      }
+  }
+  // which node values does the adjoint need?  children of products (siblings), everything under
+  // the normaliser, and for the log semiring sums and their children (softmax weights)
+  std::vector<char> need(d->n_nodes, 0);
+  for (int p = 0; p < d->n_nodes; ++p) {
+    const int k = d->node_kind[p];
+    const int nc = d->child_ptr[p + 1] - d->child_ptr[p];
+    if (d->semiring == VAEL_SEMIRING_PROB) {
+      if (k == VAEL_NODE_PROD && nc >= 2)
+        for (int e = d->child_ptr[p]; e < d->child_ptr[p + 1]; ++e) need[d->child_idx[e]] = 1;
+    } else if (k == VAEL_NODE_SUM) {
+      need[p] = 1;
+      for (int e = d->child_ptr[p]; e < d->child_ptr[p + 1]; ++e) need[d->child_idx[e]] = 1;
+    }
+  }
+  if (c->norm_node >= 0) need[c->norm_node] = 1;
+  for (int n = d->n_nodes - 1; n >= 0; --n)  // closure: a kept node needs its children
+    if (need[n])
+      for (int e = d->child_ptr[n]; e < d->child_ptr[n + 1]; ++e) need[d->child_idx[e]] = 1;
+  std::vector<int32_t> bslot(d->n_nodes, -1);
+  for (int n = 0; n < d->n_nodes; ++n)
+    if (need[n]) bslot[n] = c->n_bvals++;
+
+  std::vector<int32_t> fl_ptr(d->n_facts + 1, 0), fl;
+  for (int f = 0; f < d->n_facts; ++f) {
+    for (int n = 0; n < d->level_ptr[1]; ++n)
+      if ((d->node_kind[n] == VAEL_NODE_LEAF_POS || d->node_kind[n] == VAEL_NODE_LEAF_NEG) && d->node_arg[n] == f)
+        fl.push_back(n);
+    fl_ptr[f + 1] = (int32_t)fl.size();
+  }
+
+  // structured fast path: worlds[i*nb+k] = PROD(LEAF_POS(i), LEAF_POS(na+k))
+  c->fast_kind = 0;
+  if (d->semiring == VAEL_SEMIRING_PROB && masks_ok && members_in_world_order && d->n_worlds > 0) {
+    int nb = 0;
+    bool ok = true;
+    auto leafcol = [&](int n) { return d->node_kind[n] == VAEL_NODE_LEAF_POS ? d->node_arg[n] : -1; };
+    for (int w = 0; w < d->n_worlds && ok; ++w) {
+      const int n = d->world_node[w];
+      if (d->node_kind[n] != VAEL_NODE_PROD || d->child_ptr[n + 1] - d->child_ptr[n] != 2) { ok = false; break; }
+      if (leafcol(d->child_idx[d->child_ptr[n]]) == 0) nb = w + 1; else break;
+    }
+    if (ok && nb > 0 && d->n_worlds % nb == 0) {
+      const int na = d->n_worlds / nb;
+      ok = (na + nb == d->n_facts);
+      for (int w = 0; w < d->n_worlds && ok; ++w) {
+        const int n = d->world_node[w];
+        if (d->node_kind[n] != VAEL_NODE_PROD || d->child_ptr[n + 1] - d->child_ptr[n] != 2) { ok = false; break; }
+        ok = leafcol(d->child_idx[d->child_ptr[n]]) == w / nb && leafcol(d->child_idx[d->child_ptr[n] + 1]) == na + w % nb;
+      }
+      if (ok && ad2_supported(na, nb)) {
+        c->fast_kind = 2; c->ad_na = na; c->ad_nb = nb;
+        c->norm_fast_ok = c->norm_node >= 0 && norm_is_ad2(d, c->norm_node, na, nb);
+      }
+    }
+  }
+
+  cudaError_t e = cudaSuccess;
+  auto up = [&](auto** dp, const auto& v) { if (e == cudaSuccess) e = upload(dp, v); };
+  up(&c->d_nodes, nodes); up(&c->d_edges, edges); up(&c->d_world_node, wn); up(&c->d_query_node, qn);
+  if (masks_ok) up(&c->d_qmask, qmask);
+  up(&c->d_par_ptr, par_ptr); up(&c->d_par_rec, par_rec); up(&c->d_bslot, bslot);
+  up(&c->d_fact_leaf_ptr, fl_ptr); up(&c->d_fact_leaf, fl);
+  if (e != cudaSuccess) {
+    vael_circuit_destroy(c);
+    return cuda_fail(e, "circuit upload");
+  }
+  *out = c;
+  return VAEL_OK;
+}
+
+extern "C" int vael_circuit_fast_kind(const vael_circuit_t* c) { return c ? c->fast_kind : 0; }
+extern "C" uint64_t vael_circuit_hash(const vael_circuit_t* c) { return c ? c->hash : 0; }
+
+// ---------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------
+static void fill_gen(const vael_circuit_t* c, GenParams& G) {
+  memset(&G, 0, sizeof(G));
+  G.nodes = c->d_nodes; G.edges = c->d_edges; G.world_node = c->d_world_node; G.query_node = c->d_query_node;
+  G.qmask = c->d_qmask; G.mask_words = c->mask_words;
+  G.n_nodes = c->n_nodes; G.n_facts = c->n_facts; G.n_worlds = c->n_worlds; G.n_queries = c->n_queries;
+  G.n_levels = c->n_levels; G.semiring = c->semiring; G.norm_node = c->norm_node;
+  for (int L = 0; L <= c->n_levels; ++L) G.level_ptr[L] = c->h_level_ptr[L];
+  G.bslot = c->d_bslot; G.n_bvals = c->n_bvals; G.par_ptr = c->d_par_ptr; G.par_rec = c->d_par_rec;
+  G.fact_leaf_ptr = c->d_fact_leaf_ptr; G.fact_leaf = c->d_fact_leaf;
+}
+
+static int check_common(const vael_circuit_t* c, const float* facts, const int32_t* qidx, int32_t qs, int64_t B,
+                        uint32_t flags, bool need_query) {
+  if (!c) return fail(VAEL_E_INVALID, "null circuit");
+  if (B < 0) return fail(VAEL_E_INVALID, "negative batch size");
+  if (B > 0 && !facts) return fail(VAEL_E_INVALID, "null facts");
+  int dev = -1;
+  CK(cudaGetDevice(&dev));
+  if (dev != c->device) return fail(VAEL_E_INVALID, "circuit was created on another CUDA device");
+  if ((flags & VAEL_FLAG_NORMALIZE) && c->norm_node < 0)
+    return fail(VAEL_E_UNSUPPORTED, "NORMALIZE requested but the circuit has no normaliser node");
+  if (need_query && !qidx && (qs < 0 || qs >= c->n_queries))
+    return fail(VAEL_E_INVALID, "query index out of range");
+  if ((flags & VAEL_FLAG_EVIDENCE) && !c->d_qmask)
+    return fail(VAEL_E_UNSUPPORTED, "EVIDENCE needs query nodes that are sums over world nodes");
+  return VAEL_OK;
+}
+
+static bool use_fast(const vael_circuit_t* c, uint32_t flags) {
+  if (c->fast_kind != 2 || (flags & VAEL_FLAG_FORCE_GENERIC)) return false;
+  if ((flags & VAEL_FLAG_NORMALIZE) && !c->norm_fast_ok) return false;
+  return true;
+}
+
+extern "C" int vael_circuit_forward(const vael_circuit_t* c, const float* facts, const int32_t* qidx, int32_t qs,
+                                    int64_t B, float* worlds, float* query, uint32_t flags, void* stream) {
+  const bool needq = query != nullptr || (flags & VAEL_FLAG_EVIDENCE);
+  if (int rc = check_common(c, facts, qidx, qs, B, flags, needq)) return rc;
+  if (B == 0) return VAEL_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (use_fast(c, flags)) {
+    Ad2Params P{};
+    P.facts = facts; P.qidx = qidx; P.qscalar = needq ? qs : -1; P.n_queries = c->n_queries; P.qmask = c->d_qmask;
+    P.B = B; P.worlds = worlds; P.query = query;
+    CK(ad2_forward(c->ad_na, c->ad_nb, P, flags & VAEL_FLAG_NORMALIZE, flags & VAEL_FLAG_EVIDENCE, c->num_sms, st));
+    g_last_kernel = "ad2-tma";
+  } else {
+    GenParams G;
+    fill_gen(c, G);
+    G.facts = facts; G.qidx = qidx; G.qscalar = needq ? qs : -1; G.B = B; G.flags = flags; G.worlds = worlds; G.query = query;
+    if (!generic_fits(G, false)) return fail(VAEL_E_UNSUPPORTED, "circuit too large for the shared-memory tile");
+    CK(generic_forward(G, c->num_sms, st));
+    g_last_kernel = "generic-csr";
+  }
+  g_launches++;
+  return VAEL_OK;
+}
+
+extern "C" int vael_circuit_queries_all(const vael_circuit_t* c, const float* facts, int64_t B, float* queries_all,
+                                        uint32_t flags, void* stream) {
+  if (int rc = check_common(c, facts, nullptr, 0, B, flags & ~VAEL_FLAG_EVIDENCE, false)) return rc;
+  if (flags & VAEL_FLAG_EVIDENCE) return fail(VAEL_E_INVALID, "EVIDENCE is meaningless for queries_all");
+  if (B == 0) return VAEL_OK;
+  if (!queries_all) return fail(VAEL_E_INVALID, "null output");
+  GenParams G;
+  fill_gen(c, G);
+  G.facts = facts; G.qscalar = -1; G.B = B; G.flags = flags; G.queries_all = queries_all;
+  if (!generic_fits(G, false)) return fail(VAEL_E_UNSUPPORTED, "circuit too large for the shared-memory tile");
+  CK(generic_forward(G, c->num_sms, static_cast<cudaStream_t>(stream)));
+  g_last_kernel = "generic-csr";
+  g_launches++;
+  return VAEL_OK;
+}
+
+extern "C" int vael_circuit_backward(const vael_circuit_t* c, const float* facts, const int32_t* qidx, int32_t qs,
+                                     int64_t B, const float* grad_worlds, const float* grad_query,
+                                     float* grad_facts, uint32_t flags, void* stream) {
+  const bool needq = grad_query != nullptr;
+  if (int rc = check_common(c, facts, qidx, qs, B, flags, needq)) return rc;
+  if (flags & VAEL_FLAG_EVIDENCE) return fail(VAEL_E_UNSUPPORTED, "evidence mode has no adjoint (the reference only uses it under no_grad)");
+  if (B == 0) return VAEL_OK;
+  if (!grad_facts) return fail(VAEL_E_INVALID, "null grad_facts");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (use_fast(c, flags)) {
+    Ad2Params P{};
+    P.facts = facts; P.qidx = qidx; P.qscalar = needq ? qs : -1; P.n_queries = c->n_queries; P.qmask = c->d_qmask;
+    P.B = B; P.grad_worlds = grad_worlds; P.grad_query = grad_query; P.grad_facts = grad_facts;
+    CK(ad2_backward(c->ad_na, c->ad_nb, P, flags & VAEL_FLAG_NORMALIZE, c->num_sms, st));
+    g_last_kernel = "ad2-tma";
+  } else {
+    GenParams G;
+    fill_gen(c, G);
+    G.facts = facts; G.qidx = qidx; G.qscalar = needq ? qs : -1; G.B = B; G.flags = flags;
+    G.grad_worlds = grad_worlds; G.grad_query = grad_query; G.grad_facts = grad_facts;
+    if (!generic_fits(G, true)) return fail(VAEL_E_UNSUPPORTED, "circuit too large for the shared-memory tile");
+    CK(generic_backward(G, c->num_sms, st));
+    g_last_kernel = "generic-csr";
+  }
+  g_launches++;
+  return VAEL_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host-buffer variants: chunked, double-buffered over two streams so that the H2D
+// copy of chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1 overlap
+// ---------------------------------------------------------------------------
+static int ensure_slots(vael_circuit_t* x) {
+  const vael_circuit_t* c = x;
+  if (x->chunk_rows) return VAEL_OK;
+  const char* env = getenv("VAEL_HOST_CHUNK_ROWS");
+  long long rows = env && *env ? atoll(env) : (1 << 18);
+  if (rows < 32) rows = 32;
+  const size_t F = c->n_facts, W = c->n_worlds;
+  for (int s = 0; s < 2; ++s) {
+    auto& S = x->slot[s];
+    CK(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&S.facts, rows * F * 4)); CK(cudaMalloc(&S.gf, rows * F * 4));
+    CK(cudaMalloc(&S.worlds, rows * W * 4)); CK(cudaMalloc(&S.gw, rows * W * 4));
+    CK(cudaMalloc(&S.query, rows * 4)); CK(cudaMalloc(&S.gq, rows * 4)); CK(cudaMalloc(&S.qidx, rows * 4));
+  }
+  x->chunk_rows = rows;
+  return VAEL_OK;
+}
+
+static int host_pipeline(const vael_circuit_t* c, const float* facts_h, const int32_t* qidx_h, int32_t qs, int64_t B,
+                         const float* gw_h, const float* gq_h, float* worlds_h, float* query_h, float* gf_h,
+                         uint32_t flags, bool backward) {
+  if (!c) return fail(VAEL_E_INVALID, "null circuit");
+  if (B < 0 || (B > 0 && !facts_h)) return fail(VAEL_E_INVALID, "bad host buffers");
+  if (backward && B > 0 && !gf_h) return fail(VAEL_E_INVALID, "null grad_facts host buffer");
+  vael_circuit_t* x = const_cast<vael_circuit_t*>(c);
+  if (int rc = ensure_slots(x)) return rc;
+  const size_t F = c->n_facts, W = c->n_worlds;
+  int idx = 0;
+  for (int64_t r0 = 0; r0 < B; r0 += x->chunk_rows, ++idx) {
+    const int64_t n = (B - r0 < x->chunk_rows) ? (B - r0) : x->chunk_rows;
+    auto& S = x->slot[idx & 1];
+    CK(cudaMemcpyAsync(S.facts, facts_h + r0 * F, n * F * 4, cudaMemcpyHostToDevice, S.stream));
+    if (qidx_h) CK(cudaMemcpyAsync(S.qidx, qidx_h + r0, n * 4, cudaMemcpyHostToDevice, S.stream));
+    if (worlds_h || query_h) {
+      if (int rc = vael_circuit_forward(c, S.facts, qidx_h ? S.qidx : nullptr, qs, n, worlds_h ? S.worlds : nullptr,
+                                        query_h ? S.query : nullptr, flags, S.stream))
+        return rc;
+      if (worlds_h) CK(cudaMemcpyAsync(worlds_h + r0 * W, S.worlds, n * W * 4, cudaMemcpyDeviceToHost, S.stream));
+      if (query_h) CK(cudaMemcpyAsync(query_h + r0, S.query, n * 4, cudaMemcpyDeviceToHost, S.stream));
+    }
+    if (backward) {
+      if (gw_h) CK(cudaMemcpyAsync(S.gw, gw_h + r0 * W, n * W * 4, cudaMemcpyHostToDevice, S.stream));
+      if (gq_h) CK(cudaMemcpyAsync(S.gq, gq_h + r0, n * 4, cudaMemcpyHostToDevice, S.stream));
+      if (int rc = vael_circuit_backward(c, S.facts, qidx_h ? S.qidx : nullptr, qs, n, gw_h ? S.gw : nullptr,
+                                         gq_h ? S.gq : nullptr, S.gf, flags, S.stream))
+        return rc;
+      CK(cudaMemcpyAsync(gf_h + r0 * F, S.gf, n * F * 4, cudaMemcpyDeviceToHost, S.stream));
+    }
+  }
+  CK(cudaStreamSynchronize(x->slot[0].stream));
+  CK(cudaStreamSynchronize(x->slot[1].stream));
+  return VAEL_OK;
+}
+
+extern "C" int vael_circuit_forward_host(const vael_circuit_t* c, const float* facts_h, const int32_t* qidx_h,
+                                         int32_t qs, int64_t B, float* worlds_h, float* query_h, uint32_t flags) {
+  return host_pipeline(c, facts_h, qidx_h, qs, B, nullptr, nullptr, worlds_h, query_h, nullptr, flags, false);
+}
+extern "C" int vael_circuit_fwdbwd_host(const vael_circuit_t* c, const float* facts_h, const int32_t* qidx_h,
+                                        int32_t qs, int64_t B, const float* gw_h, const float* gq_h, float* worlds_h,
+                                        float* query_h, float* gf_h, uint32_t flags) {
+  return host_pipeline(c, facts_h, qidx_h, qs, B, gw_h, gq_h, worlds_h, query_h, gf_h, flags, true);
+}
+
+// ---------------------------------------------------------------------------
+// facts head, Gumbel sampling, ELBO terms
+// ---------------------------------------------------------------------------
+extern "C" int vael_facts_forward(const float* logits, int64_t B, int32_t n_groups, int32_t group, float eps,
+                                  float* facts, void* stream) {
+  if (B < 0 || n_groups <= 0 || group <= 0) return fail(VAEL_E_INVALID, "bad shape");
+  if (B == 0) return VAEL_OK;
+  if (!logits || !facts) return fail(VAEL_E_INVALID, "null pointer");
+  int sms = 0;
+  if (int rc = device_sms(&sms)) return rc;
+  CK(facts_forward(logits, B, n_groups, group, eps, facts, sms, static_cast<cudaStream_t>(stream)));
+  g_launches++;
+  return VAEL_OK;
+}
+extern "C" int vael_facts_backward(const float* logits, const float* grad_facts, int64_t B, int32_t n_groups,
+                                   int32_t group, float eps, float* grad_logits, void* stream) {
+  if (B < 0 || n_groups <= 0 || group <= 0) return fail(VAEL_E_INVALID, "bad shape");
+  if (B == 0) return VAEL_OK;
+  if (!logits || !grad_facts || !grad_logits) return fail(VAEL_E_INVALID, "null pointer");
+  int sms = 0;
+  if (int rc = device_sms(&sms)) return rc;
+  CK(facts_backward(logits, grad_facts, B, n_groups, group, eps, grad_logits, sms, static_cast<cudaStream_t>(stream)));
+  g_launches++;
+  return VAEL_OK;
+}
+
+extern "C" int vael_gumbel_world_forward(const float* scores, const float* noise, uint64_t seed, int64_t B, int32_t W,
+                                         int32_t is_log, float tau, const float* herbrand, int32_t H, float* y_soft,
+                                         int32_t* world_idx, float* world_h, void* stream) {
+  if (B < 0 || W <= 0 || W > 1024 || H < 0 || !(tau > 0.0f)) return fail(VAEL_E_INVALID, "bad shape or tau");
+  if (B == 0) return VAEL_OK;
+  if (!scores || (world_h && !herbrand)) return fail(VAEL_E_INVALID, "null pointer");
+  int sms = 0;
+  if (int rc = device_sms(&sms)) return rc;
+  GumbelParams P{};
+  P.scores = scores; P.noise = noise; P.seed = seed; P.B = B; P.W = W; P.H = H; P.is_log = is_log; P.tau = tau;
+  P.herbrand = herbrand; P.y_soft = y_soft; P.world_idx = world_idx; P.world_h = world_h;
+  CK(gumbel_forward(P, sms, static_cast<cudaStream_t>(stream)));
+  g_launches++;
+  return VAEL_OK;
+}
+extern "C" int vael_gumbel_world_backward(const float* scores, const float* y_soft, const float* grad_world_h,
+                                          int64_t B, int32_t W, int32_t is_log, float tau, const float* herbrand,
+                                          int32_t H, float* grad_scores, void* stream) {
+  if (B < 0 || W <= 0 || W > 1024 || H <= 0 || !(tau > 0.0f)) return fail(VAEL_E_INVALID, "bad shape or tau");
+  if (B == 0) return VAEL_OK;
+  if (!y_soft || !grad_world_h || !herbrand || !grad_scores || (!is_log && !scores)) return fail(VAEL_E_INVALID, "null pointer");
+  if ((size_t)W * H * 4 > 48 * 1024) return fail(VAEL_E_UNSUPPORTED, "Herbrand table larger than 48 KB");
+  int sms = 0;
+  if (int rc = device_sms(&sms)) return rc;
+  GumbelParams P{};
+  P.scores = scores; P.B = B; P.W = W; P.H = H; P.is_log = is_log; P.tau = tau; P.herbrand = herbrand;
+  P.y_soft = const_cast<float*>(y_soft); P.grad_world_h = grad_world_h; P.grad_scores = grad_scores;
+  CK(gumbel_backward(P, sms, static_cast<cudaStream_t>(stream)));
+  g_launches++;
+  return VAEL_OK;
+}
+
+extern "C" int64_t vael_elbo_workspace_bytes(void) { return (int64_t)elbo_workspace_bytes(); }
+
+extern "C" int vael_elbo_terms(const float* recon, const float* x, int64_t B, int64_t D, const float* mu,
+                               const float* logvar, int32_t L, const float* query_prob, float recon_w, float kl_w,
+                               float query_w, float* terms, float* grad_recon, float* grad_mu, float* grad_logvar,
+                               float* grad_query, void* workspace, void* stream) {
+  if (B <= 0 || D <= 0 || L < 0) return fail(VAEL_E_INVALID, "bad shape");
+  if (!recon || !x || !terms || !workspace || (L > 0 && (!mu || !logvar))) return fail(VAEL_E_INVALID, "null pointer");
+  int sms = 0;
+  if (int rc = device_sms(&sms)) return rc;
+  ElboParams P{};
+  P.recon = recon; P.x = x; P.B = B; P.D = D; P.mu = mu; P.logvar = logvar; P.L = L; P.query_prob = query_prob;
+  P.recon_w = recon_w; P.kl_w = kl_w; P.query_w = query_w; P.terms = terms; P.grad_recon = grad_recon;
+  P.grad_mu = grad_mu; P.grad_logvar = grad_logvar; P.grad_query = grad_query;
+  CK(elbo_terms(P, workspace, sms, static_cast<cudaStream_t>(stream)));
+  g_launches++;
+  return VAEL_OK;
+}

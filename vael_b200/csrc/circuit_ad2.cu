@@ -1,0 +1,473 @@
+// Structured fast path: circuits whose world level is the outer product of two
+// annotated disjunctions (2-digit MNIST addition: 10x10 worlds; Mario: 9x9) and
+// whose query nodes are sums over world nodes.
+//
+// Reference semantics: MNISTPairsVAELModel.problog_inference / compute_query
+// (models/vael.py:200-225) == query-mode sdd.evaluate (models/vael.py:98-117);
+// evidence mode == problog_inference_with_evidence (models/vael.py:119-135).
+//
+// Execution model (sm_100a): warp-autonomous pipelines.  Every warp owns a ring
+// of shared-memory stages and streams 32-row sub-tiles of the batch-major
+// tensors through them with 1-D bulk copies (cp.async.bulk, the TMA engine):
+//   global facts[32,F] --bulk--> smem --LDS.128--> registers (one batch row per
+//   lane) --FMUL/FADD--> STS.128 --> smem worlds[32,W] --bulk--> global.
+// A 32-row sub-tile of a row-major [B,F] / [B,W] tensor is one contiguous span,
+// so each transfer is a single bulk copy; lanes touch shared memory with
+// conflict-free 128-bit accesses (row strides 80 B / 400 B land 8 consecutive
+// lanes on 8 distinct 16-byte bank groups).  There is no block-level barrier.
+#include "params.cuh"
+
+namespace vael {
+
+template <int NA, int NB>
+struct Ad2Shape {
+  static constexpr int F = NA + NB;
+  static constexpr int W = NA * NB;
+  static constexpr int MW = (W + 31) / 32;
+  static constexpr int FV = (F % 4 == 0) ? 4 : ((F % 2 == 0) ? 2 : 1);
+  static constexpr int WV = (W % 4 == 0) ? 4 : ((W % 2 == 0) ? 2 : 1);
+  static constexpr int FACT_BYTES = kWarp * F * 4;  // multiple of 128
+  static constexpr int OUT_BYTES = kWarp * W * 4;   // multiple of 128
+};
+
+
+template <int V>
+__device__ __forceinline__ void lds_vec(float* dst, const float* src) {
+  if constexpr (V == 4) {
+    float4 t = *reinterpret_cast<const float4*>(src);
+    dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+  } else if constexpr (V == 2) {
+    float2 t = *reinterpret_cast<const float2*>(src);
+    dst[0] = t.x; dst[1] = t.y;
+  } else {
+    dst[0] = src[0];
+  }
+}
+template <int V>
+__device__ __forceinline__ void sts_vec(float* dst, const float* src) {
+  if constexpr (V == 4) {
+    *reinterpret_cast<float4*>(dst) = make_float4(src[0], src[1], src[2], src[3]);
+  } else if constexpr (V == 2) {
+    *reinterpret_cast<float2*>(dst) = make_float2(src[0], src[1]);
+  } else {
+    dst[0] = src[0];
+  }
+}
+
+// plain (non-bulk) copies for tails / unaligned buffers
+__device__ __forceinline__ void warp_copy(float* dst, const float* src, int n, int lane) {
+  for (int i = lane; i < n; i += kWarp) dst[i] = src[i];
+}
+
+// normaliser Z = prod over ADs of (sum(p) + (1 - sum(p))): ProbLog's WMC of the AD
+// constraints with the null-choice atom (ad_complement); == 1 up to rounding.
+template <int NA, int NB>
+__device__ __forceinline__ float ad2_normaliser(const float* p) {
+  float sa = p[0];
+#pragma unroll
+  for (int i = 1; i < NA; ++i) sa = __fadd_rn(sa, p[i]);
+  float sb = p[NA];
+#pragma unroll
+  for (int k = 1; k < NB; ++k) sb = __fadd_rn(sb, p[NA + k]);
+  const float za = __fadd_rn(sa, __fsub_rn(1.0f, sa));
+  const float zb = __fadd_rn(sb, __fsub_rn(1.0f, sb));
+  return __fmul_rn(za, zb);
+}
+
+template <int MW>
+__device__ __forceinline__ void load_mask(uint32_t* m, const Ad2Params& P, long long row, bool valid) {
+#pragma unroll
+  for (int i = 0; i < MW; ++i) m[i] = 0u;
+  if (!valid) return;
+  const int32_t q = P.qidx ? __ldg(P.qidx + row) : P.qscalar;
+  if (q >= 0 && q < P.n_queries) {
+#pragma unroll
+    for (int i = 0; i < MW; ++i) m[i] = __ldg(P.qmask + (long long)q * MW + i);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------
+template <int NA, int NB, bool NORM, bool EVID, int S, int SO>
+__global__ void __launch_bounds__(256) ad2_forward_kernel(const Ad2Params P) {
+  using Sh = Ad2Shape<NA, NB>;
+  constexpr int F = Sh::F, W = Sh::W, MW = Sh::MW, FV = Sh::FV, WV = Sh::WV;
+  constexpr int PER_WARP = S * Sh::FACT_BYTES + SO * Sh::OUT_BYTES + 128;
+  extern __shared__ __align__(128) uint8_t smem[];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  uint8_t* wbase = smem + (size_t)warp * PER_WARP;
+  float* fact_s = reinterpret_cast<float*>(wbase);
+  float* out_s = reinterpret_cast<float*>(wbase + S * Sh::FACT_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(wbase + S * Sh::FACT_BYTES + SO * Sh::OUT_BYTES);
+
+  const long long n_sub = (P.B + kWarp - 1) / kWarp;
+  const long long gw = (long long)blockIdx.x * nwarps + warp;
+  const long long GW = (long long)gridDim.x * nwarps;
+  if (gw >= n_sub) return;
+
+  const bool in_al = aligned16(P.facts);
+  const bool out_al = P.worlds != nullptr && aligned16(P.worlds);
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+
+  uint32_t phase = 0;    // bit s: parity the next wait on stage s uses
+  uint32_t via_tma = 0;  // bit s: the in-flight load of stage s went through the bulk engine
+
+  auto load_sub = [&](long long sub, int s) {
+    const long long row0 = sub * kWarp;
+    const int rows = (int)min((long long)kWarp, P.B - row0);
+    const uint32_t bytes = (uint32_t)rows * F * 4u;
+    float* dst = fact_s + s * kWarp * F;
+    const float* src = P.facts + row0 * F;
+    if (in_al && (bytes & 15u) == 0) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full[s], bytes);
+        bulk_g2s(dst, src, bytes, &full[s]);
+      }
+      via_tma |= 1u << s;
+    } else {
+      warp_copy(dst, src, rows * F, lane);
+      via_tma &= ~(1u << s);
+    }
+  };
+
+  // prologue
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const long long sub = gw + (long long)s * GW;
+    if (sub < n_sub) load_sub(sub, s);
+  }
+
+  long long it = 0;
+  for (long long sub = gw; sub < n_sub; sub += GW, ++it) {
+    const int s = (int)(it % S);
+    const int so = (int)(it % SO);
+    const long long row0 = sub * kWarp;
+    const int rows = (int)min((long long)kWarp, P.B - row0);
+    const long long row = row0 + lane;
+    const bool valid = lane < rows;
+
+    uint32_t m[MW];
+    load_mask<MW>(m, P, row, valid);
+
+    if (via_tma & (1u << s)) {
+      mbar_wait(&full[s], (phase >> s) & 1u);
+      phase ^= 1u << s;
+    } else {
+      __syncwarp();
+    }
+
+    // this lane's batch row -> registers
+    float p[F];
+    {
+      const float* src = fact_s + (s * kWarp + lane) * F;
+#pragma unroll
+      for (int c = 0; c < F / FV; ++c) lds_vec<FV>(p + c * FV, src + c * FV);
+    }
+    __syncwarp();
+    // refill this stage with the sub-tile S iterations ahead
+    {
+      const long long nxt = sub + (long long)S * GW;
+      if (nxt < n_sub) load_sub(nxt, s);
+    }
+
+    // the bulk store issued SO iterations ago must have finished reading out_s[so]
+    if (lane == 0) bulk_wait_read<SO - 1>();
+    __syncwarp();
+
+    float z = 1.0f;
+    if constexpr (NORM) z = ad2_normaliser<NA, NB>(p);
+
+    float acc = 0.0f;  // value of the selected query node
+    if constexpr (EVID) {
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const float v = __fmul_rn(p[w / NB], p[NA + (w % NB)]);
+        if ((m[w >> 5] >> (w & 31)) & 1u) acc = __fadd_rn(acc, v);
+      }
+    }
+
+    float* orow = out_s + (so * kWarp + lane) * W;
+#pragma unroll
+    for (int c = 0; c < W / WV; ++c) {
+      float o[WV];
+#pragma unroll
+      for (int u = 0; u < WV; ++u) {
+        const int w = c * WV + u;
+        float v = __fmul_rn(p[w / NB], p[NA + (w % NB)]);
+        const bool member = (m[w >> 5] >> (w & 31)) & 1u;
+        if constexpr (EVID) {
+          v = member ? v / acc : 0.0f;  // P(w | e) = [w |= e] P(w) / P(e)
+        } else {
+          if (member) acc = __fadd_rn(acc, v);
+          if constexpr (NORM) v = v / z;
+        }
+        o[u] = v;
+      }
+      sts_vec<WV>(orow + c * WV, o);
+    }
+
+    if (P.query != nullptr && valid) {
+      float qv = acc;  // WMC of the selected query node, sequential fp32 sum in world order
+      if constexpr (NORM) qv = acc / z;
+      P.query[row] = qv;
+    }
+
+    if (P.worlds != nullptr) {
+      const uint32_t bytes = (uint32_t)rows * W * 4u;
+      float* dst = P.worlds + row0 * W;
+      const float* src = out_s + so * kWarp * W;
+      if (out_al && (bytes & 15u) == 0) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          bulk_s2g(dst, src, bytes);
+          bulk_commit();
+        }
+      } else {
+        __syncwarp();
+        warp_copy(dst, src, rows * W, lane);
+      }
+    }
+  }
+  if (lane == 0) bulk_wait_all<0>();
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------
+// backward (adjoint); values are recomputed from the facts, nothing was saved
+// ---------------------------------------------------------------------------
+template <int NA, int NB, bool NORM, int S, int SO>
+__global__ void __launch_bounds__(256) ad2_backward_kernel(const Ad2Params P) {
+  using Sh = Ad2Shape<NA, NB>;
+  constexpr int F = Sh::F, W = Sh::W, MW = Sh::MW, FV = Sh::FV, WV = Sh::WV;
+  constexpr int STAGE_IN = Sh::FACT_BYTES + Sh::OUT_BYTES;
+  constexpr int PER_WARP = S * STAGE_IN + SO * Sh::FACT_BYTES + 128;
+  extern __shared__ __align__(128) uint8_t smem[];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  uint8_t* wbase = smem + (size_t)warp * PER_WARP;
+  uint8_t* gout_base = wbase + S * STAGE_IN;
+  uint64_t* full = reinterpret_cast<uint64_t*>(gout_base + SO * Sh::FACT_BYTES);
+
+  const long long n_sub = (P.B + kWarp - 1) / kWarp;
+  const long long gw = (long long)blockIdx.x * nwarps + warp;
+  const long long GW = (long long)gridDim.x * nwarps;
+  if (gw >= n_sub) return;
+
+  const bool has_gw = P.grad_worlds != nullptr;
+  const bool in_al = aligned16(P.facts) && (!has_gw || aligned16(P.grad_worlds));
+  const bool out_al = aligned16(P.grad_facts);
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+
+  uint32_t phase = 0, via_tma = 0;
+
+  auto load_sub = [&](long long sub, int s) {
+    const long long row0 = sub * kWarp;
+    const int rows = (int)min((long long)kWarp, P.B - row0);
+    const uint32_t fbytes = (uint32_t)rows * F * 4u;
+    const uint32_t wbytes = has_gw ? (uint32_t)rows * W * 4u : 0u;
+    float* fdst = reinterpret_cast<float*>(wbase + s * STAGE_IN);
+    float* wdst = reinterpret_cast<float*>(wbase + s * STAGE_IN + Sh::FACT_BYTES);
+    const float* fsrc = P.facts + row0 * F;
+    const float* wsrc = has_gw ? P.grad_worlds + row0 * W : nullptr;
+    if (in_al && ((fbytes | wbytes) & 15u) == 0) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full[s], fbytes + wbytes);
+        bulk_g2s(fdst, fsrc, fbytes, &full[s]);
+        if (has_gw) bulk_g2s(wdst, wsrc, wbytes, &full[s]);
+      }
+      via_tma |= 1u << s;
+    } else {
+      warp_copy(fdst, fsrc, rows * F, lane);
+      if (has_gw) warp_copy(wdst, wsrc, rows * W, lane);
+      via_tma &= ~(1u << s);
+    }
+  };
+
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const long long sub = gw + (long long)s * GW;
+    if (sub < n_sub) load_sub(sub, s);
+  }
+
+  long long it = 0;
+  for (long long sub = gw; sub < n_sub; sub += GW, ++it) {
+    const int s = (int)(it % S);
+    const int so = (int)(it % SO);
+    const long long row0 = sub * kWarp;
+    const int rows = (int)min((long long)kWarp, P.B - row0);
+    const long long row = row0 + lane;
+    const bool valid = lane < rows;
+
+    uint32_t m[MW];
+    load_mask<MW>(m, P, row, valid);
+    float gq = 0.0f;
+    if (P.grad_query != nullptr && valid) gq = __ldg(P.grad_query + row);
+
+    if (via_tma & (1u << s)) {
+      mbar_wait(&full[s], (phase >> s) & 1u);
+      phase ^= 1u << s;
+    } else {
+      __syncwarp();
+    }
+
+    const float* frow = reinterpret_cast<const float*>(wbase + s * STAGE_IN) + lane * F;
+    const float* grow = reinterpret_cast<const float*>(wbase + s * STAGE_IN + Sh::FACT_BYTES) + lane * W;
+
+    float p[F];
+#pragma unroll
+    for (int c = 0; c < F / FV; ++c) lds_vec<FV>(p + c * FV, frow + c * FV);
+
+    float z = 1.0f;
+    if constexpr (NORM) z = ad2_normaliser<NA, NB>(p);
+
+    float g[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) g[f] = 0.0f;
+
+#pragma unroll
+    for (int c = 0; c < W / WV; ++c) {
+      float a[WV];
+      if (has_gw) {
+        lds_vec<WV>(a, grow + c * WV);
+      } else {
+#pragma unroll
+        for (int u = 0; u < WV; ++u) a[u] = 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < WV; ++u) {
+        const int w = c * WV + u;
+        float av = a[u];
+        if ((m[w >> 5] >> (w & 31)) & 1u) av += gq;
+        if constexpr (NORM) av = av / z;  // Z's own adjoint is exactly 0 (d/dp of s + (1 - s))
+        g[w / NB] = fmaf(av, p[NA + (w % NB)], g[w / NB]);
+        g[NA + (w % NB)] = fmaf(av, p[w / NB], g[NA + (w % NB)]);
+      }
+    }
+    __syncwarp();
+    {
+      const long long nxt = sub + (long long)S * GW;
+      if (nxt < n_sub) load_sub(nxt, s);
+    }
+
+    if (lane == 0) bulk_wait_read<SO - 1>();
+    __syncwarp();
+
+    float* gdst_s = reinterpret_cast<float*>(gout_base + so * Sh::FACT_BYTES);
+    {
+      float* orow = gdst_s + lane * F;
+#pragma unroll
+      for (int c = 0; c < F / FV; ++c) sts_vec<FV>(orow + c * FV, g + c * FV);
+    }
+    {
+      const uint32_t bytes = (uint32_t)rows * F * 4u;
+      float* dst = P.grad_facts + row0 * F;
+      if (out_al && (bytes & 15u) == 0) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          bulk_s2g(dst, gdst_s, bytes);
+          bulk_commit();
+        }
+      } else {
+        __syncwarp();
+        warp_copy(dst, gdst_s, rows * F, lane);
+      }
+    }
+  }
+  if (lane == 0) bulk_wait_all<0>();
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  return atoi(v);
+}
+
+template <int NA, int NB, bool NORM, bool EVID>
+static cudaError_t launch_fwd_t(const Ad2Params& P, int num_sms, cudaStream_t st) {
+  constexpr int S = 2, SO = 2;
+  using Sh = Ad2Shape<NA, NB>;
+  constexpr int PER_WARP = S * Sh::FACT_BYTES + SO * Sh::OUT_BYTES + 128;
+  static int nw = 0, cps = 0;
+  if (nw == 0) {
+    int w = env_int("VAEL_AD2_FWD_WARPS", 7);
+    w = max(1, min(8, w));
+    while (w > 1 && w * PER_WARP > 227 * 1024) --w;
+    cps = max(1, min(8, env_int("VAEL_AD2_FWD_CTAS_PER_SM", (227 * 1024) / (w * PER_WARP + 1024))));
+    cudaError_t e = cudaFuncSetAttribute(ad2_forward_kernel<NA, NB, NORM, EVID, S, SO>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, w * PER_WARP);
+    if (e != cudaSuccess) return e;
+    nw = w;
+  }
+  const long long n_sub = (P.B + kWarp - 1) / kWarp;
+  long long grid = (n_sub + nw - 1) / nw;
+  grid = min(grid, (long long)num_sms * cps);
+  ad2_forward_kernel<NA, NB, NORM, EVID, S, SO><<<(unsigned)grid, nw * 32, nw * PER_WARP, st>>>(P);
+  return cudaGetLastError();
+}
+
+template <int NA, int NB, bool NORM>
+static cudaError_t launch_bwd_t(const Ad2Params& P, int num_sms, cudaStream_t st) {
+  constexpr int S = 2, SO = 2;
+  using Sh = Ad2Shape<NA, NB>;
+  constexpr int PER_WARP = S * (Sh::FACT_BYTES + Sh::OUT_BYTES) + SO * Sh::FACT_BYTES + 128;
+  static int nw = 0, cps = 0;
+  if (nw == 0) {
+    int w = env_int("VAEL_AD2_BWD_WARPS", 6);
+    w = max(1, min(8, w));
+    while (w > 1 && w * PER_WARP > 227 * 1024) --w;
+    cps = max(1, min(8, env_int("VAEL_AD2_BWD_CTAS_PER_SM", (227 * 1024) / (w * PER_WARP + 1024))));
+    cudaError_t e = cudaFuncSetAttribute(ad2_backward_kernel<NA, NB, NORM, S, SO>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, w * PER_WARP);
+    if (e != cudaSuccess) return e;
+    nw = w;
+  }
+  const long long n_sub = (P.B + kWarp - 1) / kWarp;
+  long long grid = (n_sub + nw - 1) / nw;
+  grid = min(grid, (long long)num_sms * cps);
+  ad2_backward_kernel<NA, NB, NORM, S, SO><<<(unsigned)grid, nw * 32, nw * PER_WARP, st>>>(P);
+  return cudaGetLastError();
+}
+
+template <int NA, int NB>
+static cudaError_t launch_fwd_shape(const Ad2Params& P, bool norm, bool evid, int num_sms, cudaStream_t st) {
+  if (evid) return norm ? launch_fwd_t<NA, NB, true, true>(P, num_sms, st) : launch_fwd_t<NA, NB, false, true>(P, num_sms, st);
+  return norm ? launch_fwd_t<NA, NB, true, false>(P, num_sms, st) : launch_fwd_t<NA, NB, false, false>(P, num_sms, st);
+}
+
+bool ad2_supported(int na, int nb) { return (na == 10 && nb == 10) || (na == 9 && nb == 9); }
+
+cudaError_t ad2_forward(int na, int nb, const Ad2Params& P, bool norm, bool evid, int num_sms, cudaStream_t st) {
+  if (na == 10 && nb == 10) return launch_fwd_shape<10, 10>(P, norm, evid, num_sms, st);
+  if (na == 9 && nb == 9) return launch_fwd_shape<9, 9>(P, norm, evid, num_sms, st);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t ad2_backward(int na, int nb, const Ad2Params& P, bool norm, int num_sms, cudaStream_t st) {
+  if (na == 10 && nb == 10) return norm ? launch_bwd_t<10, 10, true>(P, num_sms, st) : launch_bwd_t<10, 10, false>(P, num_sms, st);
+  if (na == 9 && nb == 9) return norm ? launch_bwd_t<9, 9, true>(P, num_sms, st) : launch_bwd_t<9, 9, false>(P, num_sms, st);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace vael

@@ -1,0 +1,121 @@
+// Shared device helpers for the vael_b200 kernels (sm_100a).
+// PTX wrappers for the bulk-copy engine (TMA 1-D bulk copies, SASS UBLKCP),
+// mbarriers and the generic<->async proxy fence.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vael_b200.h"
+
+namespace vael {
+
+constexpr int kWarp = 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier --------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// make barrier initialisation visible to the async proxy (bulk-copy engine)
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// ---- bulk copies (cp.async.bulk, 1-D "TMA") --------------------------------
+// global -> shared, completion signalled on an mbarrier (complete_tx::bytes).
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// shared -> global, tracked by the per-thread bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// order this thread's generic-proxy shared-memory writes before later async-proxy reads
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- host-side circuit handle ----------------------------------------------
+struct NodeDesc {  // one int4 per node, read with a single broadcast load
+  int32_t kind_n;  // kind | (n_children << 8)
+  int32_t a;       // leaf: fact column; const: float bits; op: child 0 (or edge offset if n_children > 2)
+  int32_t b;       // op: child 1 (n_children == 2)
+  int32_t slot;    // value slot (== node id)
+};
+
+}  // namespace vael
+
+// Opaque handle behind vael_circuit_t (include/vael_b200.h)
+struct vael_host_slot {  // one stage of the host-buffer (e2e) pipeline
+  cudaStream_t stream;
+  float *facts, *worlds, *query, *gw, *gq, *gf;
+  int32_t* qidx;
+};
+
+struct vael_circuit {
+  int device;
+  int num_sms;
+  int32_t n_facts, n_nodes, n_levels, n_edges, n_worlds, n_queries, semiring, norm_node;
+  uint64_t hash;
+  int32_t* h_level_ptr;      // host copy [n_levels+1]
+  // device arrays — forward CSR
+  vael::NodeDesc* d_nodes;   // [n_nodes]
+  int32_t* d_edges;          // [n_edges]
+  int32_t* d_world_node;     // [n_worlds]
+  int32_t* d_query_node;     // [n_queries]
+  uint32_t* d_qmask;         // [n_queries][mask_words] world membership of each query (SUM over world nodes), or null
+  int32_t mask_words;
+  // device arrays — backward (transposed CSR: for every node the list of parent edges)
+  int32_t* d_par_ptr;        // [n_nodes+1]
+  int2* d_par_rec;           // [n_edges] {parent node, position of the child inside the parent}
+  int32_t* d_bslot;          // [n_nodes] slot of the node's value in the backward tile, -1 = not kept
+  int32_t n_bvals;
+  int32_t* d_fact_leaf_ptr;  // [n_facts+1] leaf nodes per fact column
+  int32_t* d_fact_leaf;      // leaf node ids
+  // structured fast path
+  int fast_kind;             // 0 none, 2 = two annotated disjunctions (outer product)
+  int32_t ad_na, ad_nb;      // AD sizes; fact columns [0,na) and [na,na+nb)
+  bool norm_fast_ok;         // the normaliser node has the two-AD shape the fast path recomputes
+  // host-buffer pipeline (allocated lazily by the *_host entry points)
+  vael_host_slot slot[2];
+  long long chunk_rows;
+};

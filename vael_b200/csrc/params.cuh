@@ -1,0 +1,107 @@
+// Parameter blocks and host launchers shared between the kernel translation units and capi.cu.
+#pragma once
+#include "common.cuh"
+
+namespace vael {
+
+// ---- circuit_ad2.cu --------------------------------------------------------
+struct Ad2Params {
+  const float* facts;        // [B,F]
+  const int32_t* qidx;       // [B] or null
+  int32_t qscalar;
+  int32_t n_queries;
+  const uint32_t* qmask;     // [Q][MW] world membership of every query node
+  long long B;
+  // forward
+  float* worlds;             // [B,W] or null
+  float* query;              // [B] or null
+  // backward
+  const float* grad_worlds;  // [B,W] or null
+  const float* grad_query;   // [B] or null
+  float* grad_facts;         // [B,F]
+};
+bool ad2_supported(int na, int nb);
+cudaError_t ad2_forward(int na, int nb, const Ad2Params& P, bool norm, bool evid, int num_sms, cudaStream_t st);
+cudaError_t ad2_backward(int na, int nb, const Ad2Params& P, bool norm, int num_sms, cudaStream_t st);
+
+// ---- circuit_generic.cu ----------------------------------------------------
+constexpr int kMaxLevels = 24;
+struct GenParams {
+  // forward CSR
+  const NodeDesc* nodes;
+  const int32_t* edges;
+  const int32_t* world_node;
+  const int32_t* query_node;
+  const uint32_t* qmask;  // may be null (evidence mode unsupported then)
+  int32_t mask_words;
+  int32_t n_nodes, n_facts, n_worlds, n_queries, n_levels, semiring, norm_node;
+  int32_t level_ptr[kMaxLevels + 1];
+  // batch
+  const float* facts;
+  const int32_t* qidx;
+  int32_t qscalar;
+  long long B;
+  uint32_t flags;
+  // forward outputs
+  float* worlds;       // [B,W] or null
+  float* query;        // [B] or null
+  float* queries_all;  // [B,Q] or null
+  // backward
+  const float* grad_worlds;
+  const float* grad_query;
+  float* grad_facts;
+  const int32_t* bslot;          // [n_nodes] value slot in the backward tile, -1 = not kept
+  int32_t n_bvals;
+  const int32_t* par_ptr;        // [n_nodes+1]
+  const int2* par_rec;           // [n_edges] {parent node, position of the child inside the parent}
+  const int32_t* fact_leaf_ptr;  // [F+1]
+  const int32_t* fact_leaf;      // leaf node ids per fact column
+};
+bool generic_fits(const GenParams& P, bool backward);
+cudaError_t generic_forward(const GenParams& P, int num_sms, cudaStream_t st);
+cudaError_t generic_backward(const GenParams& P, int num_sms, cudaStream_t st);
+
+// ---- sampling.cu -----------------------------------------------------------
+struct GumbelParams {
+  const float* scores;    // [B,W]
+  const float* noise;     // [B,W] or null
+  uint64_t seed;
+  long long B;
+  int32_t W, H, is_log;
+  float tau;
+  const float* herbrand;  // [W,H]
+  float* y_soft;          // [B,W]
+  int32_t* world_idx;     // [B]
+  float* world_h;         // [B,H]
+  const float* grad_world_h;  // [B,H]
+  float* grad_scores;         // [B,W]
+};
+cudaError_t gumbel_forward(const GumbelParams& P, int num_sms, cudaStream_t st);
+cudaError_t gumbel_backward(const GumbelParams& P, int num_sms, cudaStream_t st);
+cudaError_t facts_forward(const float* logits, long long B, int n_groups, int group, float eps, float* facts,
+                          int num_sms, cudaStream_t st);
+cudaError_t facts_backward(const float* logits, const float* grad_facts, long long B, int n_groups, int group,
+                           float eps, float* grad_logits, int num_sms, cudaStream_t st);
+
+// ---- elbo.cu ---------------------------------------------------------------
+struct ElboParams {
+  const float* recon;
+  const float* x;
+  long long B, D;
+  const float* mu;
+  const float* logvar;
+  int32_t L;
+  const float* query_prob;  // [B] or null
+  float recon_w, kl_w, query_w;
+  float* terms;  // [4] {loss, recon, kl, qbce}
+  float* grad_recon;
+  float* grad_mu;
+  float* grad_logvar;
+  float* grad_query;
+  unsigned int* counter;  // workspace[0]
+  double* partials;       // workspace + 16 bytes: [grid][3]
+};
+size_t elbo_workspace_bytes();
+cudaError_t elbo_terms(ElboParams P, void* workspace, int num_sms, cudaStream_t st);
+
+}  // namespace vael

@@ -1,0 +1,249 @@
+// Gumbel-softmax world sampling + Herbrand projection, and the facts head.
+//
+// Reference: logits = log(worlds_prob); world = F.gumbel_softmax(logits, tau=1, hard=True);
+// world_h = world @ herbrand_base      (models/vael.py:61-65, :82-84; Mario :335-338)
+// and MNISTPairsVAELModel.compute_facts_probability (models/vael.py:159-177).
+//
+// One warp per batch row, lane <-> world: global accesses are coalesced and the
+// max / argmax / sum reductions are warp shuffles; nothing is staged in shared
+// memory except the small 0/1 Herbrand table.
+#include "params.cuh"
+
+namespace vael {
+
+// ---- Philox4x32-10 (Salmon et al. 2011), counter = (row, world), key = seed -------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+// Gumbel(0,1) = -log(E), E ~ Exp(1) = -log(U), U in (0,1]  (torch: -empty.exponential_().log())
+__device__ __forceinline__ float gumbel_from_bits(uint32_t bits) {
+  const float u = (static_cast<float>(bits >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0,1]
+  const float e = fmaxf(-logf(u), 1.17549435e-38f);
+  return -logf(e);
+}
+
+
+template <int ITEMS>
+__global__ void __launch_bounds__(256) gumbel_forward_kernel(const GumbelParams P) {
+  const int lane = threadIdx.x & 31;
+  const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float inv_tau = 1.0f / P.tau;
+  for (long long row = gwarp; row < P.B; row += nwarp) {
+    float z[ITEMS];
+    float mx = -INFINITY;
+    int arg = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const int e = lane + j * kWarp;
+      z[j] = -INFINITY;
+      if (e < P.W) {
+        const float s = __ldg(P.scores + row * P.W + e);
+        const float logit = P.is_log ? s : logf(s);
+        float g;
+        if (P.noise != nullptr) {
+          g = __ldg(P.noise + row * P.W + e);
+        } else {
+          const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)e, 0u),
+                                        make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+          g = gumbel_from_bits(r.x);
+        }
+        z[j] = (logit + g) * inv_tau;
+        if (z[j] > mx) { mx = z[j]; arg = e; }
+      }
+    }
+    // warp arg-max, ties -> lowest world index
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oarg = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (omx > mx || (omx == mx && oarg < arg)) { mx = omx; arg = oarg; }
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      z[j] = (lane + j * kWarp < P.W) ? expf(z[j] - mx) : 0.0f;
+      sum += z[j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    float ys_arg = 0.0f;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const int e = lane + j * kWarp;
+      const float ys = z[j] / sum;
+      if (e < P.W) {
+        if (P.y_soft != nullptr) P.y_soft[row * P.W + e] = ys;
+        if (e == arg) ys_arg = ys;
+      }
+    }
+    ys_arg = __shfl_sync(0xffffffffu, ys_arg, arg & 31);
+    // straight-through forward value of the selected component: (1 - y_soft) + y_soft
+    const float one = (1.0f - ys_arg) + ys_arg;
+    if (P.world_idx != nullptr && lane == 0) P.world_idx[row] = arg;
+    if (P.world_h != nullptr) {
+      for (int h = lane; h < P.H; h += kWarp) P.world_h[row * P.H + h] = one * __ldg(P.herbrand + (long long)arg * P.H + h);
+    }
+  }
+}
+
+template <int ITEMS>
+__global__ void __launch_bounds__(256) gumbel_backward_kernel(const GumbelParams P) {
+  extern __shared__ float hb[];  // [W][H] Herbrand table
+  for (int i = threadIdx.x; i < P.W * P.H; i += blockDim.x) hb[i] = __ldg(P.herbrand + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float inv_tau = 1.0f / P.tau;
+  for (long long row = gwarp; row < P.B; row += nwarp) {
+    // grad wrt the (straight-through) world vector: G_e = sum_h gh[h] * H[e,h]
+    float G[ITEMS], ys[ITEMS];
+    float dot = 0.0f;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const int e = lane + j * kWarp;
+      G[j] = 0.0f;
+      ys[j] = 0.0f;
+      if (e < P.W) {
+        float acc = 0.0f;
+        for (int h = 0; h < P.H; ++h) acc = fmaf(__ldg(P.grad_world_h + row * P.H + h), hb[e * P.H + h], acc);
+        G[j] = acc;
+        ys[j] = __ldg(P.y_soft + row * P.W + e);
+        dot = fmaf(ys[j], acc, dot);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const int e = lane + j * kWarp;
+      if (e < P.W) {
+        float d = ys[j] * (G[j] - dot) * inv_tau;  // d loss / d logit_e
+        if (!P.is_log) d = d / __ldg(P.scores + row * P.W + e);  // logit = log p
+        P.grad_scores[row * P.W + e] = d;
+      }
+    }
+  }
+}
+
+static int pick_items(int W) {
+  const int need = (W + kWarp - 1) / kWarp;
+  const int opts[] = {1, 2, 3, 4, 8, 16, 32};
+  for (int o : opts)
+    if (need <= o) return o;
+  return -1;
+}
+
+static int launch_grid(long long B, int num_sms) {
+  const long long warps_per_block = 8;
+  long long blocks = (B + warps_per_block - 1) / warps_per_block;
+  return (int)max(1LL, min(blocks, (long long)num_sms * 8));
+}
+
+cudaError_t gumbel_forward(const GumbelParams& P, int num_sms, cudaStream_t st) {
+  const int grid = launch_grid(P.B, num_sms);
+  switch (pick_items(P.W)) {
+    case 1: gumbel_forward_kernel<1><<<grid, 256, 0, st>>>(P); break;
+    case 2: gumbel_forward_kernel<2><<<grid, 256, 0, st>>>(P); break;
+    case 3: gumbel_forward_kernel<3><<<grid, 256, 0, st>>>(P); break;
+    case 4: gumbel_forward_kernel<4><<<grid, 256, 0, st>>>(P); break;
+    case 8: gumbel_forward_kernel<8><<<grid, 256, 0, st>>>(P); break;
+    case 16: gumbel_forward_kernel<16><<<grid, 256, 0, st>>>(P); break;
+    case 32: gumbel_forward_kernel<32><<<grid, 256, 0, st>>>(P); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t gumbel_backward(const GumbelParams& P, int num_sms, cudaStream_t st) {
+  const int grid = launch_grid(P.B, num_sms);
+  const size_t smem = (size_t)P.W * P.H * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  switch (pick_items(P.W)) {
+    case 1: gumbel_backward_kernel<1><<<grid, 256, smem, st>>>(P); break;
+    case 2: gumbel_backward_kernel<2><<<grid, 256, smem, st>>>(P); break;
+    case 3: gumbel_backward_kernel<3><<<grid, 256, smem, st>>>(P); break;
+    case 4: gumbel_backward_kernel<4><<<grid, 256, smem, st>>>(P); break;
+    case 8: gumbel_backward_kernel<8><<<grid, 256, smem, st>>>(P); break;
+    case 16: gumbel_backward_kernel<16><<<grid, 256, smem, st>>>(P); break;
+    case 32: gumbel_backward_kernel<32><<<grid, 256, smem, st>>>(P); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// facts head: per group softmax, + eps, / detached sum   (models/vael.py:159-177)
+// one thread per (row, group); a group is `group` contiguous floats
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) facts_forward_kernel(const float* __restrict__ logits, long long n_groups_total,
+                                                            int group, float eps, float* __restrict__ facts) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < n_groups_total; gi += stride) {
+    const float* x = logits + gi * group;
+    float* y = facts + gi * group;
+    float mx = -INFINITY;
+    for (int i = 0; i < group; ++i) mx = fmaxf(mx, __ldg(x + i));
+    float s = 0.0f;
+    for (int i = 0; i < group; ++i) s += expf(__ldg(x + i) - mx);
+    float zsum = 0.0f;
+    for (int i = 0; i < group; ++i) {
+      const float v = expf(__ldg(x + i) - mx) / s + eps;
+      y[i] = v;
+      zsum += v;
+    }
+    for (int i = 0; i < group; ++i) y[i] = y[i] / zsum;
+  }
+}
+
+__global__ void __launch_bounds__(256) facts_backward_kernel(const float* __restrict__ logits,
+                                                             const float* __restrict__ grad_facts,
+                                                             long long n_groups_total, int group, float eps,
+                                                             float* __restrict__ grad_logits) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < n_groups_total; gi += stride) {
+    const float* x = logits + gi * group;
+    const float* gf = grad_facts + gi * group;
+    float* gx = grad_logits + gi * group;
+    float mx = -INFINITY;
+    for (int i = 0; i < group; ++i) mx = fmaxf(mx, __ldg(x + i));
+    float s = 0.0f;
+    for (int i = 0; i < group; ++i) s += expf(__ldg(x + i) - mx);
+    float zsum = 0.0f;
+    for (int i = 0; i < group; ++i) zsum += expf(__ldg(x + i) - mx) / s + eps;
+    // f = (y + eps) / Z with Z detached  ->  dL/dy_i = gf_i / Z ; softmax: dx_i = y_i (dy_i - sum_j y_j dy_j)
+    float dot = 0.0f;
+    for (int i = 0; i < group; ++i) dot = fmaf(expf(__ldg(x + i) - mx) / s, __ldg(gf + i) / zsum, dot);
+    for (int i = 0; i < group; ++i) {
+      const float yi = expf(__ldg(x + i) - mx) / s;
+      gx[i] = yi * (__ldg(gf + i) / zsum - dot);
+    }
+  }
+}
+
+cudaError_t facts_forward(const float* logits, long long B, int n_groups, int group, float eps, float* facts,
+                          int num_sms, cudaStream_t st) {
+  const long long total = B * n_groups;
+  const int grid = (int)max(1LL, min((total + 255) / 256, (long long)num_sms * 8));
+  facts_forward_kernel<<<grid, 256, 0, st>>>(logits, total, group, eps, facts);
+  return cudaGetLastError();
+}
+cudaError_t facts_backward(const float* logits, const float* grad_facts, long long B, int n_groups, int group,
+                           float eps, float* grad_logits, int num_sms, cudaStream_t st) {
+  const long long total = B * n_groups;
+  const int grid = (int)max(1LL, min((total + 255) / 256, (long long)num_sms * 8));
+  facts_backward_kernel<<<grid, 256, 0, st>>>(logits, grad_facts, total, group, eps, grad_logits);
+  return cudaGetLastError();
+}
+
+}  // namespace vael
