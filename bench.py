@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Benchmark of the VAEL logic hot path (BASELINE.json metric: circuit evals/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+One "step" = one forward + one adjoint backward of the compiled 2-digit-addition circuit
+over B batch rows per GPU (synthetic facts in the domain compute_facts_probability emits,
+per-row random query, random upstream gradients).  One eval = one (row, labelled query)
+output: 101 per row (100 digits(j,k) worlds + the addition query), SURVEY.md §8(d) M1.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+EVALS_PER_ROW = 101            # Q of query-mode evaluate: 100 worlds + 1 addition query
+FWD_BYTES = 80 + 4 + 400 + 4   # read facts[20] + query idx, write worlds[100] + query   (fp32/int32)
+BWD_BYTES = 400 + 4 + 80 + 4 + 80  # read grad_worlds, grad_query, facts, query idx; write grad_facts
+WORKLOAD = ("2digit-MNIST-addition compiled circuit (F=20 facts, W=100 worlds, Q=19 sums), fwd+bwd, "
+            "per-row query, fp32")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=1 << 23, help="batch rows per GPU per step (device-resident arm)")
+    ap.add_argument("--e2e-rows", type=int, default=1 << 20, help="batch rows per GPU per step (host-buffer arm)")
+    ap.add_argument("--cpu-rows", type=int, default=1 << 19, help="rows per step of the CPU baseline sample")
+    ap.add_argument("--train-batch", type=int, default=4096, help="per-GPU batch of the VAEL train-step probe")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def synthetic_facts(rows, device, seed):
+    """softmax(3*N(0,1)) + 1e-5, renormalised: the a14 domain."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    logits = 3.0 * torch.randn(rows, 2, 10, device=device, generator=g)
+    p = torch.softmax(logits, dim=-1) + 1e-5
+    return (p / p.sum(-1, keepdim=True)).reshape(rows, 20).contiguous(), g
+
+
+# ---------------------------------------------------------------------------
+# the reference's CPU path: oracle port of models/vael.py:208-225 + autograd
+# ---------------------------------------------------------------------------
+def cpu_reference_rate(rows, steps, warmup):
+    """evals/s of the reference's dense logic path (forward + autograd backward) on the host
+    cores, torch CPU with all its threads, on `rows` rows per step."""
+    from oracle import dense_path
+    facts, g = synthetic_facts(rows, "cpu", 1234)
+    facts = facts.reshape(rows, 2, 10)
+    w_q = dense_path.worlds_queries_matrix()
+    gw = torch.randn(rows, 100, generator=g)
+    gq = torch.randn(rows, 1, generator=g)
+    q = int(torch.randint(0, 19, (1,), generator=g))
+
+    def step():
+        f = facts.clone().requires_grad_(True)
+        qp, worlds = dense_path.dense_inference(f, w_q, q)   # one query per batch: the reference's own mode
+        torch.autograd.backward([worlds, qp], [gw, gq])
+        return f.grad
+
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return rows * EVALS_PER_ROW / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    rate, dt = cpu_reference_rate(args.cpu_rows, steps, warmup)
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": "circuit_evals_per_sec", "value": rate, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rows_per_step": args.cpu_rows, "evals_per_row": EVALS_PER_ROW},
+        "cpu_baseline": {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.cpu_rows} rows/step x {steps} steps, torch CPU fp32 port of "
+                                   f"models/vael.py:208-225 + autograd, os.cpu_count()={os.cpu_count()}"},
+        "e2e": {"value": rate, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# clocks during the timed region
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    """SM clock + throttle reasons sampled from NVML every ~1 ms by a host thread while the
+    main thread waits for the GPU (falls back to one nvidia-smi query if pynvml is missing)."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
+    def __init__(self, gpu_index):
+        self.samples, self.stop_flag, self.thread, self.nv, self.h = [], False, None, None, None
+        self.gpu_index = gpu_index
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES remaps torch's index; resolve through the PCI bus id
+            bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(gpu_index), "pci_bus_id") else None
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        self.h = h
+            self.nv = pynvml
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.nv = None
+
+    def _pump(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, rs))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
+    def stop(self, t0, t1):
+        if self.nv is None:
+            try:
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu_index)], capture_output=True, text=True, timeout=10).stdout
+                a, b = (float(v) for v in out.strip().split(","))
+                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "note": "single nvidia-smi query after the run"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples
+        mhz = [s[1] for s in inside]
+        bits = 0
+        for s in inside:
+            bits |= int(s[2])
+        reasons = sorted(n for n, b in self.REASONS.items() if bits & b)
+        try:
+            mx = float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        return {"sm_mhz": statistics.median(mhz) if mhz else None, "sm_max_mhz": mx, "reasons": reasons,
+                "samples": len(mhz)}
+
+
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from vael_b200 import _lib
+    from vael_b200.mnist_task import compile_addition_family
+    from vael_b200.ops import DeviceCircuit, _p
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the vael_b200 path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    lib = _lib.load()
+    fam = compile_addition_family(2, 10)
+    dc = DeviceCircuit(fam.circuit, dev)
+    B, K, W = args.rows, max(1, args.steps), max(3, args.warmup)
+    facts, g = synthetic_facts(B, dev, 1234 + rank)
+    qidx = torch.randint(0, 19, (B,), device=dev, dtype=torch.int32, generator=g)
+    gw = torch.randn(B, 100, device=dev, generator=g)
+    gq = torch.randn(B, device=dev, generator=g)
+    worlds = torch.empty(B, 100, device=dev)
+    query = torch.empty(B, device=dev)
+    gf = torch.empty(B, 20, device=dev)
+    stream = torch.cuda.current_stream()
+    sp = torch.cuda.current_stream().cuda_stream
+
+    def fwd():
+        _lib.check(lib.vael_circuit_forward(dc.handle, _p(facts), _p(qidx), -1, B, _p(worlds), _p(query), 0, sp))
+
+    def bwd():
+        _lib.check(lib.vael_circuit_backward(dc.handle, _p(facts), _p(qidx), -1, B, _p(gw), _p(gq), _p(gf), 0, sp))
+
+    for _ in range(W):
+        fwd(); bwd()
+    barrier()
+    # ---- timed region: exactly K steps, per-kernel events on the launching stream -------------
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = _lib.launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        ev[k][0].record(stream); fwd()
+        ev[k][1].record(stream); bwd()
+        ev[k][2].record(stream)
+    barrier()
+    t1 = time.perf_counter()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    total_ms = max_over_ranks(ev[0][0].elapsed_time(ev[K - 1][2]))
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    ms_per_step = total_ms / K
+    value = world * B * EVALS_PER_ROW / (ms_per_step * 1e-3)
+    kernel_family = _lib.last_kernel()
+
+    # ---- e2e: the C-ABI host-buffer call, pinned host memory, copies inside the timed region --------
+    Be = args.e2e_rows
+    e2e = None
+    if not args.no_e2e:
+        hf = facts[:Be].cpu().pin_memory(); hq = qidx[:Be].cpu().pin_memory()
+        hgw = gw[:Be].cpu().pin_memory(); hgq = gq[:Be].cpu().pin_memory()
+        hw = torch.empty(Be, 100).pin_memory(); hqo = torch.empty(Be).pin_memory(); hgf = torch.empty(Be, 20).pin_memory()
+
+        def e2e_step():
+            _lib.check(lib.vael_circuit_fwdbwd_host(dc.handle, _p(hf), _p(hq), -1, Be, _p(hgw), _p(hgq), _p(hw),
+                                                    _p(hqo), _p(hgf), 0))
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        ke = max(3, min(K, 10))
+        te0 = time.perf_counter()
+        for _ in range(ke):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks((time.perf_counter() - te0) / ke)
+        assert torch.equal(hw[:4096], worlds[:4096].cpu()), "e2e path and device path disagree"
+        e2e = {"value": world * Be * EVALS_PER_ROW / e2e_s, "unit": "evals/s",
+               "h2d_bytes_per_step": Be * (80 + 4 + 400 + 4), "d2h_bytes_per_step": Be * (400 + 4 + 80),
+               "rows_per_gpu": Be, "ms_per_step": e2e_s * 1e3,
+               "api": "vael_circuit_fwdbwd_host (C-ABI, pinned host buffers, chunked double-buffered copies)"}
+
+    # ---- secondary probe: VAEL train step (configs[1]), DDP when N > 1 --------------------------------
+    train = None
+    if not args.no_train:
+        try:
+            train = train_probe(args, dev, rank, world, distributed, barrier, max_over_ranks)
+        except Exception as exc:  # the probe must never cost the headline line
+            train = {"error": repr(exc)[:200]}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, dt = cpu_reference_rate(args.cpu_rows, 8, 2)
+        cpu = {"value": rate, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{args.cpu_rows} rows/step x 8 steps ({dt * 1e3:.0f} ms/step), torch CPU fp32 port of "
+                         f"models/vael.py:208-225 + autograd, os.cpu_count()={os.cpu_count()}"}
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        kern = [{"name": "ad2_forward_kernel" if kernel_family == "ad2-tma" else "generic_forward_kernel",
+                 "ms": fwd_ms, "bytes_per_row": FWD_BYTES, "GBs": B * FWD_BYTES / fwd_ms / 1e6},
+                {"name": "ad2_backward_kernel" if kernel_family == "ad2-tma" else "generic_backward_kernel",
+                 "ms": bwd_ms, "bytes_per_row": BWD_BYTES, "GBs": B * BWD_BYTES / bwd_ms / 1e6}]
+        dom = max(kern, key=lambda k: k["ms"])
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom["name"])
+        line = {
+            "metric": "circuit_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rows_per_gpu": B, "evals_per_row": EVALS_PER_ROW,
+                       "kernel_family": kernel_family, "l2": "inputs larger than L2 (per-GPU step traffic "
+                       f"{B * (FWD_BYTES + BWD_BYTES) / 1e9:.2f} GB vs 126 MB L2)", "parallelism": f"rows sharded x{world}, "
+                       "circuit replicated, no collective on the data path"},
+            "roofline": {"bound": "hbm", "kernel": dom["name"], "achieved": dom["GBs"], "peak": peak, "unit": "GB/s",
+                         "frac": dom["GBs"] / peak, "traffic": traffic, "peak_source": peak_src, "kernels": kern,
+                         "algorithmic_bytes_per_launch": B * dom["bytes_per_row"]},
+            "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu, "train": train,
+        }
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+def train_probe(args, dev, rank, world, distributed, barrier, max_over_ranks):
+    """VAEL train samples/s (BASELINE.json configs[1]: 2digit-MNIST addition, batch 4096 per GPU,
+    DDP): encoder/decoder in PyTorch, the logic path on the vael_b200 kernels, Adam, NCCL all-reduce."""
+    from vael_b200.mnist_task import build_model_dict, build_worlds_queries_matrix
+    from vael_b200.networks import MNISTPairsDecoder, MNISTPairsEncoder, MNISTPairsMLP
+    from vael_b200.train import train_step
+    from vael_b200.vael import MNISTPairsVAELModel
+    torch.manual_seed(0)
+    Bt = args.train_batch
+    model = MNISTPairsVAELModel(MNISTPairsEncoder(hidden_channels=64, latent_dim=23),
+                                MNISTPairsDecoder(label_dim=20, hidden_channels=64, latent_dim=8),
+                                MNISTPairsMLP(in_features=15, n_facts=20), (15, 8), build_model_dict(2, 10, device=dev),
+                                build_worlds_queries_matrix(2, 10).to(dev), dropout=0.5, is_train=True, device=dev,
+                                query_per_row=True).to(dev)
+    step_model = model
+    if distributed:
+        step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index])
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.randn(Bt, 1, 28, 56, device=dev, generator=g)
+    d = torch.randint(0, 10, (Bt, 2), device=dev, generator=g)
+    labels = torch.cat([d, d.sum(1, keepdim=True), -torch.ones(Bt, 1, dtype=torch.long, device=dev)], 1)
+    for _ in range(5):
+        train_step(step_model, opt, x, labels)
+    barrier()
+    n = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        terms = train_step(step_model, opt, x, labels)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / n
+    return {"metric": "vael_train_samples_per_sec", "value": world * Bt / (ms * 1e-3), "unit": "samples/s",
+            "ms_per_step": ms, "global_batch": world * Bt, "loss": float(terms[0].item()),
+            "config": "2digit-MNIST addition VAEL, synthetic 28x56 images, random-init weights, Adam, "
+                      + ("DDP/NCCL" if distributed else "single GPU")}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -38,3 +38,7 @@ out = dict(B=B, kernel=_lib.last_kernel(), fwd_ms=tf, bwd_ms=tb, fwd_GBs=B * 488
            copy_GBs=2 * a.numel() * 4 / tc / 1e6,
            env={k: v for k, v in os.environ.items() if k.startswith("VAEL_")})
 print(json.dumps(out))
+# write-only reference: how fast can this box stream pure stores?
+z = torch.empty(B * 100, device="cuda")
+tfill = timeit(lambda: z.fill_(1.0))
+print(json.dumps(dict(fill_GBs=z.numel() * 4 / tfill / 1e6)))

@@ -1,0 +1,154 @@
+"""End-to-end parity of the model mirror against the reference-equivalent composition of
+the torch oracle, with injected noise (SURVEY.md hard parts 3 and 7); the compiled-program
+`evaluate` path against the graph-path golden; the Mario path against its golden."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dense_path
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name + ".npz"))
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def build_mnist_model(device, query_per_row=False, dropout=None):
+    from vael_b200.mnist_task import build_model_dict, build_worlds_queries_matrix
+    from vael_b200.networks import MNISTPairsDecoder, MNISTPairsEncoder, MNISTPairsMLP
+    from vael_b200.vael import MNISTPairsVAELModel
+    torch.manual_seed(0)
+    enc = MNISTPairsEncoder(hidden_channels=64, latent_dim=23, dropout=0.0)
+    dec = MNISTPairsDecoder(label_dim=20, hidden_channels=64, latent_dim=8, dropout=0.0)
+    mlp = MNISTPairsMLP(in_features=15, n_facts=20)
+    model = MNISTPairsVAELModel(enc, dec, mlp, (15, 8), build_model_dict(2, 10), build_worlds_queries_matrix(2, 10).to(device),
+                                dropout=dropout, is_train=True, device=device, query_per_row=query_per_row)
+    return model.to(device)
+
+
+def reference_forward(model, x, labels, eps, gumbel, per_row):
+    """models/vael.py:39-70 composed from the oracle's dense restatement, on the CPU."""
+    enc, dec, mlp = model.encoder, model.decoder, model.mlp
+    mu, logvar = enc(x)
+    z = mu + torch.exp(logvar / 2) * eps
+    z_sub = z[:, 15:]
+    logits = torch.cat(mlp(z[:, :15]), 1)
+    facts = dense_path.facts_probability(logits)
+    w_q = dense_path.worlds_queries_matrix()
+    if per_row:
+        qp, worlds = dense_path.dense_inference_rows(facts, w_q, labels[:, -2])
+    else:
+        qp, worlds = dense_path.dense_inference(facts, w_q, int(labels[0][-2]))
+    world, _, _ = dense_path.gumbel_hard(torch.log(worlds), gumbel)
+    world_h = world @ dense_path.herbrand_base(20)
+    image = dec(torch.cat([z_sub, world_h], 1))
+    return image, mu, logvar, qp, facts, worlds
+
+
+@pytest.mark.parametrize("per_row", [False, True])
+def test_mnist_model_forward_backward_matches_reference_composition(cuda_device, per_row):
+    from vael_b200.train import loss_function
+    B = 32
+    model = build_mnist_model(cuda_device, query_per_row=per_row)
+    model.eval()  # dropout off (its RNG stream cannot match); is_train=True still samples z
+    gen = torch.Generator().manual_seed(7)
+    x = torch.randn(B, 1, 28, 56, generator=gen)
+    d = torch.randint(0, 10, (B, 2), generator=gen)
+    if not per_row:
+        d[:] = d[0]
+    labels = torch.cat([d, d.sum(1, keepdim=True), -torch.ones(B, 1, dtype=torch.long)], 1)
+    eps = torch.randn(B, 23, generator=gen)
+    gumbel = -torch.empty(B, 100).exponential_(generator=gen).log()
+
+    model.reparam_noise, model.gumbel_noise = eps.cuda(), gumbel.cuda()
+    image, mu, logvar, qp = model(x.cuda(), labels.cuda())
+    loss, rl, kl, qce, _ = loss_function(image, x.cuda(), mu, logvar, qp, labels=labels.cuda(), query=True,
+                                         recon_w=1e-1, kl_w=1e-5, query_w=1.0, sup_w=0.0, rec_loss="LAPLACE")
+    model.zero_grad()
+    loss.backward()
+    got = {n: p.grad.detach().cpu().clone() for n, p in model.named_parameters()}
+    got_out = [t.detach().cpu() for t in (image, mu, logvar, qp, model.facts_probs, model.worlds_prob)]
+    world_idx = model.world_idx.cpu()
+    assert torch.equal(model.world.argmax(1).cpu(), world_idx.long())
+
+    ref_model = build_mnist_model(torch.device("cpu"), query_per_row=per_row)
+    ref_model.load_state_dict({k: v.cpu() for k, v in model.state_dict().items()})
+    ref_model.eval()
+    ref_model.zero_grad()
+    r_image, r_mu, r_logvar, r_qp, r_facts, r_worlds = reference_forward(ref_model, x, labels, eps, gumbel, per_row)
+    r_loss, *_ = dense_path.elbo_terms(r_image, x, r_mu, r_logvar, r_qp, 1e-1, 1e-5, 1.0)
+    r_loss.backward()
+
+    for a, b, name in zip(got_out, (r_image, r_mu, r_logvar, r_qp, r_facts, r_worlds),
+                          ("image", "mu", "logvar", "query", "facts", "worlds")):
+        assert rel_err(a.numpy(), b.detach().numpy(), floor=1e-6) < 2e-4, name   # conv/linear: cuDNN vs CPU fp32
+    assert abs(loss.item() - r_loss.item()) < 1e-4 * abs(r_loss.item())
+    for n, p in ref_model.named_parameters():
+        ref = p.grad
+        assert rel_err(got[n].numpy(), ref.numpy(), floor=1e-3 * ref.abs().max().item() + 1e-9) < 2e-3, n
+
+
+def test_compiled_program_evaluate_matches_graph_path_golden(cuda_device):
+    """model_dict[mode][label].evaluate(semiring) + extract_* against the golden produced by the
+    reference's GraphSemiring / extract_* (query mode q=9, evidence mode e=7)."""
+    from vael_b200.logic import Constant, Term
+    g = load("graph_path")
+    model = build_mnist_model(cuda_device)
+    facts = cu(g["facts"])
+    model.update_semiring_weights(facts)
+    res = model.model_dict["query"][9].evaluate(semiring=model.semiring)
+    keys = [Term("digits")(Constant(j), Constant(k)) for j in range(10) for k in range(10)]
+    assert list(res.keys())[:100] == keys and str(list(res.keys())[-1]) == "addition(img,9)"
+    stacked = torch.stack([res[k] for k in keys], 1).cpu().numpy()
+    np.testing.assert_allclose(stacked, g["query_res_worlds"], rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(res[list(res.keys())[-1]].cpu().numpy(), g["query_res_last"], rtol=1e-5)
+    np.testing.assert_allclose(model.extract_query_probability(res).cpu().numpy(), g["extract_query"], rtol=1e-5)
+    np.testing.assert_allclose(model.extract_worlds_probability(res).cpu().numpy(), g["extract_worlds"], rtol=1e-5, atol=1e-12)
+    wp = model.problog_inference_with_evidence(facts, 7)
+    np.testing.assert_allclose(wp.cpu().numpy(), g["evidence_extract_worlds"], rtol=1e-5, atol=1e-12)
+    # the generic (base-class) query path, made real
+    from vael_b200.vael import VAELModel
+    qp, worlds = VAELModel.problog_inference(model, facts, labels=None, query=9)
+    np.testing.assert_allclose(qp.cpu().numpy(), g["extract_query"], rtol=1e-5)
+    np.testing.assert_allclose(worlds.cpu().numpy(), g["extract_worlds"], rtol=1e-5, atol=1e-12)
+
+
+def test_all_queries_matches_dense_mask_matmul(cuda_device):
+    g = load("mnist_dense")
+    model = build_mnist_model(cuda_device)
+    facts = cu(g["facts"])
+    allq = model.all_queries(facts).cpu().numpy()
+    ref = g["worlds_q9"] @ g["w_q"][:, :19]
+    np.testing.assert_allclose(allq, ref, rtol=1e-5)
+    for q in (0, 9, 18):
+        np.testing.assert_allclose(allq[:, q], g[f"query_q{q}"][:, 0], rtol=1e-5)
+
+
+def test_mario_logic_path_matches_reference_golden(cuda_device):
+    from vael_b200.networks import MarioMLP
+    from vael_b200.vael import MarioVAELModel
+    g = load("mario")
+    tabs = {n: cu(g[n].astype(np.float32)) for n in ("W_all", "WQ_all", "W_adm", "WQ_adm")}
+    m = MarioVAELModel(None, None, MarioMLP(18, 18, 32), (18, 30), None, tabs["WQ_all"], tabs["W_all"], tabs["WQ_adm"],
+                       tabs["W_adm"], (3, 3), device=cuda_device)
+    facts = cu(g["facts"]).requires_grad_(True)
+    worlds = m.compute_worlds_prob_conj(facts)
+    query = m.compute_query_prob(cu(g["moves"]), worlds)
+    adm = m.admissible_worlds_logprob(facts)
+    assert rel_err(worlds.detach().cpu().numpy(), g["worlds"]) < 1e-5
+    assert rel_err(query.detach().cpu().numpy(), g["query"]) < 1e-5
+    assert rel_err(adm.detach().cpu().numpy(), g["adm_logprob"]) < 1e-5
+    (gf,) = torch.autograd.grad((worlds * cu(g["gw"])).sum() + (query * cu(g["gq"])).sum() + (adm * cu(g["ga"])).sum(), [facts])
+    ref = g["grad_facts"]
+    assert rel_err(gf.cpu().numpy(), ref, floor=1e-3 * np.abs(ref).max()) < 1e-4
+    cond = m.compute_conditioned_worlds_prob(facts[:1].detach(), torch.tensor([0., 1., 0., 0.]))
+    np.testing.assert_allclose(cond.cpu().numpy(), g["cond_worlds"], rtol=1e-5)

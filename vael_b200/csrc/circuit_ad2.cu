@@ -89,7 +89,7 @@ __device__ __forceinline__ void load_mask(uint32_t* m, const Ad2Params& P, long 
 // ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
-template <int NA, int NB, bool NORM, bool EVID, int S, int SO>
+template <int NA, int NB, bool NORM, bool EVID, int S, int SO, bool STG = false>
 __global__ void __launch_bounds__(256) ad2_forward_kernel(const Ad2Params P) {
   using Sh = Ad2Shape<NA, NB>;
   constexpr int F = Sh::F, W = Sh::W, MW = Sh::MW, FV = Sh::FV, WV = Sh::WV;
@@ -225,7 +225,20 @@ __global__ void __launch_bounds__(256) ad2_forward_kernel(const Ad2Params P) {
       const uint32_t bytes = (uint32_t)rows * W * 4u;
       float* dst = P.worlds + row0 * W;
       const float* src = out_s + so * kWarp * W;
-      if (out_al && (bytes & 15u) == 0) {
+      if constexpr (STG) {
+        // experiment: drain the tile with coalesced 128-bit stores instead of the bulk engine
+        __syncwarp();
+        if (out_al && (bytes & 15u) == 0) {
+          const float4* s4 = reinterpret_cast<const float4*>(src);
+          float4* d4 = reinterpret_cast<float4*>(dst);
+          const int n4 = (int)(bytes >> 4);
+#pragma unroll 5
+          for (int i = lane; i < n4; i += kWarp) __stcs(d4 + i, s4[i]);
+        } else {
+          warp_copy(dst, src, rows * W, lane);
+        }
+        __syncwarp();
+      } else if (out_al && (bytes & 15u) == 0) {
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -404,27 +417,34 @@ static int env_int(const char* name, int dflt) {
   return atoi(v);
 }
 
-template <int NA, int NB, bool NORM, bool EVID>
-static cudaError_t launch_fwd_t(const Ad2Params& P, int num_sms, cudaStream_t st) {
-  constexpr int S = 2, SO = 2;
+template <int NA, int NB, bool NORM, bool EVID, int S, int SO, bool STG = false>
+static cudaError_t launch_fwd_cfg(const Ad2Params& P, int num_sms, cudaStream_t st) {
   using Sh = Ad2Shape<NA, NB>;
   constexpr int PER_WARP = S * Sh::FACT_BYTES + SO * Sh::OUT_BYTES + 128;
-  static int nw = 0, cps = 0;
-  if (nw == 0) {
-    int w = env_int("VAEL_AD2_FWD_WARPS", 7);
-    w = max(1, min(8, w));
-    while (w > 1 && w * PER_WARP > 227 * 1024) --w;
-    cps = max(1, min(8, env_int("VAEL_AD2_FWD_CTAS_PER_SM", (227 * 1024) / (w * PER_WARP + 1024))));
-    cudaError_t e = cudaFuncSetAttribute(ad2_forward_kernel<NA, NB, NORM, EVID, S, SO>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, w * PER_WARP);
-    if (e != cudaSuccess) return e;
-    nw = w;
-  }
+  int nw = max(1, min(8, env_int("VAEL_AD2_FWD_WARPS", 7)));
+  while (nw > 1 && nw * PER_WARP > 227 * 1024) --nw;
+  const int cps = max(1, min(8, env_int("VAEL_AD2_FWD_CTAS_PER_SM", (227 * 1024) / (nw * PER_WARP + 1024))));
+  cudaError_t e = cudaFuncSetAttribute(ad2_forward_kernel<NA, NB, NORM, EVID, S, SO, STG>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, nw * PER_WARP);
+  if (e != cudaSuccess) return e;
   const long long n_sub = (P.B + kWarp - 1) / kWarp;
   long long grid = (n_sub + nw - 1) / nw;
   grid = min(grid, (long long)num_sms * cps);
-  ad2_forward_kernel<NA, NB, NORM, EVID, S, SO><<<(unsigned)grid, nw * 32, nw * PER_WARP, st>>>(P);
+  ad2_forward_kernel<NA, NB, NORM, EVID, S, SO, STG><<<(unsigned)grid, nw * 32, nw * PER_WARP, st>>>(P);
   return cudaGetLastError();
+}
+
+template <int NA, int NB, bool NORM, bool EVID>
+static cudaError_t launch_fwd_t(const Ad2Params& P, int num_sms, cudaStream_t st) {
+  // pipeline depth (load stages S, store stages SO) — tunable for experiments, default 2/2
+  static const int cfg = env_int("VAEL_AD2_FWD_STAGES", 22);
+  if constexpr (!NORM && !EVID) {
+    if (cfg == 23) return launch_fwd_cfg<NA, NB, NORM, EVID, 2, 3>(P, num_sms, st);
+    if (cfg == 33) return launch_fwd_cfg<NA, NB, NORM, EVID, 3, 3>(P, num_sms, st);
+    if (cfg == 21) return launch_fwd_cfg<NA, NB, NORM, EVID, 2, 1, true>(P, num_sms, st);
+    if (cfg == 31) return launch_fwd_cfg<NA, NB, NORM, EVID, 3, 1, true>(P, num_sms, st);
+  }
+  return launch_fwd_cfg<NA, NB, NORM, EVID, 2, 2>(P, num_sms, st);
 }
 
 template <int NA, int NB, bool NORM>
@@ -432,17 +452,12 @@ static cudaError_t launch_bwd_t(const Ad2Params& P, int num_sms, cudaStream_t st
   constexpr int S = 2, SO = 2;
   using Sh = Ad2Shape<NA, NB>;
   constexpr int PER_WARP = S * (Sh::FACT_BYTES + Sh::OUT_BYTES) + SO * Sh::FACT_BYTES + 128;
-  static int nw = 0, cps = 0;
-  if (nw == 0) {
-    int w = env_int("VAEL_AD2_BWD_WARPS", 6);
-    w = max(1, min(8, w));
-    while (w > 1 && w * PER_WARP > 227 * 1024) --w;
-    cps = max(1, min(8, env_int("VAEL_AD2_BWD_CTAS_PER_SM", (227 * 1024) / (w * PER_WARP + 1024))));
-    cudaError_t e = cudaFuncSetAttribute(ad2_backward_kernel<NA, NB, NORM, S, SO>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, w * PER_WARP);
-    if (e != cudaSuccess) return e;
-    nw = w;
-  }
+  int nw = max(1, min(8, env_int("VAEL_AD2_BWD_WARPS", 6)));
+  while (nw > 1 && nw * PER_WARP > 227 * 1024) --nw;
+  const int cps = max(1, min(8, env_int("VAEL_AD2_BWD_CTAS_PER_SM", (227 * 1024) / (nw * PER_WARP + 1024))));
+  cudaError_t e = cudaFuncSetAttribute(ad2_backward_kernel<NA, NB, NORM, S, SO>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, nw * PER_WARP);
+  if (e != cudaSuccess) return e;
   const long long n_sub = (P.B + kWarp - 1) / kWarp;
   long long grid = (n_sub + nw - 1) / nw;
   grid = min(grid, (long long)num_sms * cps);

@@ -60,6 +60,12 @@ class DeviceCircuit:
         except Exception:
             pass
 
+    def __deepcopy__(self, memo):  # immutable and device-bound: share, never duplicate
+        return self
+
+    def __reduce__(self):
+        raise TypeError("DeviceCircuit holds a device handle and cannot be pickled; pickle the Circuit")
+
     # sizes
     @property
     def n_facts(self): return self.circuit.n_facts

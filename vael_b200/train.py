@@ -1,0 +1,89 @@
+"""Loss functions and the training step.
+
+loss_function / mario_loss_function keep the reference signatures and return values
+(utils/mnist_utils/train.py:13-51, utils/mario_utils/train.py:11-65); with the shipped
+configuration (rec_loss='LAPLACE', config.py:17,45) on CUDA tensors every term and its
+gradient comes from one pass of the ELBO kernel.  `train_step` is the body of the
+reference's batch loop (utils/mnist_utils/train.py:105-150) without its five per-step
+`.cpu()` synchronisations; under torch.distributed the encoder/decoder gradients are
+averaged by DistributedDataParallel (NCCL), the circuit has no parameters.
+"""
+from __future__ import annotations
+
+import torch
+
+from .ops import elbo_terms
+
+
+def _recon_other(x_recon, x, rec_loss):
+    if rec_loss == "BCE":
+        return torch.nn.functional.binary_cross_entropy(torch.flatten(x_recon), torch.flatten(x), reduction="mean")
+    if rec_loss == "MSE":
+        return torch.nn.functional.mse_loss(torch.flatten(x_recon), torch.flatten(x), reduction="mean")
+    raise ValueError("Unknown reconstruction loss! Valid input are 'BCE', 'LAPLACE', or 'MSE'")
+
+
+def _kl(mu, logvar):
+    return torch.mean(-0.5 * torch.sum(1.0 + logvar - mu.pow(2) - logvar.exp(), dim=1))
+
+
+def _qbce(p):
+    p = torch.flatten(p)
+    return torch.nn.functional.binary_cross_entropy(p, torch.ones_like(p), reduction="mean")
+
+
+def img_log_likelihood(recon, xs):
+    """log Laplace(xs | recon, 1) summed over (C,H,W) (utils/mnist_utils/train.py:54-55)."""
+    return (-0.6931471805599453 - (xs - recon).abs()).sum(dim=(1, 2, 3))
+
+
+def loss_function(x_recon, x, mu, logvar, add_prob, model=None, labels=None, query=True, recon_w=1, kl_w=1, query_w=1,
+                  sup_w=1, sup=False, rec_loss="MSE"):
+    """-> (loss, recon_loss, gauss_kl_div, query_cross_entropy, label_cross_entropy)"""
+    zero = torch.zeros(size=(), device=x_recon.device)
+    if sup:
+        raise NotImplementedError("digit supervision reads model.digits_probs, which no reference model defines "
+                                  "(utils/mnist_utils/train.py:35-43; sup_w=0 in config.py:28)")
+    if rec_loss == "LAPLACE" and x_recon.is_cuda:
+        loss, terms = elbo_terms(x_recon, x, mu, logvar, add_prob if query else None, recon_w, kl_w,
+                                 query_w if query else 0.0)
+        return loss, terms[1], terms[2], (terms[3] if query else zero), zero
+    recon_loss = -img_log_likelihood(x_recon, x).mean() if rec_loss == "LAPLACE" else _recon_other(x_recon, x, rec_loss)
+    kl = _kl(mu, logvar)
+    qce = _qbce(add_prob) if query else zero
+    return recon_w * recon_loss + kl_w * kl + query_w * qce + sup_w * zero, recon_loss, kl, qce, zero
+
+
+def mario_loss_function(x1, x_recon1, mu1, logvar1, x2, x_recon2, mu2, logvar2, query_prob, recon_w=1, kl_w=1,
+                        query_w=1, sup_w=1, sup=False, rec_loss="MSE"):
+    """-> dict(elbo, true_elbo, recon_loss1/2, gauss_kl_div1/2, queryBCE, labelBCE)"""
+    zero = torch.zeros(size=(), device=x_recon1.device)
+    if rec_loss == "LAPLACE" and x_recon1.is_cuda:
+        # frame 1 carries the query term, frame 2 only reconstruction + KL
+        l1, t1 = elbo_terms(x_recon1, x1, mu1, logvar1, query_prob, recon_w, kl_w, query_w)
+        l2, t2 = elbo_terms(x_recon2, x2, mu2, logvar2, None, recon_w, kl_w, 0.0)
+        r1, k1, qb, r2, k2 = t1[1], t1[2], t1[3], t2[1], t2[2]
+        elbo = l1 + l2
+    else:
+        if rec_loss == "LAPLACE":
+            r1, r2 = -img_log_likelihood(x_recon1, x1).mean(), -img_log_likelihood(x_recon2, x2).mean()
+        else:
+            r1, r2 = _recon_other(x_recon1, x1, rec_loss), _recon_other(x_recon2, x2, rec_loss)
+        k1, k2, qb = _kl(mu1, logvar1), _kl(mu2, logvar2), _qbce(query_prob)
+        elbo = recon_w * (r1 + r2) + kl_w * (k1 + k2) + query_w * qb + sup_w * zero
+    true_elbo = (r1 + r2 + k1 + k2 + qb + zero).detach()
+    return {"elbo": elbo, "true_elbo": true_elbo, "recon_loss1": r1, "recon_loss2": r2, "gauss_kl_div1": k1,
+            "gauss_kl_div2": k2, "queryBCE": qb, "labelBCE": zero}
+
+
+def train_step(model, optimizer, data, labels, recon_w=1e-1, kl_w=1e-5, query_w=1.0, rec_loss="LAPLACE"):
+    """One optimisation step on a [B,1,28,56] batch; returns the detached [4] term vector
+    (loss, recon, kl, qbce) on the device — no host synchronisation."""
+    optimizer.zero_grad(set_to_none=True)
+    recon, mu, logvar, add_prob = model(data, labels)
+    loss, rl, kl, qce, _ = loss_function(recon, data, mu, logvar, add_prob, labels=labels, query=True,
+                                         recon_w=recon_w, kl_w=kl_w, query_w=query_w, sup_w=0.0, sup=False,
+                                         rec_loss=rec_loss)
+    loss.backward()
+    optimizer.step()
+    return torch.stack([loss.detach(), rl.detach(), kl.detach(), qce.detach()])
