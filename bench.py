@@ -183,9 +183,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the vael_b200 path has no CPU fallback "
                          "(use --impl reference for the CPU baseline)")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from vael_b200 import parallel
+    world, rank, local = parallel.env_world()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     distributed = world > 1
@@ -198,16 +197,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        t = torch.tensor([x], device=dev, dtype=torch.float64)
-        if distributed:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return parallel.max_over_ranks(x, dev)
 
     lib = _lib.load()
     fam = compile_addition_family(2, 10)
     dc = DeviceCircuit(fam.circuit, dev)
     B, K, W = args.rows, max(1, args.steps), max(3, args.warmup)
-    facts, g = synthetic_facts(B, dev, 1234 + rank)
+    facts, g = synthetic_facts(B, dev, parallel.rank_seed(1234, rank))
     qidx = torch.randint(0, 19, (B,), device=dev, dtype=torch.int32, generator=g)
     gw = torch.randn(B, 100, device=dev, generator=g)
     gq = torch.randn(B, device=dev, generator=g)
@@ -304,7 +300,10 @@ def run_ours(args):
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(dom["name"])
+            # per-launch dram__bytes_read.sum + dram__bytes_write.sum of the same kernel from the committed
+            # `ncu --set full` capture (profiles/*_ncu.md); only quoted when that capture used this row count
+            t = json.load(open(tpath)).get(dom["name"]) or {}
+            traffic = t.get("bytes") if t.get("rows") == B else None
         line = {
             "metric": "circuit_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

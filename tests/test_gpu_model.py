@@ -57,6 +57,10 @@ def reference_forward(model, x, labels, eps, gumbel, per_row):
 @pytest.mark.parametrize("per_row", [False, True])
 def test_mnist_model_forward_backward_matches_reference_composition(cuda_device, per_row):
     from vael_b200.train import loss_function
+    # the CNNs run through cuDNN/cuBLAS here and through the CPU kernels in the reference arm:
+    # keep them in true fp32 so that the comparison is about the logic path
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     B = 32
     model = build_mnist_model(cuda_device, query_per_row=per_row)
     model.eval()  # dropout off (its RNG stream cannot match); is_train=True still samples z
@@ -90,7 +94,9 @@ def test_mnist_model_forward_backward_matches_reference_composition(cuda_device,
 
     for a, b, name in zip(got_out, (r_image, r_mu, r_logvar, r_qp, r_facts, r_worlds),
                           ("image", "mu", "logvar", "query", "facts", "worlds")):
-        assert rel_err(a.numpy(), b.detach().numpy(), floor=1e-6) < 2e-4, name   # conv/linear: cuDNN vs CPU fp32
+        b = b.detach().numpy()
+        err = rel_err(a.numpy(), b, floor=1e-3 * float(np.abs(b).max()) + 1e-9)
+        assert err < 2e-4, (name, err)   # conv/linear: cuDNN vs CPU fp32
     assert abs(loss.item() - r_loss.item()) < 1e-4 * abs(r_loss.item())
     for n, p in ref_model.named_parameters():
         ref = p.grad

@@ -1,0 +1,221 @@
+"""CPU tests of the host side: the circuit compiler against its bit-exact golden and against the
+reference's own tables (w_q, Herbrand base, the four Mario .pt tables), the GraphSemiring mirror
+against the reference op tables, and the C-ABI library (loads, exports every symbol the header
+declares, rejects bad descriptions before touching CUDA).  No compute entry point is called."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+ARRAYS = ("node_kind", "node_arg", "level_ptr", "child_ptr", "child_idx", "const_val", "world_node", "query_node")
+
+
+def load(name):
+    return np.load(os.path.join(G, name + ".npz"), allow_pickle=False)
+
+
+# ---------------------------------------------------------------------------
+# compiler
+# ---------------------------------------------------------------------------
+def test_two_digit_circuit_arrays_bit_exact_against_golden(addition_family):
+    g, c = load("circuit_addition_2digit"), addition_family.circuit
+    for k in ARRAYS:
+        a = getattr(c, k)
+        assert a.dtype == g[k].dtype and np.array_equal(a, g[k]), k
+    assert int(g["n_facts"]) == c.n_facts == 20 and int(g["norm_node"]) == c.norm_node
+    assert list(g["fact_labels"]) == list(c.fact_labels)
+    assert list(g["world_atoms"]) == list(c.world_atoms) and list(g["query_atoms"]) == list(c.query_atoms)
+    assert str(load("graph_path")["circuit_sha256"]) == c.sha256()
+    c.validate()
+
+
+def test_world_indexing_and_query_table_match_reference(addition_family):
+    """World w = d1*10+d2 (models/vael.py:218-221,255-258); the circuit's world->query membership is the
+    reference's build_worlds_queries_matrix (mnist_task_VAEL.py:222-234); fact columns are p_1y then p_2y."""
+    from vael_b200.mnist_task import build_worlds_queries_matrix
+    c, g = addition_family.circuit, load("mnist_dense")
+    assert list(c.world_atoms) == [f"digits({j},{k})" for j in range(10) for k in range(10)]
+    assert list(c.query_atoms) == [f"addition(img,{s})" for s in range(19)]
+    assert list(c.fact_labels) == [f"p_{p}{d}" for p in (1, 2) for d in range(10)]
+    wq_ref = g["w_q"]
+    assert np.array_equal(c.worlds_queries_matrix(), wq_ref[:, :19])
+    assert np.array_equal(build_worlds_queries_matrix(2, 10).numpy(), wq_ref)
+    # world node (j,k) is the product of the literals p_1j and p_2k
+    for w in (0, 7, 42, 99):
+        ch = c.children(int(c.world_node[w]))
+        assert [int(c.node_arg[n]) for n in ch] == [w // 10, 10 + w % 10]
+    # query members are listed in world order (the kernels add them in that order)
+    pos = {int(n): w for w, n in enumerate(c.world_node)}
+    for q in range(19):
+        n = int(c.query_node[q])
+        ws = [pos[int(x)] for x in c.children(n)] if int(c.node_kind[n]) == 4 else [pos[n]]
+        assert ws == sorted(ws) and ws == [w for w in range(100) if w // 10 + w % 10 == q]
+
+
+def test_program_family_views_and_text(addition_family):
+    """38 programs (2 modes x 19 sums, mnist_task_VAEL.py:208-217) share one circuit; the text follows
+    utils/mnist_utils/problog_model.py:27-54 (ADs, rules, digit query, then addition query | evidence)."""
+    fam = addition_family
+    assert len(fam.views) == 38
+    v = fam.views[("query", 9)]
+    assert v.mode == "query" and v.query_index == 9 and str(v.result_atoms[-1]) == "addition(img,9)"
+    assert "query(digits(X,Y))." in v.text and "query(addition(img,9))." in v.text
+    assert "addition(X,N) :- digit(X,1,N1), digit(X,2,N2), N is N1 + N2." in v.text
+    e = fam.views[("evidence", 7)]
+    assert e.mode == "evidence" and e.query_index == 7 and "evidence(addition(img,7))." in e.text
+    assert len(e.result_atoms) == 100
+    assert "0.1::digit" not in v.text and "p_10::digit(X,1,0)" in v.text and "p_29::digit(X,2,9)" in v.text
+
+
+def test_herbrand_base_matches_reference():
+    from vael_b200.networks import MNISTPairsMLP
+    from vael_b200.vael import MNISTPairsVAELModel
+    m = MNISTPairsVAELModel(None, None, MNISTPairsMLP(15, 20), (15, 8), None, None, device="cpu")
+    assert np.array_equal(m.herbrand_base.numpy(), load("mnist_dense")["herbrand"])
+    assert [str(t) for t in m.weights_dict] == [f"p_{p}{d}" for p in (1, 2) for d in range(10)]
+
+
+def test_three_digit_family_structure():
+    """The scaled program (BASELINE.json configs[4]): 3 ADs, 1000 worlds in mixed-radix order, sums 0..27."""
+    from vael_b200.mnist_task import compile_addition_family
+    c = compile_addition_family(3, 10).circuit
+    assert (c.n_facts, c.n_worlds, c.n_queries) == (30, 1000, 28)
+    assert list(c.world_atoms[:3]) == ["digits(0,0,0)", "digits(0,0,1)", "digits(0,0,2)"] and c.world_atoms[999] == "digits(9,9,9)"
+    wq = c.worlds_queries_matrix()
+    d = np.indices((10, 10, 10)).reshape(3, -1).sum(0)
+    assert np.array_equal(wq, (d[:, None] == np.arange(28)[None]).astype(wq.dtype))
+    c.validate()
+
+
+def test_mario_tables_regenerated_from_the_rule_program_bit_exact():
+    """utils/mario_utils/problog_matrices/3x3/{W_all,WQ_all,W_adm,WQ_adm}.pt regenerated by compiling the
+    move-rule program (utils/mario_utils/problog_model.py:3-62) must equal the reference files bit for bit."""
+    from vael_b200.mario_task import compile_mario_family, mario_tables
+    g = load("mario")
+    W_all, WQ_all, W_adm, WQ_adm = mario_tables(compile_mario_family((3, 3)))
+    for mine, name in ((W_all, "W_all"), (WQ_all, "WQ_all"), (W_adm, "W_adm"), (WQ_adm, "WQ_adm")):
+        assert mine.shape == g[name].shape and np.array_equal(mine.astype(np.int8), g[name]), name
+
+
+def test_circuit_serialisation_round_trip(tmp_path, addition_family):
+    from vael_b200.circuit import Circuit
+    c = addition_family.circuit
+    p = tmp_path / "c.npz"
+    c.save(p)
+    c2 = Circuit.load(p)
+    assert c2.sha256() == c.sha256() and c2.fnv1a64() == c.fnv1a64()
+    bad = Circuit.load(p)
+    bad.child_idx = bad.child_idx.copy()
+    bad.child_idx[-1] = bad.n_nodes - 1          # a child in its own level
+    with pytest.raises(ValueError):
+        bad.validate()
+
+
+def test_compiler_rejects_what_it_cannot_compile():
+    from vael_b200.compiler import CompileError, compile_family
+    with pytest.raises(CompileError):
+        compile_family({0: "a :- b.\nquery(a)."})                       # no probabilistic facts
+    with pytest.raises(CompileError):
+        compile_family({0: "p_1::a; p_2::b.\nevidence(a, false).\nquery(b)."})   # negative evidence
+
+
+# ---------------------------------------------------------------------------
+# GraphSemiring mirror (utils/graph_semiring.py:5-60) against the reference op tables
+# ---------------------------------------------------------------------------
+def test_graph_semiring_mirror_matches_reference_tables():
+    from vael_b200.graph_semiring import GraphSemiring
+    g = load("semiring_ops")
+    T = lambda k: torch.from_numpy(g[k])
+    s = GraphSemiring(batch_size=8, device=torch.device("cpu"))
+    assert s.eps == 1e-12 and s.batch_size == 8
+    cases = {"pp": ("a", "b_plain"), "pz": ("a", "b_zero"), "zp": ("a_zero", "b_plain"), "po": ("a", "b_one"),
+             "op": ("a_one", "b_plain")}
+    for tag, (x, y) in cases.items():
+        if f"plus_{tag}" in g.files:
+            assert torch.equal(s.plus(T(x), T(y)), T(f"plus_{tag}")), tag
+            assert torch.equal(s.times(T(x), T(y)), T(f"times_{tag}")), tag
+    assert torch.equal(s.negate(T("a")), T("negate_a"))
+    assert torch.equal(s.one(), T("one")) and torch.equal(s.zero(), T("zero"))
+    s.set_weights({"k": T("a")})
+    assert torch.equal(s.value("k"), T("value_hit")) and s.value(0.25) == 0.25
+    # the elementwise variant is what the kernels implement: no batch-wide shortcut
+    e = GraphSemiring(8, torch.device("cpu"), elementwise=True)
+    assert torch.equal(e.plus(T("a"), T("b_zero")), T("a") + T("b_zero"))
+
+
+def test_fact_matrix_recovers_the_contiguous_block_without_a_copy():
+    from vael_b200.graph_semiring import GraphSemiring
+    from vael_b200.logic import Term
+    facts = torch.rand(6, 2, 10, requires_grad=True)
+    fp = facts * 1.0
+    terms = [Term(f"p_{p}{d}") for p in (1, 2) for d in range(10)]
+    s = GraphSemiring(6)
+    s.set_weights({t: fp[:, i // 10, i % 10] for i, t in enumerate(terms)})   # models/vael.py:236-240
+    m = s.fact_matrix(terms)
+    assert m.shape == (6, 20) and m.data_ptr() == fp.data_ptr() and m.requires_grad
+    s.set_weights({t: torch.rand(6) for t in terms})
+    assert s.fact_matrix(terms).shape == (6, 20)
+    with pytest.raises(KeyError):
+        GraphSemiring(6).fact_matrix(terms)
+
+
+# ---------------------------------------------------------------------------
+# C-ABI library
+# ---------------------------------------------------------------------------
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "vael_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return re.findall(r"VAEL_API\s+[\w\s\*]+?\b(vael_\w+)\s*\(", text)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from vael_b200 import _lib
+    names = header_symbols()
+    assert len(names) >= 19 and len(set(names)) == len(names)
+    lib = _lib.load()
+    for n in names:
+        assert hasattr(lib, n), f"libvael_b200.so does not export {n}"
+    assert set(names) == set(_lib.EXPORTED_SYMBOLS), "ctypes prototypes and include/vael_b200.h disagree"
+    assert lib.vael_abi_version() == 1
+    assert lib.vael_elbo_workspace_bytes() > 0 and lib.vael_launch_count() >= 0
+
+
+def test_library_validates_descriptions_before_touching_cuda(addition_family):
+    from vael_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.vael_circuit_create(None, C.byref(h)) == 1 and b"null" in lib.vael_last_error()
+    c = addition_family.circuit
+    import copy
+    bad = copy.copy(c)
+    bad.child_idx = c.child_idx.copy()
+    bad.child_idx[-1] = c.n_nodes - 1
+    assert lib.vael_circuit_create(C.byref(_lib.make_desc(bad)), C.byref(h)) == 1
+    assert b"strictly lower level" in lib.vael_last_error()
+    bad2 = copy.copy(c)
+    bad2.world_node = c.world_node.copy()
+    bad2.world_node[3] = 10 ** 6
+    assert lib.vael_circuit_create(C.byref(_lib.make_desc(bad2)), C.byref(h)) == 1
+    assert lib.vael_circuit_fast_kind(None) == 0 and lib.vael_circuit_hash(None) == 0
+    lib.vael_circuit_destroy(None)
+
+
+def test_product_path_has_no_cpu_fallback(addition_family):
+    """CPU tensors are refused loudly; nothing under vael_b200/ imports the oracle."""
+    from vael_b200.ops import DeviceCircuit, facts_from_logits
+    with pytest.raises(RuntimeError, match="CPU|CUDA|cuda"):
+        facts_from_logits(torch.randn(4, 20), 2)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CUDA device"):
+            DeviceCircuit(addition_family.circuit)
+    pkg = os.path.join(ROOT, "vael_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

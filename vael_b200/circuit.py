@@ -68,19 +68,25 @@ class Circuit:
         return lv
 
     def validate(self) -> None:
-        assert self.level_ptr[0] == 0 and self.level_ptr[-1] == self.n_nodes
-        assert self.child_ptr[0] == 0 and self.child_ptr[-1] == self.n_edges
+        """Host-side twin of the checks vael_circuit_create makes; raises ValueError."""
+        def need(ok, msg):
+            if not ok:
+                raise ValueError(f"invalid circuit: {msg}")
+        need(self.level_ptr[0] == 0 and self.level_ptr[-1] == self.n_nodes, "level_ptr does not cover the nodes")
+        need(self.child_ptr[0] == 0 and self.child_ptr[-1] == self.n_edges, "child_ptr does not cover the edges")
         lv = self.level_of()
         for n in range(self.n_nodes):
             k = int(self.node_kind[n])
             ch = self.children(n)
             if k in (LEAF_POS, LEAF_NEG):
-                assert 0 <= self.node_arg[n] < self.n_facts and len(ch) == 0 and lv[n] == 0
+                need(0 <= self.node_arg[n] < self.n_facts and len(ch) == 0 and lv[n] == 0, f"bad leaf {n}")
             elif k == CONST:
-                assert 0 <= self.node_arg[n] < len(self.const_val) and len(ch) == 0
+                need(0 <= self.node_arg[n] < len(self.const_val) and len(ch) == 0, f"bad constant {n}")
             else:
-                assert k in (PROD, SUM, COMPL)
-                assert all(lv[c] < lv[n] for c in ch), "children must be in strictly lower levels"
+                need(k in (PROD, SUM, COMPL), f"unknown node kind {k}")
+                need(all(0 <= c < self.n_nodes and lv[c] < lv[n] for c in ch), "children must be in strictly lower levels")
+        need(all(0 <= w < self.n_nodes for w in self.world_node), "world node out of range")
+        need(all(0 <= q < self.n_nodes for q in self.query_node), "query node out of range")
 
     # ---- identity -----------------------------------------------------------
     def serialize(self) -> bytes:

@@ -555,7 +555,6 @@ extern "C" int vael_gumbel_world_backward(const float* scores, const float* y_so
   if (B < 0 || W <= 0 || W > 1024 || H <= 0 || !(tau > 0.0f)) return fail(VAEL_E_INVALID, "bad shape or tau");
   if (B == 0) return VAEL_OK;
   if (!y_soft || !grad_world_h || !herbrand || !grad_scores || (!is_log && !scores)) return fail(VAEL_E_INVALID, "null pointer");
-  if ((size_t)W * H * 4 > 48 * 1024) return fail(VAEL_E_UNSUPPORTED, "Herbrand table larger than 48 KB");
   int sms = 0;
   if (int rc = device_sms(&sms)) return rc;
   GumbelParams P{};

@@ -75,6 +75,7 @@ struct GumbelParams {
   float* world_h;         // [B,H]
   const float* grad_world_h;  // [B,H]
   float* grad_scores;         // [B,W]
+  int32_t hb_in_smem;         // set by the launcher: Herbrand table staged in shared memory
 };
 cudaError_t gumbel_forward(const GumbelParams& P, int num_sms, cudaStream_t st);
 cudaError_t gumbel_backward(const GumbelParams& P, int num_sms, cudaStream_t st);

@@ -98,9 +98,13 @@ __global__ void __launch_bounds__(256) gumbel_forward_kernel(const GumbelParams 
 
 template <int ITEMS>
 __global__ void __launch_bounds__(256) gumbel_backward_kernel(const GumbelParams P) {
-  extern __shared__ float hb[];  // [W][H] Herbrand table
-  for (int i = threadIdx.x; i < P.W * P.H; i += blockDim.x) hb[i] = __ldg(P.herbrand + i);
-  __syncthreads();
+  extern __shared__ float hb_s[];  // [W][H] Herbrand table (when it fits; else read through L1/L2)
+  const float* hb = P.herbrand;
+  if (P.hb_in_smem) {
+    for (int i = threadIdx.x; i < P.W * P.H; i += blockDim.x) hb_s[i] = __ldg(P.herbrand + i);
+    __syncthreads();
+    hb = hb_s;
+  }
   const int lane = threadIdx.x & 31;
   const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -165,21 +169,31 @@ cudaError_t gumbel_forward(const GumbelParams& P, int num_sms, cudaStream_t st) 
   return cudaGetLastError();
 }
 
+template <int ITEMS>
+static cudaError_t launch_gumbel_bwd(GumbelParams P, int grid, cudaStream_t st) {
+  size_t smem = (size_t)P.W * P.H * sizeof(float);
+  P.hb_in_smem = smem <= (size_t)200 * 1024;
+  if (!P.hb_in_smem) smem = 0;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(gumbel_backward_kernel<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  gumbel_backward_kernel<ITEMS><<<grid, 256, smem, st>>>(P);
+  return cudaGetLastError();
+}
+
 cudaError_t gumbel_backward(const GumbelParams& P, int num_sms, cudaStream_t st) {
   const int grid = launch_grid(P.B, num_sms);
-  const size_t smem = (size_t)P.W * P.H * sizeof(float);
-  if (smem > 48 * 1024) return cudaErrorInvalidValue;
   switch (pick_items(P.W)) {
-    case 1: gumbel_backward_kernel<1><<<grid, 256, smem, st>>>(P); break;
-    case 2: gumbel_backward_kernel<2><<<grid, 256, smem, st>>>(P); break;
-    case 3: gumbel_backward_kernel<3><<<grid, 256, smem, st>>>(P); break;
-    case 4: gumbel_backward_kernel<4><<<grid, 256, smem, st>>>(P); break;
-    case 8: gumbel_backward_kernel<8><<<grid, 256, smem, st>>>(P); break;
-    case 16: gumbel_backward_kernel<16><<<grid, 256, smem, st>>>(P); break;
-    case 32: gumbel_backward_kernel<32><<<grid, 256, smem, st>>>(P); break;
+    case 1: return launch_gumbel_bwd<1>(P, grid, st);
+    case 2: return launch_gumbel_bwd<2>(P, grid, st);
+    case 3: return launch_gumbel_bwd<3>(P, grid, st);
+    case 4: return launch_gumbel_bwd<4>(P, grid, st);
+    case 8: return launch_gumbel_bwd<8>(P, grid, st);
+    case 16: return launch_gumbel_bwd<16>(P, grid, st);
+    case 32: return launch_gumbel_bwd<32>(P, grid, st);
     default: return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------
