@@ -96,7 +96,7 @@ VAEL_API int vael_abi_version(void);
 VAEL_API const char* vael_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 VAEL_API int64_t vael_launch_count(void);
-/* name of the kernel family the last forward/backward used: "ad2-tma", "generic-csr" */
+/* name of the kernel family the last forward/backward used: "ad2-tma", "adw-tma2d", "generic-csr" */
 VAEL_API const char* vael_last_kernel(void);
 
 /* ---- circuit lifetime ---------------------------------------------------- */
@@ -107,7 +107,8 @@ VAEL_API const char* vael_last_kernel(void);
  * (utils/mnist_utils/mnist_task_VAEL.py:208-217).                            */
 VAEL_API int vael_circuit_create(const vael_circuit_desc_t* desc, vael_circuit_t** out);
 VAEL_API void vael_circuit_destroy(vael_circuit_t* c);
-/* 0 = generic CSR only, 2 = two-AD outer-product fast path available */
+/* 0 = generic CSR only; 2 / 3 = structured path for worlds that are the outer product of two / three
+ * annotated disjunctions (1-D bulk-copy tiles / 2-D tensor-map tiles) */
 VAEL_API int vael_circuit_fast_kind(const vael_circuit_t* c);
 /* 64-bit FNV-1a hash of the uploaded arrays (bit-exact circuit identity) */
 VAEL_API uint64_t vael_circuit_hash(const vael_circuit_t* c);

@@ -67,9 +67,9 @@ static void fnv(uint64_t& h, const void* data, size_t n) {
   for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
 }
 
-// Is `z` the ProbLog normaliser of two annotated disjunctions over fact columns [0,na) and
-// [na,na+nb):  PROD( SUM(leaves of AD a..., COMPL(leaves of AD a...)), SUM(... b ...) ) ?
-static bool norm_is_ad2(const vael_circuit_desc_t* d, int z, int na, int nb) {
+// Is `z` the ProbLog normaliser of K annotated disjunctions over the fact column ranges
+// [offs[a], offs[a]+sizes[a]):  PROD_a( SUM(leaves of AD a..., COMPL(leaves of AD a...)) ) ?
+static bool norm_is_adk(const vael_circuit_desc_t* d, int z, int K, const int* sizes, const int* offs) {
   auto kind = [&](int n) { return (int)d->node_kind[n]; };
   auto nch = [&](int n) { return d->child_ptr[n + 1] - d->child_ptr[n]; };
   auto ch = [&](int n, int i) { return d->child_idx[d->child_ptr[n] + i]; };
@@ -80,9 +80,8 @@ static bool norm_is_ad2(const vael_circuit_desc_t* d, int z, int na, int nb) {
     }
     return true;
   };
-  if (kind(z) != VAEL_NODE_PROD || nch(z) != 2) return false;
-  const int sizes[2] = {na, nb}, offs[2] = {0, na};
-  for (int a = 0; a < 2; ++a) {
+  if (kind(z) != VAEL_NODE_PROD || nch(z) != K) return false;
+  for (int a = 0; a < K; ++a) {
     const int s = ch(z, a);
     if (kind(s) != VAEL_NODE_SUM || nch(s) != sizes[a] + 1) return false;
     if (!leaves_are(s, 0, sizes[a], offs[a])) return false;
@@ -93,13 +92,39 @@ static bool norm_is_ad2(const vael_circuit_desc_t* d, int z, int na, int nb) {
   return true;
 }
 
+// Fact columns of the literals of a world node that is a left-deep product of positive literals,
+// PROD(PROD(PROD(l1, l2), l3), ...) — the order the kernels multiply in.  false if it is anything else.
+static bool world_literals(const vael_circuit_desc_t* d, int n, std::vector<int>& cols) {
+  auto kind = [&](int x) { return (int)d->node_kind[x]; };
+  auto nch = [&](int x) { return d->child_ptr[x + 1] - d->child_ptr[x]; };
+  auto ch = [&](int x, int i) { return d->child_idx[d->child_ptr[x] + i]; };
+  std::vector<int> rev;
+  int cur = n;
+  for (int depth = 0; depth < 16; ++depth) {
+    if (kind(cur) != VAEL_NODE_PROD || nch(cur) < 2) return false;
+    for (int e = nch(cur) - 1; e >= 1; --e) {
+      const int c = ch(cur, e);
+      if (kind(c) != VAEL_NODE_LEAF_POS) return false;
+      rev.push_back(d->node_arg[c]);
+    }
+    const int first = ch(cur, 0);
+    if (kind(first) == VAEL_NODE_LEAF_POS) {
+      rev.push_back(d->node_arg[first]);
+      cols.assign(rev.rbegin(), rev.rend());
+      return true;
+    }
+    cur = first;
+  }
+  return false;
+}
+
 extern "C" void vael_circuit_destroy(vael_circuit_t* c) {
   if (!c) return;
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(c->device);
   cudaFree(c->d_nodes); cudaFree(c->d_edges); cudaFree(c->d_world_node); cudaFree(c->d_query_node);
-  cudaFree(c->d_qmask); cudaFree(c->d_par_ptr); cudaFree(c->d_par_rec); cudaFree(c->d_bslot);
+  cudaFree(c->d_qmask); cudaFree(c->d_qmask_c); cudaFree(c->d_par_ptr); cudaFree(c->d_par_rec); cudaFree(c->d_bslot);
   cudaFree(c->d_fact_leaf_ptr); cudaFree(c->d_fact_leaf);
   for (auto& S : c->slot) {
     cudaFree(S.facts); cudaFree(S.worlds); cudaFree(S.query); cudaFree(S.gw); cudaFree(S.gq); cudaFree(S.gf);
@@ -292,36 +317,53 @@ extern "C" int vael_circuit_create(const vael_circuit_desc_t* d, vael_circuit_t*
     fl_ptr[f + 1] = (int32_t)fl.size();
   }
 
-  // structured fast path: worlds[i*nb+k] = PROD(LEAF_POS(i), LEAF_POS(na+k))
+  // structured fast paths: world w = left-deep product of one positive literal per annotated disjunction,
+  // worlds in mixed-radix order (first AD most significant), AD fact columns contiguous and in order
   c->fast_kind = 0;
+  std::vector<uint32_t> qmask_c;
   if (d->semiring == VAEL_SEMIRING_PROB && masks_ok && members_in_world_order && d->n_worlds > 0) {
-    int nb = 0;
-    bool ok = true;
-    auto leafcol = [&](int n) { return d->node_kind[n] == VAEL_NODE_LEAF_POS ? d->node_arg[n] : -1; };
+    std::vector<int> cols;
+    int K = 0, sizes[4] = {0, 0, 0, 0}, offs[4] = {0, 0, 0, 0};
+    bool ok = world_literals(d, d->world_node[0], cols) && cols.size() >= 2 && cols.size() <= 3 && cols[0] == 0;
+    if (ok) {
+      K = (int)cols.size();
+      long long prod = 1;
+      for (int k = 0; k < K; ++k) {
+        offs[k] = cols[k];
+        sizes[k] = (k + 1 < K ? cols[k + 1] : d->n_facts) - cols[k];
+        ok = ok && sizes[k] > 0;
+        prod *= sizes[k] > 0 ? sizes[k] : 1;
+      }
+      ok = ok && prod == d->n_worlds;
+    }
     for (int w = 0; w < d->n_worlds && ok; ++w) {
-      const int n = d->world_node[w];
-      if (d->node_kind[n] != VAEL_NODE_PROD || d->child_ptr[n + 1] - d->child_ptr[n] != 2) { ok = false; break; }
-      if (leafcol(d->child_idx[d->child_ptr[n]]) == 0) nb = w + 1; else break;
-    }
-    if (ok && nb > 0 && d->n_worlds % nb == 0) {
-      const int na = d->n_worlds / nb;
-      ok = (na + nb == d->n_facts);
-      for (int w = 0; w < d->n_worlds && ok; ++w) {
-        const int n = d->world_node[w];
-        if (d->node_kind[n] != VAEL_NODE_PROD || d->child_ptr[n + 1] - d->child_ptr[n] != 2) { ok = false; break; }
-        ok = leafcol(d->child_idx[d->child_ptr[n]]) == w / nb && leafcol(d->child_idx[d->child_ptr[n] + 1]) == na + w % nb;
-      }
-      if (ok && ad2_supported(na, nb)) {
-        c->fast_kind = 2; c->ad_na = na; c->ad_nb = nb;
-        c->norm_fast_ok = c->norm_node >= 0 && norm_is_ad2(d, c->norm_node, na, nb);
+      ok = world_literals(d, d->world_node[w], cols) && (int)cols.size() == K;
+      int rem = w;
+      for (int k = K - 1; k >= 0 && ok; --k) {
+        ok = cols[k] == offs[k] + rem % sizes[k];
+        rem /= sizes[k];
       }
     }
+    if (ok && K == 2 && ad2_supported(sizes[0], sizes[1])) {
+      c->fast_kind = 2; c->ad_na = sizes[0]; c->ad_nb = sizes[1];
+    } else if (ok && K == 3 && adw_supported(sizes[0], sizes[1], sizes[2])) {
+      c->fast_kind = 3; c->ad_np = sizes[0]; c->ad_na = sizes[1]; c->ad_nb = sizes[2];
+      // chunked masks: chunk i = worlds [i*C, (i+1)*C), bit (w % C) of its MWC words
+      const int C = sizes[1] * sizes[2], MWC = (C + 31) / 32;
+      qmask_c.assign((size_t)d->n_queries * sizes[0] * MWC, 0u);
+      for (int q = 0; q < d->n_queries; ++q)
+        for (int w = 0; w < d->n_worlds; ++w)
+          if ((qmask[(size_t)q * c->mask_words + (w >> 5)] >> (w & 31)) & 1u)
+            qmask_c[((size_t)q * sizes[0] + w / C) * MWC + ((w % C) >> 5)] |= 1u << ((w % C) & 31);
+    }
+    if (c->fast_kind) c->norm_fast_ok = c->norm_node >= 0 && norm_is_adk(d, c->norm_node, K, sizes, offs);
   }
 
   cudaError_t e = cudaSuccess;
   auto up = [&](auto** dp, const auto& v) { if (e == cudaSuccess) e = upload(dp, v); };
   up(&c->d_nodes, nodes); up(&c->d_edges, edges); up(&c->d_world_node, wn); up(&c->d_query_node, qn);
   if (masks_ok) up(&c->d_qmask, qmask);
+  if (!qmask_c.empty()) up(&c->d_qmask_c, qmask_c);
   up(&c->d_par_ptr, par_ptr); up(&c->d_par_rec, par_rec); up(&c->d_bslot, bslot);
   up(&c->d_fact_leaf_ptr, fl_ptr); up(&c->d_fact_leaf, fl);
   if (e != cudaSuccess) {
@@ -366,10 +408,13 @@ static int check_common(const vael_circuit_t* c, const float* facts, const int32
   return VAEL_OK;
 }
 
-static bool use_fast(const vael_circuit_t* c, uint32_t flags) {
-  if (c->fast_kind != 2 || (flags & VAEL_FLAG_FORCE_GENERIC)) return false;
-  if ((flags & VAEL_FLAG_NORMALIZE) && !c->norm_fast_ok) return false;
-  return true;
+// 0 = generic CSR kernel, 2 = ad2 (1-D bulk tiles), 3 = adw (2-D tensor-map tiles); `wide` is the [B,W] tensor
+// of the call, whose base address the tensor map needs 16-byte aligned
+static int pick_kernel(const vael_circuit_t* c, uint32_t flags, const float* wide) {
+  if (c->fast_kind == 0 || (flags & VAEL_FLAG_FORCE_GENERIC)) return 0;
+  if ((flags & VAEL_FLAG_NORMALIZE) && !c->norm_fast_ok) return 0;
+  if (c->fast_kind == 3 && !adw_usable(wide)) return 0;
+  return c->fast_kind;
 }
 
 extern "C" int vael_circuit_forward(const vael_circuit_t* c, const float* facts, const int32_t* qidx, int32_t qs,
@@ -378,12 +423,19 @@ extern "C" int vael_circuit_forward(const vael_circuit_t* c, const float* facts,
   if (int rc = check_common(c, facts, qidx, qs, B, flags, needq)) return rc;
   if (B == 0) return VAEL_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (use_fast(c, flags)) {
+  const int kern = pick_kernel(c, flags, worlds);
+  if (kern == 2) {
     Ad2Params P{};
     P.facts = facts; P.qidx = qidx; P.qscalar = needq ? qs : -1; P.n_queries = c->n_queries; P.qmask = c->d_qmask;
     P.B = B; P.worlds = worlds; P.query = query;
     CK(ad2_forward(c->ad_na, c->ad_nb, P, flags & VAEL_FLAG_NORMALIZE, flags & VAEL_FLAG_EVIDENCE, c->num_sms, st));
     g_last_kernel = "ad2-tma";
+  } else if (kern == 3) {
+    AdwParams P{};
+    P.facts = facts; P.qidx = qidx; P.qscalar = needq ? qs : -1; P.n_queries = c->n_queries; P.n_chunks = c->ad_np;
+    P.qmask_c = c->d_qmask_c; P.B = B; P.worlds = worlds; P.query = query;
+    CK(adw_forward(c->ad_np, c->ad_na, c->ad_nb, P, flags & VAEL_FLAG_NORMALIZE, flags & VAEL_FLAG_EVIDENCE, c->num_sms, st));
+    g_last_kernel = "adw-tma2d";
   } else {
     GenParams G;
     fill_gen(c, G);
@@ -421,12 +473,19 @@ extern "C" int vael_circuit_backward(const vael_circuit_t* c, const float* facts
   if (B == 0) return VAEL_OK;
   if (!grad_facts) return fail(VAEL_E_INVALID, "null grad_facts");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (use_fast(c, flags)) {
+  const int kern = pick_kernel(c, flags, grad_worlds);
+  if (kern == 2) {
     Ad2Params P{};
     P.facts = facts; P.qidx = qidx; P.qscalar = needq ? qs : -1; P.n_queries = c->n_queries; P.qmask = c->d_qmask;
     P.B = B; P.grad_worlds = grad_worlds; P.grad_query = grad_query; P.grad_facts = grad_facts;
     CK(ad2_backward(c->ad_na, c->ad_nb, P, flags & VAEL_FLAG_NORMALIZE, c->num_sms, st));
     g_last_kernel = "ad2-tma";
+  } else if (kern == 3) {
+    AdwParams P{};
+    P.facts = facts; P.qidx = qidx; P.qscalar = needq ? qs : -1; P.n_queries = c->n_queries; P.n_chunks = c->ad_np;
+    P.qmask_c = c->d_qmask_c; P.B = B; P.grad_worlds = grad_worlds; P.grad_query = grad_query; P.grad_facts = grad_facts;
+    CK(adw_backward(c->ad_np, c->ad_na, c->ad_nb, P, flags & VAEL_FLAG_NORMALIZE, c->num_sms, st));
+    g_last_kernel = "adw-tma2d";
   } else {
     GenParams G;
     fill_gen(c, G);

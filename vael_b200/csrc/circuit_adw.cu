@@ -1,0 +1,559 @@
+// Structured path for WIDE world levels: circuits whose worlds are the outer product of
+// three annotated disjunctions (3-digit MNIST addition: 10 x 10 x 10 = 1000 worlds, the
+// "scaled logic program" of BASELINE.json configs[4]) and whose query nodes are sums over
+// world nodes.
+//
+// Reference semantics: the k-digit generalisation of MNISTPairsVAELModel.problog_inference
+// (models/vael.py:200-225) == query-mode sdd.evaluate (models/vael.py:98-117); evidence mode ==
+// problog_inference_with_evidence (models/vael.py:119-135).  World w = (i*NA + j)*NB + k has the
+// value (p1[i] * p2[j]) * p3[k] — the left-deep product the compiled CSR holds.
+//
+// Execution model (sm_100a): warp-autonomous pipelines like circuit_ad2.cu, but a 32-row x
+// 1000-world tile is 128 KB, so the world level is swept in COLUMN CHUNKS of C = NA*NB worlds
+// (one chunk per value i of the leading AD).  A 32-row x C-column chunk of the row-major [B,W]
+// tensor is a strided box: it is moved by the TMA unit through a 2-D tensor map
+// (cp.async.bulk.tensor.2d, SASS UTMALDG / UTMASTG), rows beyond B clipped / zero-filled by
+// the hardware.  The [32,F] facts tile and the [32,F] grad_facts tile are contiguous and use
+// 1-D bulk copies.  Lane <-> batch row; shared-memory accesses are conflict-free 128-bit
+// (row stride C*4 = 400 B puts 8 consecutive lanes on 8 distinct 16-byte bank groups).
+#include <cuda.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "params.cuh"
+
+namespace vael {
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+template <int NP, int NA, int NB>
+struct AdwShape {
+  static constexpr int F = NP + NA + NB;
+  static constexpr int C = NA * NB;   // worlds per chunk
+  static constexpr int W = NP * C;
+  static constexpr int MWC = (C + 31) / 32;  // mask words per (query, chunk)
+  static constexpr int FV = (F % 4 == 0) ? 4 : ((F % 2 == 0) ? 2 : 1);
+  static constexpr int CV = (C % 4 == 0) ? 4 : ((C % 2 == 0) ? 2 : 1);
+  static constexpr int FACT_BYTES = ((kWarp * F * 4 + 127) / 128) * 128;
+  static constexpr int CH_BYTES = kWarp * C * 4;
+  static_assert(CH_BYTES % 128 == 0, "chunk tile must keep the stages 128-byte aligned");
+  static_assert((C * 4) % 16 == 0, "TMA box rows are multiples of 16 bytes");
+};
+
+template <int V>
+__device__ __forceinline__ void w_lds(float* dst, const float* src) {
+  if constexpr (V == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(src);
+    dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+  } else if constexpr (V == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(src);
+    dst[0] = t.x; dst[1] = t.y;
+  } else {
+    dst[0] = src[0];
+  }
+}
+template <int V>
+__device__ __forceinline__ void w_sts(float* dst, const float* src) {
+  if constexpr (V == 4) {
+    *reinterpret_cast<float4*>(dst) = make_float4(src[0], src[1], src[2], src[3]);
+  } else if constexpr (V == 2) {
+    *reinterpret_cast<float2*>(dst) = make_float2(src[0], src[1]);
+  } else {
+    dst[0] = src[0];
+  }
+}
+
+// normaliser Z = ((za * zb) * zc), z_g = sum(p_g) + (1 - sum(p_g)): ProbLog's WMC of the AD constraints
+template <int NP, int NA, int NB>
+__device__ __forceinline__ float adw_normaliser(const float* frow, const float* pa, const float* pb) {
+  float sp = frow[0];
+#pragma unroll 1
+  for (int i = 1; i < NP; ++i) sp = __fadd_rn(sp, frow[i]);
+  float sa = pa[0];
+#pragma unroll
+  for (int j = 1; j < NA; ++j) sa = __fadd_rn(sa, pa[j]);
+  float sb = pb[0];
+#pragma unroll
+  for (int k = 1; k < NB; ++k) sb = __fadd_rn(sb, pb[k]);
+  const float zp = __fadd_rn(sp, __fsub_rn(1.0f, sp));
+  const float za = __fadd_rn(sa, __fsub_rn(1.0f, sa));
+  const float zb = __fadd_rn(sb, __fsub_rn(1.0f, sb));
+  return __fmul_rn(__fmul_rn(zp, za), zb);
+}
+
+template <int MWC>
+__device__ __forceinline__ void load_chunk_mask(uint32_t* m, const AdwParams& P, int q, int chunk) {
+  if (q < 0) {
+#pragma unroll
+    for (int i = 0; i < MWC; ++i) m[i] = 0u;
+    return;
+  }
+  const uint32_t* src = P.qmask_c + ((long long)q * P.n_chunks + chunk) * MWC;
+  if constexpr (MWC == 4) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(src));
+    m[0] = t.x; m[1] = t.y; m[2] = t.z; m[3] = t.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < MWC; ++i) m[i] = __ldg(src + i);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------
+template <int NP, int NA, int NB, bool NORM, bool EVID, int S, int SO>
+__global__ void __launch_bounds__(256) adw_forward_kernel(const __grid_constant__ CUtensorMap tm_worlds,
+                                                          const AdwParams P) {
+  using Sh = AdwShape<NP, NA, NB>;
+  constexpr int F = Sh::F, C = Sh::C, MWC = Sh::MWC, FV = Sh::FV, CV = Sh::CV;
+  constexpr int PER_WARP = S * Sh::FACT_BYTES + SO * Sh::CH_BYTES + 128;
+  extern __shared__ __align__(128) uint8_t smem[];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  uint8_t* wbase = smem + (size_t)warp * PER_WARP;
+  uint8_t* out_base = wbase + S * Sh::FACT_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(out_base + SO * Sh::CH_BYTES);
+
+  const long long n_sub = (P.B + kWarp - 1) / kWarp;
+  const long long gw = (long long)blockIdx.x * nwarps + warp;
+  const long long GW = (long long)gridDim.x * nwarps;
+  if (gw >= n_sub) return;
+
+  const bool in_al = aligned16(P.facts);
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+
+  uint32_t phase = 0, via_tma = 0;
+  auto load_facts = [&](long long sub, int s) {
+    const long long row0 = sub * kWarp;
+    const int rows = (int)min((long long)kWarp, P.B - row0);
+    const uint32_t bytes = (uint32_t)rows * F * 4u;
+    float* dst = reinterpret_cast<float*>(wbase + s * Sh::FACT_BYTES);
+    const float* src = P.facts + row0 * F;
+    if (in_al && (bytes & 15u) == 0) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full[s], bytes);
+        bulk_g2s(dst, src, bytes, &full[s]);
+      }
+      via_tma |= 1u << s;
+    } else {
+      for (int i = lane; i < rows * F; i += kWarp) dst[i] = src[i];
+      via_tma &= ~(1u << s);
+    }
+  };
+
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const long long sub = gw + (long long)s * GW;
+    if (sub < n_sub) load_facts(sub, s);
+  }
+
+  long long it = 0;
+  long long nchunk = 0;  // chunks stored so far by this warp (selects the out stage)
+  for (long long sub = gw; sub < n_sub; sub += GW, ++it) {
+    const int s = (int)(it % S);
+    const long long row0 = sub * kWarp;
+    const int rows = (int)min((long long)kWarp, P.B - row0);
+    const long long row = row0 + lane;
+    const bool valid = lane < rows;
+
+    int q = -1;
+    if (valid) {
+      q = P.qidx ? __ldg(P.qidx + row) : P.qscalar;
+      if (q < 0 || q >= P.n_queries) q = -1;
+    }
+
+    if (via_tma & (1u << s)) {
+      mbar_wait(&full[s], (phase >> s) & 1u);
+      phase ^= 1u << s;
+    } else {
+      __syncwarp();
+    }
+
+    const float* frow = reinterpret_cast<const float*>(wbase + s * Sh::FACT_BYTES) + lane * F;
+    float pa[NA], pb[NB];
+    {
+      float tmp[F];  // only the [NP, F) part stays live
+#pragma unroll
+      for (int c = 0; c < F / FV; ++c) w_lds<FV>(tmp + c * FV, frow + c * FV);
+#pragma unroll
+      for (int j = 0; j < NA; ++j) pa[j] = tmp[NP + j];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) pb[k] = tmp[NP + NA + k];
+    }
+    float z = 1.0f;
+    if constexpr (NORM) z = adw_normaliser<NP, NA, NB>(frow, pa, pb);
+
+    float acc = 0.0f;  // value of the selected query node: sequential fp32 sum in world order
+    if constexpr (EVID) {
+#pragma unroll 1
+      for (int i = 0; i < NP; ++i) {
+        uint32_t m[MWC];
+        load_chunk_mask<MWC>(m, P, q, i);
+        const float pre = frow[i];
+#pragma unroll
+        for (int w = 0; w < C; ++w) {
+          const float v = __fmul_rn(__fmul_rn(pre, pa[w / NB]), pb[w % NB]);
+          if ((m[w >> 5] >> (w & 31)) & 1u) acc = __fadd_rn(acc, v);
+        }
+      }
+    }
+
+#pragma unroll 1
+    for (int i = 0; i < NP; ++i, ++nchunk) {
+      uint32_t m[MWC];
+      load_chunk_mask<MWC>(m, P, q, i);
+      const float pre = frow[i];
+      float t[NA];
+#pragma unroll
+      for (int j = 0; j < NA; ++j) t[j] = __fmul_rn(pre, pa[j]);
+
+      const int so = (int)(nchunk % SO);
+      float* orow = reinterpret_cast<float*>(out_base + so * Sh::CH_BYTES) + lane * C;
+      if (P.worlds != nullptr) {
+        // the tensor store issued SO chunks ago must have finished reading this stage
+        if (lane == 0) bulk_wait_read<SO - 1>();
+        __syncwarp();
+      }
+#pragma unroll
+      for (int c = 0; c < C / CV; ++c) {
+        float o[CV];
+#pragma unroll
+        for (int u = 0; u < CV; ++u) {
+          const int w = c * CV + u;
+          float v = __fmul_rn(t[w / NB], pb[w % NB]);
+          const bool member = (m[w >> 5] >> (w & 31)) & 1u;
+          if constexpr (EVID) {
+            v = member ? v / acc : 0.0f;  // P(w | e) = [w |= e] P(w) / P(e)
+          } else {
+            if (member) acc = __fadd_rn(acc, v);
+            if constexpr (NORM) v = v / z;
+          }
+          o[u] = v;
+        }
+        if (P.worlds != nullptr) w_sts<CV>(orow + c * CV, o);
+      }
+      if (P.worlds != nullptr) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tm_worlds, out_base + so * Sh::CH_BYTES, i * C, (int)row0);
+          bulk_commit();
+        }
+      }
+    }
+
+    if (P.query != nullptr && valid) {
+      float qv = acc;
+      if constexpr (NORM) qv = acc / z;
+      P.query[row] = qv;
+    }
+
+    // every lane is done with this facts stage: refill it with the tile S iterations ahead
+    __syncwarp();
+    {
+      const long long nxt = sub + (long long)S * GW;
+      if (nxt < n_sub) load_facts(nxt, s);
+    }
+  }
+  if (lane == 0) bulk_wait_all<0>();
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------
+// backward (adjoint); node values are recomputed from the facts
+// ---------------------------------------------------------------------------
+template <int NP, int NA, int NB, bool NORM, int S>
+__global__ void __launch_bounds__(256) adw_backward_kernel(const __grid_constant__ CUtensorMap tm_gw,
+                                                           const AdwParams P) {
+  using Sh = AdwShape<NP, NA, NB>;
+  constexpr int F = Sh::F, C = Sh::C, MWC = Sh::MWC, FV = Sh::FV, CV = Sh::CV;
+  constexpr int SF = 2, SG = 2;  // facts ring, grad_facts ring
+  constexpr int PER_WARP = S * Sh::CH_BYTES + (SF + SG) * Sh::FACT_BYTES + 128;
+  extern __shared__ __align__(128) uint8_t smem[];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  uint8_t* wbase = smem + (size_t)warp * PER_WARP;
+  uint8_t* fact_base = wbase + S * Sh::CH_BYTES;
+  uint8_t* gout_base = fact_base + SF * Sh::FACT_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(gout_base + SG * Sh::FACT_BYTES);  // [S] chunk stages
+  uint64_t* ffull = full + S;                                                      // [SF] facts stages
+
+  const long long n_sub = (P.B + kWarp - 1) / kWarp;
+  const long long gw = (long long)blockIdx.x * nwarps + warp;
+  const long long GW = (long long)gridDim.x * nwarps;
+  if (gw >= n_sub) return;
+
+  const bool has_gw = P.grad_worlds != nullptr;
+  const bool in_al = aligned16(P.facts);
+  const bool out_al = aligned16(P.grad_facts);
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+#pragma unroll
+    for (int s = 0; s < SF; ++s) mbar_init(&ffull[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+
+  uint32_t fphase = 0, fvia = 0;
+  auto load_facts = [&](long long sub, int fs) {
+    const long long row0 = sub * kWarp;
+    const int rows = (int)min((long long)kWarp, P.B - row0);
+    const uint32_t bytes = (uint32_t)rows * F * 4u;
+    float* dst = reinterpret_cast<float*>(fact_base + fs * Sh::FACT_BYTES);
+    const float* src = P.facts + row0 * F;
+    if (in_al && (bytes & 15u) == 0) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&ffull[fs], bytes);
+        bulk_g2s(dst, src, bytes, &ffull[fs]);
+      }
+      fvia |= 1u << fs;
+    } else {
+      for (int i = lane; i < rows * F; i += kWarp) dst[i] = src[i];
+      fvia &= ~(1u << fs);
+    }
+  };
+  // chunk n of this warp's sequence = (tile n / NP, leading-AD value n % NP)
+  auto issue_chunk = [&](long long n) {
+    const long long tt = n / NP;
+    const int ii = (int)(n - tt * NP);
+    const long long sub = gw + tt * GW;
+    if (sub >= n_sub) return;
+    if (ii == 0) load_facts(sub, (int)(tt % SF));
+    if (has_gw && lane == 0) {
+      const int s = (int)(n % S);
+      mbar_arrive_expect_tx(&full[s], (uint32_t)Sh::CH_BYTES);  // the box is always delivered whole (OOB rows = 0)
+      tma_load_2d(wbase + s * Sh::CH_BYTES, &tm_gw, ii * C, (int)(sub * kWarp), &full[s]);
+    }
+  };
+
+#pragma unroll 1
+  for (int n = 0; n < S; ++n) issue_chunk(n);
+
+  long long n = 0, tt = 0;
+  for (long long sub = gw; sub < n_sub; sub += GW, ++tt) {
+    const int fs = (int)(tt % SF), gs = (int)(tt % SG);
+    const long long row0 = sub * kWarp;
+    const int rows = (int)min((long long)kWarp, P.B - row0);
+    const long long row = row0 + lane;
+    const bool valid = lane < rows;
+
+    int q = -1;
+    float gq = 0.0f;
+    if (valid && P.grad_query != nullptr) {
+      q = P.qidx ? __ldg(P.qidx + row) : P.qscalar;
+      if (q < 0 || q >= P.n_queries) q = -1;
+      gq = __ldg(P.grad_query + row);
+    }
+
+    if (fvia & (1u << fs)) {
+      mbar_wait(&ffull[fs], (fphase >> fs) & 1u);
+      fphase ^= 1u << fs;
+    } else {
+      __syncwarp();
+    }
+    const float* frow = reinterpret_cast<const float*>(fact_base + fs * Sh::FACT_BYTES) + lane * F;
+    float pa[NA], pb[NB];
+    {
+      float tmp[F];
+#pragma unroll
+      for (int c = 0; c < F / FV; ++c) w_lds<FV>(tmp + c * FV, frow + c * FV);
+#pragma unroll
+      for (int j = 0; j < NA; ++j) pa[j] = tmp[NP + j];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) pb[k] = tmp[NP + NA + k];
+    }
+    float z = 1.0f;
+    if constexpr (NORM) z = adw_normaliser<NP, NA, NB>(frow, pa, pb);
+
+    // the bulk store of grad_facts issued SG tiles ago must have finished reading this stage
+    if (lane == 0) bulk_wait_read<SG - 1>();
+    __syncwarp();
+    float* grow_out = reinterpret_cast<float*>(gout_base + gs * Sh::FACT_BYTES) + lane * F;
+
+    float ga[NA], gb[NB];
+#pragma unroll
+    for (int j = 0; j < NA; ++j) ga[j] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) gb[k] = 0.0f;
+
+#pragma unroll 1
+    for (int i = 0; i < NP; ++i, ++n) {
+      const int s = (int)(n % S);
+      uint32_t m[MWC];
+      load_chunk_mask<MWC>(m, P, q, i);
+      const float pre = frow[i];
+      float u[NB], v[NA];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) u[k] = pre * pb[k];
+#pragma unroll
+      for (int j = 0; j < NA; ++j) v[j] = pre * pa[j];
+      if (has_gw) mbar_wait(&full[s], (uint32_t)((n / S) & 1));
+      const float* grow = reinterpret_cast<const float*>(wbase + s * Sh::CH_BYTES) + lane * C;
+      float si = 0.0f;
+#pragma unroll
+      for (int c = 0; c < C / CV; ++c) {
+        float a[CV];
+        if (has_gw) {
+          w_lds<CV>(a, grow + c * CV);
+        } else {
+#pragma unroll
+          for (int x = 0; x < CV; ++x) a[x] = 0.0f;
+        }
+#pragma unroll
+        for (int x = 0; x < CV; ++x) {
+          const int w = c * CV + x;
+          float av = a[x];
+          if ((m[w >> 5] >> (w & 31)) & 1u) av += gq;
+          if constexpr (NORM) av = av / z;  // Z's own adjoint is exactly 0
+          si = fmaf(av, pa[w / NB] * pb[w % NB], si);
+          ga[w / NB] = fmaf(av, u[w % NB], ga[w / NB]);
+          gb[w % NB] = fmaf(av, v[w / NB], gb[w % NB]);
+        }
+      }
+      grow_out[i] = si;
+      __syncwarp();          // every lane has read chunk stage s
+      issue_chunk(n + S);    // refill it (and, on a tile boundary, start the next facts tile)
+    }
+#pragma unroll
+    for (int j = 0; j < NA; ++j) grow_out[NP + j] = ga[j];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) grow_out[NP + NA + k] = gb[k];
+
+    {
+      const uint32_t bytes = (uint32_t)rows * F * 4u;
+      float* dst = P.grad_facts + row0 * F;
+      const float* src = reinterpret_cast<const float*>(gout_base + gs * Sh::FACT_BYTES);
+      if (out_al && (bytes & 15u) == 0) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          bulk_s2g(dst, src, bytes);
+          bulk_commit();
+        }
+      } else {
+        __syncwarp();
+        for (int i = lane; i < rows * F; i += kWarp) dst[i] = src[i];
+        if (lane == 0) bulk_commit();  // keep one group per tile so that wait_group.read<SG-1> counts tiles
+      }
+    }
+  }
+  if (lane == 0) bulk_wait_all<0>();
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static tmap_encode_fn tmap_encoder() {
+  static tmap_encode_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) == cudaSuccess &&
+        st == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<tmap_encode_fn>(p);
+  }
+  return fn;
+}
+
+// [B,W] fp32 row-major tensor, box = [32 rows, C columns]
+static bool make_map(CUtensorMap* map, const float* base, long long B, int W, int C) {
+  tmap_encode_fn enc = tmap_encoder();
+  if (!enc || !aligned16(base)) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)B};
+  const cuuint64_t strides[1] = {(cuuint64_t)W * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)C, (cuuint32_t)kWarp};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int adw_env(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+template <int NP, int NA, int NB, bool NORM, bool EVID>
+static cudaError_t launch_fwd(const AdwParams& P, int num_sms, cudaStream_t st) {
+  using Sh = AdwShape<NP, NA, NB>;
+  constexpr int S = 2, SO = 3;
+  constexpr int PER_WARP = S * Sh::FACT_BYTES + SO * Sh::CH_BYTES + 128;
+  alignas(64) CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (P.worlds != nullptr && !make_map(&map, P.worlds, P.B, Sh::W, Sh::C)) return cudaErrorNotSupported;
+  int nw = max(1, min(8, adw_env("VAEL_ADW_FWD_WARPS", 4)));
+  while (nw > 1 && nw * PER_WARP > 227 * 1024) --nw;
+  auto kern = adw_forward_kernel<NP, NA, NB, NORM, EVID, S, SO>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, nw * PER_WARP);
+  if (e != cudaSuccess) return e;
+  const long long n_sub = (P.B + kWarp - 1) / kWarp;
+  const long long grid = min((n_sub + nw - 1) / nw, (long long)num_sms);
+  kern<<<(unsigned)grid, nw * 32, nw * PER_WARP, st>>>(map, P);
+  return cudaGetLastError();
+}
+
+template <int NP, int NA, int NB, bool NORM>
+static cudaError_t launch_bwd(const AdwParams& P, int num_sms, cudaStream_t st) {
+  using Sh = AdwShape<NP, NA, NB>;
+  constexpr int S = 3;
+  constexpr int PER_WARP = S * Sh::CH_BYTES + 4 * Sh::FACT_BYTES + 128;
+  alignas(64) CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (P.grad_worlds != nullptr && !make_map(&map, P.grad_worlds, P.B, Sh::W, Sh::C)) return cudaErrorNotSupported;
+  int nw = max(1, min(8, adw_env("VAEL_ADW_BWD_WARPS", 4)));
+  while (nw > 1 && nw * PER_WARP > 227 * 1024) --nw;
+  auto kern = adw_backward_kernel<NP, NA, NB, NORM, S>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, nw * PER_WARP);
+  if (e != cudaSuccess) return e;
+  const long long n_sub = (P.B + kWarp - 1) / kWarp;
+  const long long grid = min((n_sub + nw - 1) / nw, (long long)num_sms);
+  kern<<<(unsigned)grid, nw * 32, nw * PER_WARP, st>>>(map, P);
+  return cudaGetLastError();
+}
+
+bool adw_supported(int np, int na, int nb) { return np == 10 && na == 10 && nb == 10; }
+
+// can this call go through the tensor-map path?  (16-byte aligned [B,W] base, driver entry point present)
+bool adw_usable(const float* wide_tensor) { return tmap_encoder() != nullptr && (wide_tensor == nullptr || aligned16(wide_tensor)); }
+
+cudaError_t adw_forward(int np, int na, int nb, const AdwParams& P, bool norm, bool evid, int num_sms,
+                        cudaStream_t st) {
+  if (!adw_supported(np, na, nb)) return cudaErrorInvalidValue;
+  if (evid) return norm ? launch_fwd<10, 10, 10, true, true>(P, num_sms, st) : launch_fwd<10, 10, 10, false, true>(P, num_sms, st);
+  return norm ? launch_fwd<10, 10, 10, true, false>(P, num_sms, st) : launch_fwd<10, 10, 10, false, false>(P, num_sms, st);
+}
+
+cudaError_t adw_backward(int np, int na, int nb, const AdwParams& P, bool norm, int num_sms, cudaStream_t st) {
+  if (!adw_supported(np, na, nb)) return cudaErrorInvalidValue;
+  return norm ? launch_bwd<10, 10, 10, true>(P, num_sms, st) : launch_bwd<10, 10, 10, false>(P, num_sms, st);
+}
+
+}  // namespace vael

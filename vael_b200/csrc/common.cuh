@@ -72,7 +72,7 @@ __device__ __forceinline__ void bulk_wait_all() {
 // order this thread's generic-proxy shared-memory writes before later async-proxy reads
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+__host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- host-side circuit handle ----------------------------------------------
 struct NodeDesc {  // one int4 per node, read with a single broadcast load
@@ -112,9 +112,10 @@ struct vael_circuit {
   int32_t* d_fact_leaf_ptr;  // [n_facts+1] leaf nodes per fact column
   int32_t* d_fact_leaf;      // leaf node ids
   // structured fast path
-  int fast_kind;             // 0 none, 2 = two annotated disjunctions (outer product)
-  int32_t ad_na, ad_nb;      // AD sizes; fact columns [0,na) and [na,na+nb)
-  bool norm_fast_ok;         // the normaliser node has the two-AD shape the fast path recomputes
+  int fast_kind;             // 0 none, 2 / 3 = worlds are the outer product of two / three annotated disjunctions
+  int32_t ad_np, ad_na, ad_nb;  // AD sizes (np = leading AD, only for fast_kind 3); fact columns in that order
+  bool norm_fast_ok;         // the normaliser node has the per-AD shape the fast paths recompute
+  uint32_t* d_qmask_c;       // fast_kind 3: [n_queries][np][ceil(na*nb/32)] chunked membership masks
   // host-buffer pipeline (allocated lazily by the *_host entry points)
   vael_host_slot slot[2];
   long long chunk_rows;

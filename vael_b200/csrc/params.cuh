@@ -24,6 +24,26 @@ bool ad2_supported(int na, int nb);
 cudaError_t ad2_forward(int na, int nb, const Ad2Params& P, bool norm, bool evid, int num_sms, cudaStream_t st);
 cudaError_t ad2_backward(int na, int nb, const Ad2Params& P, bool norm, int num_sms, cudaStream_t st);
 
+// ---- circuit_adw.cu (wide world levels: three annotated disjunctions, TMA 2-D tiles) ----
+struct AdwParams {
+  const float* facts;        // [B,F]
+  const int32_t* qidx;       // [B] or null
+  int32_t qscalar;
+  int32_t n_queries;
+  int32_t n_chunks;          // size of the leading AD = number of column chunks
+  const uint32_t* qmask_c;   // [Q][n_chunks][MWC] world membership of every query node, chunk by chunk
+  long long B;
+  float* worlds;             // [B,W] or null
+  float* query;              // [B] or null
+  const float* grad_worlds;  // [B,W] or null
+  const float* grad_query;   // [B] or null
+  float* grad_facts;         // [B,F]
+};
+bool adw_supported(int np, int na, int nb);
+bool adw_usable(const float* wide_tensor);
+cudaError_t adw_forward(int np, int na, int nb, const AdwParams& P, bool norm, bool evid, int num_sms, cudaStream_t st);
+cudaError_t adw_backward(int np, int na, int nb, const AdwParams& P, bool norm, int num_sms, cudaStream_t st);
+
 // ---- circuit_generic.cu ----------------------------------------------------
 constexpr int kMaxLevels = 24;
 struct GenParams {
