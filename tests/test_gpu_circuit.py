@@ -97,13 +97,26 @@ def test_backward(dc, addition_family, B, normalize, force_generic):
     assert rel_err(f2.grad.cpu().numpy(), g2, floor=1e-3 * np.abs(g2).max()) < 1e-4
 
 
-def test_queries_all(dc, addition_family):
+@pytest.mark.parametrize("normalize", [False, True])
+@pytest.mark.parametrize("B", [1, 33, 257, 5000])
+def test_queries_all(dc, addition_family, B, normalize):
+    """[B,19] = worlds @ w_q (utils/mnist_utils/metrics.py:71-75) from the fused kernel and from the
+    generic CSR kernel, both bit-exact against the CSR-order fp32 oracle."""
+    from vael_b200 import _lib
     from vael_b200.ops import circuit_queries_all
     circ = addition_family.circuit
-    facts = synthetic_facts(257, seed=3)
-    ref = fp_interp.queries_all(circ, facts)
-    out = circuit_queries_all(dc, torch.from_numpy(facts).cuda())
+    facts = synthetic_facts(B, seed=3 + B)
+    ref = fp_interp.queries_all(circ, facts, normalize=normalize)
+    f = torch.from_numpy(facts).cuda()
+    out = circuit_queries_all(dc, f, normalize=normalize)
+    assert _lib.last_kernel() == "ad2-queries"
     np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    out_g = circuit_queries_all(dc, f, normalize=normalize, force_generic=True)
+    assert _lib.last_kernel() == "generic-csr"
+    np.testing.assert_array_equal(out_g.cpu().numpy(), ref)
+    if not normalize:   # the reference's dense form: worlds @ w_q
+        w = (facts[:, :10, None] * facts[:, None, 10:]).reshape(B, 100).astype(np.float64)
+        np.testing.assert_allclose(out.cpu().numpy(), w @ circ.worlds_queries_matrix().astype(np.float64), rtol=1e-5)
 
 
 def test_empty_batch_and_errors(dc):

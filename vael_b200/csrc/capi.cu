@@ -124,7 +124,7 @@ extern "C" void vael_circuit_destroy(vael_circuit_t* c) {
   cudaGetDevice(&prev);
   cudaSetDevice(c->device);
   cudaFree(c->d_nodes); cudaFree(c->d_edges); cudaFree(c->d_world_node); cudaFree(c->d_query_node);
-  cudaFree(c->d_qmask); cudaFree(c->d_qmask_c); cudaFree(c->d_par_ptr); cudaFree(c->d_par_rec); cudaFree(c->d_bslot);
+  cudaFree(c->d_qmask); cudaFree(c->d_qm_ptr); cudaFree(c->d_qm_idx); cudaFree(c->d_qmask_c); cudaFree(c->d_par_ptr); cudaFree(c->d_par_rec); cudaFree(c->d_bslot);
   cudaFree(c->d_fact_leaf_ptr); cudaFree(c->d_fact_leaf);
   for (auto& S : c->slot) {
     cudaFree(S.facts); cudaFree(S.worlds); cudaFree(S.query); cudaFree(S.gw); cudaFree(S.gq); cudaFree(S.gf);
@@ -362,7 +362,17 @@ extern "C" int vael_circuit_create(const vael_circuit_desc_t* d, vael_circuit_t*
   cudaError_t e = cudaSuccess;
   auto up = [&](auto** dp, const auto& v) { if (e == cudaSuccess) e = upload(dp, v); };
   up(&c->d_nodes, nodes); up(&c->d_edges, edges); up(&c->d_world_node, wn); up(&c->d_query_node, qn);
-  if (masks_ok) up(&c->d_qmask, qmask);
+  if (masks_ok) {
+    up(&c->d_qmask, qmask);
+    std::vector<int32_t> qm_ptr(d->n_queries + 1, 0), qm_idx;
+    for (int q = 0; q < d->n_queries; ++q) {
+      for (int w = 0; w < d->n_worlds; ++w)
+        if ((qmask[(size_t)q * c->mask_words + (w >> 5)] >> (w & 31)) & 1u) qm_idx.push_back(w);
+      qm_ptr[q + 1] = (int32_t)qm_idx.size();
+    }
+    if (qm_idx.empty()) qm_idx.push_back(0);
+    up(&c->d_qm_ptr, qm_ptr); up(&c->d_qm_idx, qm_idx);
+  }
   if (!qmask_c.empty()) up(&c->d_qmask_c, qmask_c);
   up(&c->d_par_ptr, par_ptr); up(&c->d_par_rec, par_rec); up(&c->d_bslot, bslot);
   up(&c->d_fact_leaf_ptr, fl_ptr); up(&c->d_fact_leaf, fl);
@@ -454,6 +464,15 @@ extern "C" int vael_circuit_queries_all(const vael_circuit_t* c, const float* fa
   if (flags & VAEL_FLAG_EVIDENCE) return fail(VAEL_E_INVALID, "EVIDENCE is meaningless for queries_all");
   if (B == 0) return VAEL_OK;
   if (!queries_all) return fail(VAEL_E_INVALID, "null output");
+  if (pick_kernel(c, flags, nullptr) == 2 && c->n_queries <= 64) {
+    Ad2QParams P{};
+    P.facts = facts; P.B = B; P.n_queries = c->n_queries; P.qm_ptr = c->d_qm_ptr; P.qm_idx = c->d_qm_idx;
+    P.queries_all = queries_all;
+    CK(ad2_queries_all(c->ad_na, c->ad_nb, P, flags & VAEL_FLAG_NORMALIZE, c->num_sms, static_cast<cudaStream_t>(stream)));
+    g_last_kernel = "ad2-queries";
+    g_launches++;
+    return VAEL_OK;
+  }
   GenParams G;
   fill_gen(c, G);
   G.facts = facts; G.qscalar = -1; G.B = B; G.flags = flags; G.queries_all = queries_all;

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(256) ad2_forward_kernel(const Ad2Params P) {
 
   const bool in_al = aligned16(P.facts);
   const bool out_al = P.worlds != nullptr && aligned16(P.worlds);
+  const uint64_t pol = l2_policy_evict_first();
 
   if (lane == 0) {
 #pragma unroll
@@ -130,7 +131,8 @@ __global__ void __launch_bounds__(256) ad2_forward_kernel(const Ad2Params P) {
     if (in_al && (bytes & 15u) == 0) {
       if (lane == 0) {
         mbar_arrive_expect_tx(&full[s], bytes);
-        bulk_g2s(dst, src, bytes, &full[s]);
+        if (P.l2_hint >= 2) bulk_g2s_hint(dst, src, bytes, &full[s], pol);
+        else bulk_g2s(dst, src, bytes, &full[s]);
       }
       via_tma |= 1u << s;
     } else {
@@ -242,7 +244,8 @@ __global__ void __launch_bounds__(256) ad2_forward_kernel(const Ad2Params P) {
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          bulk_s2g(dst, src, bytes);
+          if (P.l2_hint >= 1) bulk_s2g_hint(dst, src, bytes, pol);
+          else bulk_s2g(dst, src, bytes);
           bulk_commit();
         }
       } else {
@@ -280,6 +283,7 @@ __global__ void __launch_bounds__(256) ad2_backward_kernel(const Ad2Params P) {
   const bool has_gw = P.grad_worlds != nullptr;
   const bool in_al = aligned16(P.facts) && (!has_gw || aligned16(P.grad_worlds));
   const bool out_al = aligned16(P.grad_facts);
+  const uint64_t pol = l2_policy_evict_first();
 
   if (lane == 0) {
 #pragma unroll
@@ -302,8 +306,13 @@ __global__ void __launch_bounds__(256) ad2_backward_kernel(const Ad2Params P) {
     if (in_al && ((fbytes | wbytes) & 15u) == 0) {
       if (lane == 0) {
         mbar_arrive_expect_tx(&full[s], fbytes + wbytes);
-        bulk_g2s(fdst, fsrc, fbytes, &full[s]);
-        if (has_gw) bulk_g2s(wdst, wsrc, wbytes, &full[s]);
+        if (P.l2_hint >= 2) {
+          bulk_g2s_hint(fdst, fsrc, fbytes, &full[s], pol);
+          if (has_gw) bulk_g2s_hint(wdst, wsrc, wbytes, &full[s], pol);
+        } else {
+          bulk_g2s(fdst, fsrc, fbytes, &full[s]);
+          if (has_gw) bulk_g2s(wdst, wsrc, wbytes, &full[s]);
+        }
       }
       via_tma |= 1u << s;
     } else {
@@ -395,7 +404,8 @@ __global__ void __launch_bounds__(256) ad2_backward_kernel(const Ad2Params P) {
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          bulk_s2g(dst, gdst_s, bytes);
+          if (P.l2_hint >= 1) bulk_s2g_hint(dst, gdst_s, bytes, pol);
+          else bulk_s2g(dst, gdst_s, bytes);
           bulk_commit();
         }
       } else {
@@ -409,6 +419,63 @@ __global__ void __launch_bounds__(256) ad2_backward_kernel(const Ad2Params P) {
 }
 
 // ---------------------------------------------------------------------------
+// all query nodes at once: queries_all[b, q] = sum over the member worlds of q, in world order
+// (the worlds[B,W] @ w_q[W,Q] mask contraction of utils/mnist_utils/metrics.py:71-75 and
+// compute_query, models/vael.py:200-206, fused after the product level: the worlds never leave the SM).
+// One warp per 32-row tile, lane <-> row; the W products of a row live in a shared-memory row
+// (written 128-bit, read back per member), the [32,Q] result tile is contiguous in global memory.
+// ---------------------------------------------------------------------------
+template <int NA, int NB, bool NORM>
+__global__ void __launch_bounds__(256) ad2_queries_kernel(const Ad2QParams P) {
+  using Sh = Ad2Shape<NA, NB>;
+  constexpr int F = Sh::F, W = Sh::W, FV = Sh::FV, WV = Sh::WV;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int Q = P.n_queries;
+  const int per_warp = Sh::FACT_BYTES + Sh::OUT_BYTES + ((kWarp * Q * 4 + 127) / 128) * 128;
+  float* fs = reinterpret_cast<float*>(smem + (size_t)warp * per_warp);
+  float* ws = reinterpret_cast<float*>(smem + (size_t)warp * per_warp + Sh::FACT_BYTES);
+  float* qs = reinterpret_cast<float*>(smem + (size_t)warp * per_warp + Sh::FACT_BYTES + Sh::OUT_BYTES);
+
+  const long long n_sub = (P.B + kWarp - 1) / kWarp;
+  const long long gw = (long long)blockIdx.x * nwarps + warp;
+  const long long GW = (long long)gridDim.x * nwarps;
+  for (long long sub = gw; sub < n_sub; sub += GW) {
+    const long long row0 = sub * kWarp;
+    const int rows = (int)min((long long)kWarp, P.B - row0);
+    __syncwarp();
+    {
+      const float* src = P.facts + row0 * F;
+      for (int i = lane; i < kWarp * F; i += kWarp) fs[i] = (i < rows * F) ? __ldg(src + i) : 0.5f;
+    }
+    __syncwarp();
+    float p[F];
+#pragma unroll
+    for (int c = 0; c < F / FV; ++c) lds_vec<FV>(p + c * FV, fs + lane * F + c * FV);
+    float z = 1.0f;
+    if constexpr (NORM) z = ad2_normaliser<NA, NB>(p);
+    float* wrow = ws + lane * W;
+#pragma unroll
+    for (int c = 0; c < W / WV; ++c) {
+      float o[WV];
+#pragma unroll
+      for (int u = 0; u < WV; ++u) o[u] = __fmul_rn(p[(c * WV + u) / NB], p[NA + ((c * WV + u) % NB)]);
+      sts_vec<WV>(wrow + c * WV, o);
+    }
+    for (int q = 0; q < Q; ++q) {
+      const int b = __ldg(P.qm_ptr + q), e = __ldg(P.qm_ptr + q + 1);
+      float acc = 0.0f;
+      for (int i = b; i < e; ++i) acc = __fadd_rn(acc, wrow[__ldg(P.qm_idx + i)]);
+      if constexpr (NORM) acc = acc / z;
+      qs[lane * Q + q] = acc;
+    }
+    __syncwarp();
+    float* dst = P.queries_all + row0 * Q;
+    for (int i = lane; i < rows * Q; i += kWarp) dst[i] = qs[i];
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
 static int env_int(const char* name, int dflt) {
@@ -416,12 +483,16 @@ static int env_int(const char* name, int dflt) {
   if (!v || !*v) return dflt;
   return atoi(v);
 }
+int l2_hint_env() {
+  static const int h = env_int("VAEL_L2_HINT", 0);
+  return h;
+}
 
 template <int NA, int NB, bool NORM, bool EVID, int S, int SO, bool STG = false>
 static cudaError_t launch_fwd_cfg(const Ad2Params& P, int num_sms, cudaStream_t st) {
   using Sh = Ad2Shape<NA, NB>;
   constexpr int PER_WARP = S * Sh::FACT_BYTES + SO * Sh::OUT_BYTES + 128;
-  int nw = max(1, min(8, env_int("VAEL_AD2_FWD_WARPS", 7)));
+  int nw = max(1, min(8, env_int("VAEL_AD2_FWD_WARPS", 5)));
   while (nw > 1 && nw * PER_WARP > 227 * 1024) --nw;
   const int cps = max(1, min(8, env_int("VAEL_AD2_FWD_CTAS_PER_SM", (227 * 1024) / (nw * PER_WARP + 1024))));
   cudaError_t e = cudaFuncSetAttribute(ad2_forward_kernel<NA, NB, NORM, EVID, S, SO, STG>,
@@ -430,7 +501,9 @@ static cudaError_t launch_fwd_cfg(const Ad2Params& P, int num_sms, cudaStream_t 
   const long long n_sub = (P.B + kWarp - 1) / kWarp;
   long long grid = (n_sub + nw - 1) / nw;
   grid = min(grid, (long long)num_sms * cps);
-  ad2_forward_kernel<NA, NB, NORM, EVID, S, SO, STG><<<(unsigned)grid, nw * 32, nw * PER_WARP, st>>>(P);
+  Ad2Params Q = P;
+  Q.l2_hint = l2_hint_env();
+  ad2_forward_kernel<NA, NB, NORM, EVID, S, SO, STG><<<(unsigned)grid, nw * 32, nw * PER_WARP, st>>>(Q);
   return cudaGetLastError();
 }
 
@@ -461,7 +534,9 @@ static cudaError_t launch_bwd_t(const Ad2Params& P, int num_sms, cudaStream_t st
   const long long n_sub = (P.B + kWarp - 1) / kWarp;
   long long grid = (n_sub + nw - 1) / nw;
   grid = min(grid, (long long)num_sms * cps);
-  ad2_backward_kernel<NA, NB, NORM, S, SO><<<(unsigned)grid, nw * 32, nw * PER_WARP, st>>>(P);
+  Ad2Params Q = P;
+  Q.l2_hint = l2_hint_env();
+  ad2_backward_kernel<NA, NB, NORM, S, SO><<<(unsigned)grid, nw * 32, nw * PER_WARP, st>>>(Q);
   return cudaGetLastError();
 }
 
@@ -469,6 +544,28 @@ template <int NA, int NB>
 static cudaError_t launch_fwd_shape(const Ad2Params& P, bool norm, bool evid, int num_sms, cudaStream_t st) {
   if (evid) return norm ? launch_fwd_t<NA, NB, true, true>(P, num_sms, st) : launch_fwd_t<NA, NB, false, true>(P, num_sms, st);
   return norm ? launch_fwd_t<NA, NB, true, false>(P, num_sms, st) : launch_fwd_t<NA, NB, false, false>(P, num_sms, st);
+}
+
+template <int NA, int NB>
+static cudaError_t launch_queries(const Ad2QParams& P, bool norm, int num_sms, cudaStream_t st) {
+  using Sh = Ad2Shape<NA, NB>;
+  const int per_warp = Sh::FACT_BYTES + Sh::OUT_BYTES + ((kWarp * P.n_queries * 4 + 127) / 128) * 128;
+  int nw = 8;
+  while (nw > 1 && nw * per_warp > 100 * 1024) --nw;  // two CTAs per SM
+  auto kern = norm ? ad2_queries_kernel<NA, NB, true> : ad2_queries_kernel<NA, NB, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, nw * per_warp);
+  if (e != cudaSuccess) return e;
+  const long long n_sub = (P.B + kWarp - 1) / kWarp;
+  const long long grid = min((n_sub + nw - 1) / nw, (long long)num_sms * 2);
+  kern<<<(unsigned)grid, nw * 32, nw * per_warp, st>>>(P);
+  return cudaGetLastError();
+}
+
+cudaError_t ad2_queries_all(int na, int nb, const Ad2QParams& P, bool norm, int num_sms, cudaStream_t st) {
+  if (P.n_queries > 64) return cudaErrorInvalidValue;
+  if (na == 10 && nb == 10) return launch_queries<10, 10>(P, norm, num_sms, st);
+  if (na == 9 && nb == 9) return launch_queries<9, 9>(P, norm, num_sms, st);
+  return cudaErrorInvalidValue;
 }
 
 bool ad2_supported(int na, int nb) { return (na == 10 && nb == 10) || (na == 9 && nb == 9); }

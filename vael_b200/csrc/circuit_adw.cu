@@ -30,6 +30,20 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, const void* smem_src, int c0, int c1,
+                                                  uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                                 uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -133,6 +147,7 @@ __global__ void __launch_bounds__(256) adw_forward_kernel(const __grid_constant_
   if (gw >= n_sub) return;
 
   const bool in_al = aligned16(P.facts);
+  const uint64_t pol = l2_policy_evict_first();
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
@@ -254,7 +269,8 @@ __global__ void __launch_bounds__(256) adw_forward_kernel(const __grid_constant_
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tm_worlds, out_base + so * Sh::CH_BYTES, i * C, (int)row0);
+          if (P.l2_hint >= 1) tma_store_2d_hint(&tm_worlds, out_base + so * Sh::CH_BYTES, i * C, (int)row0, pol);
+          else tma_store_2d(&tm_worlds, out_base + so * Sh::CH_BYTES, i * C, (int)row0);
           bulk_commit();
         }
       }
@@ -305,6 +321,7 @@ __global__ void __launch_bounds__(256) adw_backward_kernel(const __grid_constant
   const bool has_gw = P.grad_worlds != nullptr;
   const bool in_al = aligned16(P.facts);
   const bool out_al = aligned16(P.grad_facts);
+  const uint64_t pol = l2_policy_evict_first();
 
   if (lane == 0) {
 #pragma unroll
@@ -343,7 +360,8 @@ __global__ void __launch_bounds__(256) adw_backward_kernel(const __grid_constant
     if (has_gw && lane == 0) {
       const int s = (int)(n % S);
       mbar_arrive_expect_tx(&full[s], (uint32_t)Sh::CH_BYTES);  // the box is always delivered whole (OOB rows = 0)
-      tma_load_2d(wbase + s * Sh::CH_BYTES, &tm_gw, ii * C, (int)(sub * kWarp), &full[s]);
+      if (P.l2_hint >= 2) tma_load_2d_hint(wbase + s * Sh::CH_BYTES, &tm_gw, ii * C, (int)(sub * kWarp), &full[s], pol);
+      else tma_load_2d(wbase + s * Sh::CH_BYTES, &tm_gw, ii * C, (int)(sub * kWarp), &full[s]);
     }
   };
 
@@ -501,15 +519,16 @@ static int adw_env(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
-template <int NP, int NA, int NB, bool NORM, bool EVID>
-static cudaError_t launch_fwd(const AdwParams& P, int num_sms, cudaStream_t st) {
+template <int NP, int NA, int NB, bool NORM, bool EVID, int S, int SO>
+static cudaError_t launch_fwd_cfg(const AdwParams& P0, int num_sms, cudaStream_t st) {
   using Sh = AdwShape<NP, NA, NB>;
-  constexpr int S = 2, SO = 3;
   constexpr int PER_WARP = S * Sh::FACT_BYTES + SO * Sh::CH_BYTES + 128;
+  AdwParams P = P0;
+  P.l2_hint = l2_hint_env();
   alignas(64) CUtensorMap map;
   memset(&map, 0, sizeof(map));
   if (P.worlds != nullptr && !make_map(&map, P.worlds, P.B, Sh::W, Sh::C)) return cudaErrorNotSupported;
-  int nw = max(1, min(8, adw_env("VAEL_ADW_FWD_WARPS", 4)));
+  int nw = max(1, min(8, adw_env("VAEL_ADW_FWD_WARPS", 3)));
   while (nw > 1 && nw * PER_WARP > 227 * 1024) --nw;
   auto kern = adw_forward_kernel<NP, NA, NB, NORM, EVID, S, SO>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, nw * PER_WARP);
@@ -520,15 +539,26 @@ static cudaError_t launch_fwd(const AdwParams& P, int num_sms, cudaStream_t st) 
   return cudaGetLastError();
 }
 
-template <int NP, int NA, int NB, bool NORM>
-static cudaError_t launch_bwd(const AdwParams& P, int num_sms, cudaStream_t st) {
+template <int NP, int NA, int NB, bool NORM, bool EVID>
+static cudaError_t launch_fwd(const AdwParams& P, int num_sms, cudaStream_t st) {
+  static const int cfg = adw_env("VAEL_ADW_FWD_STAGES", 23);  // <load stages><store stages>
+  if constexpr (!NORM && !EVID) {
+    if (cfg == 22) return launch_fwd_cfg<NP, NA, NB, NORM, EVID, 2, 2>(P, num_sms, st);
+    if (cfg == 24) return launch_fwd_cfg<NP, NA, NB, NORM, EVID, 2, 4>(P, num_sms, st);
+  }
+  return launch_fwd_cfg<NP, NA, NB, NORM, EVID, 2, 3>(P, num_sms, st);
+}
+
+template <int NP, int NA, int NB, bool NORM, int S>
+static cudaError_t launch_bwd_cfg(const AdwParams& P0, int num_sms, cudaStream_t st) {
   using Sh = AdwShape<NP, NA, NB>;
-  constexpr int S = 3;
   constexpr int PER_WARP = S * Sh::CH_BYTES + 4 * Sh::FACT_BYTES + 128;
+  AdwParams P = P0;
+  P.l2_hint = l2_hint_env();
   alignas(64) CUtensorMap map;
   memset(&map, 0, sizeof(map));
   if (P.grad_worlds != nullptr && !make_map(&map, P.grad_worlds, P.B, Sh::W, Sh::C)) return cudaErrorNotSupported;
-  int nw = max(1, min(8, adw_env("VAEL_ADW_BWD_WARPS", 4)));
+  int nw = max(1, min(8, adw_env("VAEL_ADW_BWD_WARPS", (227 * 1024 - 1024) / PER_WARP)));
   while (nw > 1 && nw * PER_WARP > 227 * 1024) --nw;
   auto kern = adw_backward_kernel<NP, NA, NB, NORM, S>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, nw * PER_WARP);
@@ -537,6 +567,16 @@ static cudaError_t launch_bwd(const AdwParams& P, int num_sms, cudaStream_t st) 
   const long long grid = min((n_sub + nw - 1) / nw, (long long)num_sms);
   kern<<<(unsigned)grid, nw * 32, nw * PER_WARP, st>>>(map, P);
   return cudaGetLastError();
+}
+
+template <int NP, int NA, int NB, bool NORM>
+static cudaError_t launch_bwd(const AdwParams& P, int num_sms, cudaStream_t st) {
+  static const int cfg = adw_env("VAEL_ADW_BWD_STAGES", 3);
+  if constexpr (!NORM) {
+    if (cfg == 2) return launch_bwd_cfg<NP, NA, NB, NORM, 2>(P, num_sms, st);
+    if (cfg == 4) return launch_bwd_cfg<NP, NA, NB, NORM, 4>(P, num_sms, st);
+  }
+  return launch_bwd_cfg<NP, NA, NB, NORM, 3>(P, num_sms, st);
 }
 
 bool adw_supported(int np, int na, int nb) { return np == 10 && na == 10 && nb == 10; }

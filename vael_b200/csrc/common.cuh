@@ -59,6 +59,25 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
                "r"(smem_u32(smem_src)), "r"(bytes)
                : "memory");
 }
+// same copies carrying an L2 eviction-priority hint (streaming data: evict_first)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                              uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void* gmem_dst, const void* smem_src, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gmem_dst),
+               "r"(smem_u32(smem_src)), "r"(bytes), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most N of this thread's bulk groups still READ their shared-memory source
 template <int N>
@@ -115,6 +134,8 @@ struct vael_circuit {
   int fast_kind;             // 0 none, 2 / 3 = worlds are the outer product of two / three annotated disjunctions
   int32_t ad_np, ad_na, ad_nb;  // AD sizes (np = leading AD, only for fast_kind 3); fact columns in that order
   bool norm_fast_ok;         // the normaliser node has the per-AD shape the fast paths recompute
+  int32_t* d_qm_ptr;         // [n_queries+1] member worlds of every query node (CSR, world order) — set with d_qmask
+  int32_t* d_qm_idx;
   uint32_t* d_qmask_c;       // fast_kind 3: [n_queries][np][ceil(na*nb/32)] chunked membership masks
   // host-buffer pipeline (allocated lazily by the *_host entry points)
   vael_host_slot slot[2];

@@ -19,8 +19,19 @@ struct Ad2Params {
   const float* grad_worlds;  // [B,W] or null
   const float* grad_query;   // [B] or null
   float* grad_facts;         // [B,F]
+  int32_t l2_hint;           // 0 none, 1 = evict_first on the streaming stores, 2 = on loads and stores
 };
+struct Ad2QParams {           // all query nodes at once
+  const float* facts;         // [B,F]
+  long long B;
+  int32_t n_queries;
+  const int32_t* qm_ptr;      // [Q+1] CSR of the member worlds of every query node, in world order
+  const int32_t* qm_idx;
+  float* queries_all;         // [B,Q]
+};
+cudaError_t ad2_queries_all(int na, int nb, const Ad2QParams& P, bool norm, int num_sms, cudaStream_t st);
 bool ad2_supported(int na, int nb);
+int l2_hint_env();  // VAEL_L2_HINT (experiments)
 cudaError_t ad2_forward(int na, int nb, const Ad2Params& P, bool norm, bool evid, int num_sms, cudaStream_t st);
 cudaError_t ad2_backward(int na, int nb, const Ad2Params& P, bool norm, int num_sms, cudaStream_t st);
 
@@ -38,6 +49,7 @@ struct AdwParams {
   const float* grad_worlds;  // [B,W] or null
   const float* grad_query;   // [B] or null
   float* grad_facts;         // [B,F]
+  int32_t l2_hint;           // as Ad2Params
 };
 bool adw_supported(int np, int na, int nb);
 bool adw_usable(const float* wide_tensor);

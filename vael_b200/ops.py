@@ -141,14 +141,16 @@ def circuit_forward(dc: DeviceCircuit, facts: torch.Tensor, query=None, *, norma
     return (worlds if want_worlds else None), (q if want_query else None)
 
 
-def circuit_queries_all(dc: DeviceCircuit, facts: torch.Tensor, *, normalize: bool = False) -> torch.Tensor:
+def circuit_queries_all(dc: DeviceCircuit, facts: torch.Tensor, *, normalize: bool = False,
+                        force_generic: bool = False) -> torch.Tensor:
     """[B,Q] values of every query node (the worlds @ w_q contraction of
     utils/mnist_utils/metrics.py:71-75).  Evaluation-only."""
     f2 = _require_cuda_f32(facts.detach(), "facts").reshape(facts.shape[0], dc.n_facts)
     out = torch.empty((f2.shape[0], dc.n_queries), device=f2.device, dtype=torch.float32)
     with torch.cuda.device(f2.device):
         _lib.check(dc.lib.vael_circuit_queries_all(dc.handle, _p(f2), f2.shape[0], _p(out),
-                                                   FLAG_NORMALIZE if normalize else 0, _stream_ptr()))
+                                                   (FLAG_NORMALIZE if normalize else 0) |
+                                                   (FLAG_FORCE_GENERIC if force_generic else 0), _stream_ptr()))
     return out
 
 
