@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--wide-rows", type=int, default=1 << 20, help="rows per GPU of the 3-digit (W=1000) probe")
     return ap.parse_args()
 
 
@@ -85,6 +87,66 @@ def cpu_reference_rate(rows, steps, warmup):
         times.append(time.perf_counter() - t0)
     dt = sum(times) / len(times)
     return rows * EVALS_PER_ROW / dt, dt
+
+
+def cpu_extras():
+    """The other CPU legs SURVEY.md §8(d) asks to be timed beside the GPU numbers (small, bounded):
+    (ii) the reference's GRAPH path — the GraphSemiring port (batch-wide shortcuts, host-side identity
+    vectors and all) driven node by node over the compiled circuit, one evaluate() = 101 queries;
+    (iii) a reference-equivalent full VAEL train step (CNNs + dense logic + ELBO + Adam) at B = 32."""
+    from oracle import dense_path, graph_path
+    from oracle.semiring_port import SemiringPort
+    from vael_b200.mnist_task import compile_addition_family
+    from vael_b200.networks import MNISTPairsDecoder, MNISTPairsEncoder, MNISTPairsMLP
+    out = {}
+    circ = compile_addition_family(2, 10).circuit
+    for B in (32, 4096):
+        facts, _ = synthetic_facts(B, "cpu", 7)
+        facts = facts.reshape(B, 2, 10)
+
+        def evaluate():
+            sr = SemiringPort(batch_size=B)
+            sr.set_weights(graph_path.bind_weights(facts, circ.fact_labels))
+            return graph_path.evaluate(circ, sr, mode="query", query_index=9)
+
+        evaluate()
+        n = 3
+        t0 = time.perf_counter()
+        for _ in range(n):
+            evaluate()
+        dt = (time.perf_counter() - t0) / n
+        out[f"graph_path_B{B}"] = {"ms_per_evaluate": dt * 1e3, "evals_per_sec": B * EVALS_PER_ROW / dt,
+                                   "what": "GraphSemiring port driven over the CSR circuit, forward only"}
+    torch.manual_seed(0)
+    enc, dec, mlp = (MNISTPairsEncoder(hidden_channels=64, latent_dim=23), MNISTPairsDecoder(label_dim=20, hidden_channels=64, latent_dim=8),
+                     MNISTPairsMLP(in_features=15, n_facts=20))
+    params = [p for m in (enc, dec, mlp) for p in m.parameters()]
+    opt = torch.optim.Adam(params, lr=1e-3)
+    B = 32
+    x = torch.randn(B, 1, 28, 56)
+    w_q, hb = dense_path.worlds_queries_matrix(), dense_path.herbrand_base(20)
+
+    def step():
+        opt.zero_grad()
+        mu, logvar = enc(x)
+        z = mu + torch.exp(logvar / 2) * torch.randn(B, 23)
+        facts = dense_path.facts_probability(torch.cat(mlp(z[:, :15]), 1))
+        qp, worlds = dense_path.dense_inference(facts, w_q, 9)
+        world = torch.nn.functional.gumbel_softmax(torch.log(worlds), tau=1, hard=True)
+        image = dec(torch.cat([z[:, 15:], world @ hb], 1))
+        loss, *_ = dense_path.elbo_terms(image, x, mu, logvar, qp, 1e-1, 1e-5, 1.0)
+        loss.backward()
+        opt.step()
+
+    for _ in range(2):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        step()
+    dt = (time.perf_counter() - t0) / 5
+    out["train_step_B32"] = {"ms_per_step": dt * 1e3, "samples_per_sec": B / dt,
+                             "what": "reference-equivalent MNIST VAEL train step on the host cores (torch CPU)"}
+    return out
 
 
 def run_reference(args):
@@ -278,6 +340,14 @@ def run_ours(args):
         except Exception as exc:  # the probe must never cost the headline line
             train = {"error": repr(exc)[:200]}
 
+    # ---- secondary workloads (same kernels' siblings; informational, never the headline) ---------------------
+    secondary = None
+    if not args.no_secondary:
+        try:
+            secondary = secondary_probe(args, dev, rank, world, barrier, max_over_ranks, lib)
+        except Exception as exc:
+            secondary = {"error": repr(exc)[:200]}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -285,6 +355,10 @@ def run_ours(args):
         cpu = {"value": rate, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{args.cpu_rows} rows/step x 8 steps ({dt * 1e3:.0f} ms/step), torch CPU fp32 port of "
                          f"models/vael.py:208-225 + autograd, os.cpu_count()={os.cpu_count()}"}
+        try:
+            cpu["also"] = cpu_extras()
+        except Exception as exc:
+            cpu["also"] = {"error": repr(exc)[:200]}
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -317,49 +391,136 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": B * dom["bytes_per_row"]},
             "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu, "train": train,
+            "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()
 
 
+def _time_pair(fwd, bwd, n, barrier, max_over_ranks):
+    for _ in range(3):
+        fwd(); bwd()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * n + 1)]
+    ev[0].record()
+    for k in range(n):
+        fwd(); ev[2 * k + 1].record()
+        bwd(); ev[2 * k + 2].record()
+    barrier()
+    f = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(n)) / n
+    b = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(n)) / n
+    return max_over_ranks(f), max_over_ranks(b)
+
+
+def secondary_probe(args, dev, rank, world, barrier, max_over_ranks, lib):
+    """configs[4] (3-digit addition, W = 1000: the wide-level TMA 2-D kernels), the generic level-by-level
+    CSR kernel on the 2-digit circuit, and the fused all-queries kernel; per-GPU rows fixed (weak scaling)."""
+    from vael_b200 import _lib, parallel
+    from vael_b200.mnist_task import compile_addition_family
+    from vael_b200.ops import DeviceCircuit, _p
+    sp = torch.cuda.current_stream().cuda_stream
+    peak_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peak_path))["hbm_gbs"]) if os.path.exists(peak_path) else 6650.0
+    out = {}
+
+    # -- 3-digit addition: F=30, W=1000, Q=28 -> fwd 4128 B/row, bwd 4248 B/row, 1001 evals/row
+    B = args.wide_rows
+    dc3 = DeviceCircuit(compile_addition_family(3, 10).circuit, dev)
+    g = torch.Generator(device=dev).manual_seed(parallel.rank_seed(4321, rank))
+    p = torch.softmax(3.0 * torch.randn(B, 3, 10, device=dev, generator=g), -1) + 1e-5
+    facts = (p / p.sum(-1, keepdim=True)).reshape(B, 30).contiguous()
+    qidx = torch.randint(0, 28, (B,), device=dev, dtype=torch.int32, generator=g)
+    gw = torch.randn(B, 1000, device=dev, generator=g); gq = torch.randn(B, device=dev, generator=g)
+    worlds = torch.empty(B, 1000, device=dev); query = torch.empty(B, device=dev); gf = torch.empty(B, 30, device=dev)
+    f_ms, b_ms = _time_pair(
+        lambda: _lib.check(lib.vael_circuit_forward(dc3.handle, _p(facts), _p(qidx), -1, B, _p(worlds), _p(query), 0, sp)),
+        lambda: _lib.check(lib.vael_circuit_backward(dc3.handle, _p(facts), _p(qidx), -1, B, _p(gw), _p(gq), _p(gf), 0, sp)),
+        10, barrier, max_over_ranks)
+    out["addition_3digit"] = {
+        "workload": "3digit-addition compiled circuit (F=30, W=1000, Q=28), fwd+bwd, per-row query, fp32",
+        "rows_per_gpu": B, "kernel_family": _lib.last_kernel(), "evals_per_sec": world * B * 1001 / ((f_ms + b_ms) * 1e-3),
+        "fwd": {"ms": f_ms, "bytes_per_row": 4128, "GBs": B * 4128 / f_ms / 1e6, "frac": B * 4128 / f_ms / 1e6 / peak},
+        "bwd": {"ms": b_ms, "bytes_per_row": 4248, "GBs": B * 4248 / b_ms / 1e6, "frac": B * 4248 / b_ms / 1e6 / peak}}
+    del worlds, gw, facts, p
+    torch.cuda.empty_cache()
+
+    # -- generic level-by-level CSR kernel (VAEL_FLAG_FORCE_GENERIC) and all-queries on the 2-digit circuit
+    B2 = 1 << 21
+    dc2 = DeviceCircuit(compile_addition_family(2, 10).circuit, dev)
+    facts2, g2 = synthetic_facts(B2, dev, parallel.rank_seed(99, rank))
+    q2 = torch.randint(0, 19, (B2,), device=dev, dtype=torch.int32, generator=g2)
+    gw2 = torch.randn(B2, 100, device=dev, generator=g2); gq2 = torch.randn(B2, device=dev, generator=g2)
+    w2 = torch.empty(B2, 100, device=dev); qo2 = torch.empty(B2, device=dev); gf2 = torch.empty(B2, 20, device=dev)
+    f_ms, b_ms = _time_pair(
+        lambda: _lib.check(lib.vael_circuit_forward(dc2.handle, _p(facts2), _p(q2), -1, B2, _p(w2), _p(qo2), 4, sp)),
+        lambda: _lib.check(lib.vael_circuit_backward(dc2.handle, _p(facts2), _p(q2), -1, B2, _p(gw2), _p(gq2), _p(gf2), 4, sp)),
+        10, barrier, max_over_ranks)
+    out["generic_csr_2digit"] = {
+        "workload": "2-digit circuit through the generic level-ordered CSR kernels", "rows_per_gpu": B2,
+        "fwd": {"ms": f_ms, "GBs": B2 * FWD_BYTES / f_ms / 1e6, "frac": B2 * FWD_BYTES / f_ms / 1e6 / peak},
+        "bwd": {"ms": b_ms, "GBs": B2 * BWD_BYTES / b_ms / 1e6, "frac": B2 * BWD_BYTES / b_ms / 1e6 / peak}}
+    qa = torch.empty(B2, 19, device=dev)
+    a_ms, _ = _time_pair(lambda: _lib.check(lib.vael_circuit_queries_all(dc2.handle, _p(facts2), B2, _p(qa), 0, sp)),
+                         lambda: None, 10, barrier, max_over_ranks)
+    out["all_queries_2digit"] = {"workload": "all 19 sums per row (worlds @ w_q fused, worlds not materialised)",
+                                 "rows_per_gpu": B2, "kernel_family": _lib.last_kernel(), "ms": a_ms,
+                                 "bytes_per_row": 80 + 76, "GBs": B2 * 156 / a_ms / 1e6,
+                                 "rows_per_sec": world * B2 / (a_ms * 1e-3)}
+    return out
+
+
 def train_probe(args, dev, rank, world, distributed, barrier, max_over_ranks):
-    """VAEL train samples/s (BASELINE.json configs[1]: 2digit-MNIST addition, batch 4096 per GPU,
-    DDP): encoder/decoder in PyTorch, the logic path on the vael_b200 kernels, Adam, NCCL all-reduce."""
+    """VAEL train samples/s: BASELINE.json configs[1] (2digit-MNIST addition, batch 4096 per GPU, DDP when
+    N > 1) and configs[0] (the B = 32 reference configuration): encoder/decoder in PyTorch, the logic path
+    on the vael_b200 kernels, Adam; the whole step is one CUDA graph at N = 1, DDP/NCCL eager at N > 1."""
     from vael_b200.mnist_task import build_model_dict, build_worlds_queries_matrix
     from vael_b200.networks import MNISTPairsDecoder, MNISTPairsEncoder, MNISTPairsMLP
-    from vael_b200.train import train_step
+    from vael_b200.train import GraphedTrainStep, train_step
     from vael_b200.vael import MNISTPairsVAELModel
-    torch.manual_seed(0)
-    Bt = args.train_batch
-    model = MNISTPairsVAELModel(MNISTPairsEncoder(hidden_channels=64, latent_dim=23),
-                                MNISTPairsDecoder(label_dim=20, hidden_channels=64, latent_dim=8),
-                                MNISTPairsMLP(in_features=15, n_facts=20), (15, 8), build_model_dict(2, 10, device=dev),
-                                build_worlds_queries_matrix(2, 10).to(dev), dropout=0.5, is_train=True, device=dev,
-                                query_per_row=True).to(dev)
-    step_model = model
-    if distributed:
-        step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index])
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    x = torch.randn(Bt, 1, 28, 56, device=dev, generator=g)
-    d = torch.randint(0, 10, (Bt, 2), device=dev, generator=g)
-    labels = torch.cat([d, d.sum(1, keepdim=True), -torch.ones(Bt, 1, dtype=torch.long, device=dev)], 1)
-    for _ in range(5):
-        train_step(step_model, opt, x, labels)
-    barrier()
-    n = 20
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n):
-        terms = train_step(step_model, opt, x, labels)
-    e1.record()
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1)) / n
-    return {"metric": "vael_train_samples_per_sec", "value": world * Bt / (ms * 1e-3), "unit": "samples/s",
-            "ms_per_step": ms, "global_batch": world * Bt, "loss": float(terms[0].item()),
-            "config": "2digit-MNIST addition VAEL, synthetic 28x56 images, random-init weights, Adam, "
-                      + ("DDP/NCCL" if distributed else "single GPU")}
+    from vael_b200 import parallel
+    model_dict = build_model_dict(2, 10, device=dev)
+    w_q = build_worlds_queries_matrix(2, 10).to(dev)
+
+    def run(Bt, graphed, n):
+        torch.manual_seed(0)
+        model = MNISTPairsVAELModel(MNISTPairsEncoder(hidden_channels=64, latent_dim=23),
+                                    MNISTPairsDecoder(label_dim=20, hidden_channels=64, latent_dim=8),
+                                    MNISTPairsMLP(in_features=15, n_facts=20), (15, 8), model_dict, w_q, dropout=0.5,
+                                    is_train=True, device=dev, query_per_row=True).to(dev)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=graphed)
+        g = torch.Generator(device=dev).manual_seed(parallel.rank_seed(1234, rank))
+        x = torch.randn(Bt, 1, 28, 56, device=dev, generator=g)
+        d = torch.randint(0, 10, (Bt, 2), device=dev, generator=g)
+        labels = torch.cat([d, d.sum(1, keepdim=True), -torch.ones(Bt, 1, dtype=torch.long, device=dev)], 1)
+        if graphed:
+            stepper = GraphedTrainStep(model, opt, tuple(x.shape), tuple(labels.shape), device=dev)
+            step = lambda: stepper(x, labels)
+        else:
+            step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index]) if distributed else model
+            step = lambda: train_step(step_model, opt, x, labels)
+        for _ in range(5):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            terms = step()
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / n
+        return {"value": world * Bt / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "global_batch": world * Bt,
+                "loss": float(terms[0].item()), "mode": "cuda-graph" if graphed else ("ddp-nccl eager" if distributed else "eager")}
+
+    out = {"metric": "vael_train_samples_per_sec",
+           "config": "2digit-MNIST addition VAEL, synthetic 28x56 images, random-init weights, Adam, fp32 "
+                     "(cuDNN TF32 convolutions as in stock PyTorch)"}
+    main = run(args.train_batch, graphed=not distributed, n=20)
+    out.update(main)
+    out["eager"] = run(args.train_batch, graphed=False, n=20) if not distributed else None
+    if not distributed:
+        out["reference_config_B32"] = {"cuda_graph": run(32, True, 200), "eager": run(32, False, 50)}
+    return out
 
 
 if __name__ == "__main__":

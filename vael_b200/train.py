@@ -87,3 +87,45 @@ def train_step(model, optimizer, data, labels, recon_w=1e-1, kl_w=1e-5, query_w=
     loss.backward()
     optimizer.step()
     return torch.stack([loss.detach(), rl.detach(), kl.detach(), qce.detach()])
+
+
+class GraphedTrainStep:
+    """The whole optimisation step (forward, ELBO, adjoint, Adam) captured once in a CUDA graph and
+    replayed per batch: the B=32 reference configuration is launch-bound (~150 kernels of a few
+    microseconds each), so removing the per-kernel launch and Python cost is what makes the step fast
+    (SURVEY.md §7 hard part 8, §8(f) rank 3).  Every vael_b200 kernel only enqueues work on the current
+    stream, so the capture needs nothing special; random numbers come from torch's graph-safe Philox
+    generator (`model.graph_safe_rng = True` makes the world sampler take its Gumbel noise from it
+    instead of a host-drawn seed, which a graph would freeze).
+
+    Usage: step = GraphedTrainStep(model, optimizer, batch_shape); terms = step(data, labels)
+    The optimizer must be capturable (torch.optim.Adam(..., capturable=True)).
+    """
+
+    def __init__(self, model, optimizer, data_shape, labels_shape=None, device=None, warmup=3, **loss_kw):
+        device = torch.device(device) if device is not None else next(model.parameters()).device
+        if device.type != "cuda":
+            raise RuntimeError("vael_b200: CUDA graphs need a CUDA device")
+        self.model, self.optimizer, self.loss_kw = model, optimizer, loss_kw
+        B = data_shape[0]
+        self.data = torch.zeros(data_shape, device=device)
+        self.labels = torch.zeros(labels_shape or (B, 4), dtype=torch.long, device=device)
+        model.graph_safe_rng = True
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):   # allocator warm-up, lazy circuit upload, cuDNN plan selection
+                train_step(model, optimizer, self.data, self.labels, **loss_kw)
+        torch.cuda.current_stream(device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.terms = train_step(model, optimizer, self.data, self.labels, **loss_kw)
+
+    def __call__(self, data, labels):
+        """Copies the batch into the static buffers and replays the step; returns the [4] term vector
+        (a static device tensor, overwritten by the next call)."""
+        self.data.copy_(data, non_blocking=True)
+        self.labels.copy_(labels, non_blocking=True)
+        self.graph.replay()
+        return self.terms

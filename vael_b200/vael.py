@@ -39,6 +39,9 @@ class VAELModel(nn.Module):
         self.gumbel_noise = None     # tests inject [B,W] Gumbel noise here (SURVEY.md hard part 7)
         self.reparam_noise = None    # and [B,L] normal noise here
         self._world_cache = None
+        # True: Gumbel noise from torch's (CUDA-graph-safe) device generator instead of the kernel's own
+        # Philox stream seeded from the host — needed when the step is captured in a CUDA graph
+        self.graph_safe_rng = False
 
     # ---- sampled world: kept as (index, y_soft), materialised one-hot on demand -----------------
     @property
@@ -59,7 +62,10 @@ class VAELModel(nn.Module):
 
     def sample_world(self, scores, herbrand, is_log=False):
         """Gumbel-softmax(hard) world + its Herbrand vector in one kernel (models/vael.py:61-65)."""
-        world_h, idx, y_soft = gumbel_world(scores, herbrand, tau=1.0, is_log=is_log, noise=self.gumbel_noise)
+        noise = self.gumbel_noise
+        if noise is None and self.graph_safe_rng:
+            noise = -torch.empty_like(scores).exponential_().log()
+        world_h, idx, y_soft = gumbel_world(scores, herbrand, tau=1.0, is_log=is_log, noise=noise)
         self._world_cache = (idx, y_soft)
         self.world_idx = idx
         return world_h
