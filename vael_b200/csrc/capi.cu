@@ -123,16 +123,14 @@ extern "C" void vael_circuit_destroy(vael_circuit_t* c) {
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(c->device);
-  cudaFree(c->d_nodes); cudaFree(c->d_edges); cudaFree(c->d_world_node); cudaFree(c->d_query_node);
-  cudaFree(c->d_qmask); cudaFree(c->d_qm_ptr); cudaFree(c->d_qm_idx); cudaFree(c->d_qmask_c); cudaFree(c->d_par_ptr); cudaFree(c->d_par_rec); cudaFree(c->d_bslot);
-  cudaFree(c->d_fact_leaf_ptr); cudaFree(c->d_fact_leaf);
+  gen_program_destroy(c->gen);
+  cudaFree(c->d_qmask); cudaFree(c->d_qm_ptr); cudaFree(c->d_qm_idx); cudaFree(c->d_qmask_c);
   for (auto& S : c->slot) {
     cudaFree(S.facts); cudaFree(S.worlds); cudaFree(S.query); cudaFree(S.gw); cudaFree(S.gq); cudaFree(S.gf);
     cudaFree(S.qidx);
     if (S.stream) cudaStreamDestroy(S.stream);
   }
   cudaSetDevice(prev);
-  free(c->h_level_ptr);
   delete c;
 }
 
@@ -202,8 +200,6 @@ extern "C" int vael_circuit_create(const vael_circuit_desc_t* d, vael_circuit_t*
   c->n_facts = d->n_facts; c->n_nodes = d->n_nodes; c->n_levels = d->n_levels; c->n_edges = d->n_edges;
   c->n_worlds = d->n_worlds; c->n_queries = d->n_queries; c->semiring = d->semiring;
   c->norm_node = d->norm_node < 0 ? -1 : d->norm_node;
-  c->h_level_ptr = static_cast<int32_t*>(malloc(sizeof(int32_t) * (d->n_levels + 1)));
-  memcpy(c->h_level_ptr, d->level_ptr, sizeof(int32_t) * (d->n_levels + 1));
 
   // identity hash of the arrays as given
   uint64_t h = 1469598103934665603ull;
@@ -218,30 +214,6 @@ extern "C" int vael_circuit_create(const vael_circuit_desc_t* d, vael_circuit_t*
   if (d->n_worlds) fnv(h, d->world_node, sizeof(int32_t) * d->n_worlds);
   if (d->n_queries) fnv(h, d->query_node, sizeof(int32_t) * d->n_queries);
   c->hash = h;
-
-  // node descriptors
-  std::vector<NodeDesc> nodes(d->n_nodes);
-  for (int n = 0; n < d->n_nodes; ++n) {
-    const int k = d->node_kind[n];
-    const int nc = d->child_ptr[n + 1] - d->child_ptr[n];
-    NodeDesc nd{};
-    nd.kind_n = k | (nc << 8);
-    nd.slot = n;
-    if (k == VAEL_NODE_LEAF_POS || k == VAEL_NODE_LEAF_NEG) {
-      nd.a = d->node_arg[n];
-    } else if (k == VAEL_NODE_CONST) {
-      float v = d->const_val[d->node_arg[n]];
-      memcpy(&nd.a, &v, 4);
-    } else if (nc <= 2) {
-      nd.a = nc >= 1 ? d->child_idx[d->child_ptr[n]] : 0;
-      nd.b = nc == 2 ? d->child_idx[d->child_ptr[n] + 1] : 0;
-    } else {
-      nd.a = d->child_ptr[n];  // offset into the edge array
-    }
-    nodes[n] = nd;
-  }
-  std::vector<int32_t> edges(d->child_idx, d->child_idx + d->n_edges);
-  std::vector<int32_t> wn(d->world_node, d->world_node + d->n_worlds), qn(d->query_node, d->query_node + d->n_queries);
 
   // query -> world membership bit masks (only if every query is a SUM over world nodes)
   c->mask_words = (d->n_worlds + 31) / 32;
@@ -272,49 +244,6 @@ extern "C" int vael_circuit_create(const vael_circuit_desc_t* d, vael_circuit_t*
       if (w <= prev) { members_in_world_order = false; break; }
       prev = w;
     }
-  }
-
-  // parent lists (transposed CSR) for the gather-form adjoint
-  std::vector<int32_t> par_ptr(d->n_nodes + 1, 0);
-  for (int e = 0; e < d->n_edges; ++e) par_ptr[d->child_idx[e] + 1]++;
-  for (int n = 0; n < d->n_nodes; ++n) par_ptr[n + 1] += par_ptr[n];
-  std::vector<int2> par_rec(d->n_edges);
-  {
-    std::vector<int32_t> fill(par_ptr.begin(), par_ptr.end() - 1);
-    for (int p = 0; p < d->n_nodes; ++p)
-      for (int e = d->child_ptr[p]; e < d->child_ptr[p + 1]; ++e) {
-        const int ch = d->child_idx[e];
-        par_rec[fill[ch]++] = make_int2(p, e - d->child_ptr[p]);
-      }
-  }
-  // which node values does the adjoint need?  children of products (siblings), everything under
-  // the normaliser, and for the log semiring sums and their children (softmax weights)
-  std::vector<char> need(d->n_nodes, 0);
-  for (int p = 0; p < d->n_nodes; ++p) {
-    const int k = d->node_kind[p];
-    const int nc = d->child_ptr[p + 1] - d->child_ptr[p];
-    if (d->semiring == VAEL_SEMIRING_PROB) {
-      if (k == VAEL_NODE_PROD && nc >= 2)
-        for (int e = d->child_ptr[p]; e < d->child_ptr[p + 1]; ++e) need[d->child_idx[e]] = 1;
-    } else if (k == VAEL_NODE_SUM) {
-      need[p] = 1;
-      for (int e = d->child_ptr[p]; e < d->child_ptr[p + 1]; ++e) need[d->child_idx[e]] = 1;
-    }
-  }
-  if (c->norm_node >= 0) need[c->norm_node] = 1;
-  for (int n = d->n_nodes - 1; n >= 0; --n)  // closure: a kept node needs its children
-    if (need[n])
-      for (int e = d->child_ptr[n]; e < d->child_ptr[n + 1]; ++e) need[d->child_idx[e]] = 1;
-  std::vector<int32_t> bslot(d->n_nodes, -1);
-  for (int n = 0; n < d->n_nodes; ++n)
-    if (need[n]) bslot[n] = c->n_bvals++;
-
-  std::vector<int32_t> fl_ptr(d->n_facts + 1, 0), fl;
-  for (int f = 0; f < d->n_facts; ++f) {
-    for (int n = 0; n < d->level_ptr[1]; ++n)
-      if ((d->node_kind[n] == VAEL_NODE_LEAF_POS || d->node_kind[n] == VAEL_NODE_LEAF_NEG) && d->node_arg[n] == f)
-        fl.push_back(n);
-    fl_ptr[f + 1] = (int32_t)fl.size();
   }
 
   // structured fast paths: world w = left-deep product of one positive literal per annotated disjunction,
@@ -361,7 +290,6 @@ extern "C" int vael_circuit_create(const vael_circuit_desc_t* d, vael_circuit_t*
 
   cudaError_t e = cudaSuccess;
   auto up = [&](auto** dp, const auto& v) { if (e == cudaSuccess) e = upload(dp, v); };
-  up(&c->d_nodes, nodes); up(&c->d_edges, edges); up(&c->d_world_node, wn); up(&c->d_query_node, qn);
   if (masks_ok) {
     up(&c->d_qmask, qmask);
     std::vector<int32_t> qm_ptr(d->n_queries + 1, 0), qm_idx;
@@ -374,8 +302,7 @@ extern "C" int vael_circuit_create(const vael_circuit_desc_t* d, vael_circuit_t*
     up(&c->d_qm_ptr, qm_ptr); up(&c->d_qm_idx, qm_idx);
   }
   if (!qmask_c.empty()) up(&c->d_qmask_c, qmask_c);
-  up(&c->d_par_ptr, par_ptr); up(&c->d_par_rec, par_rec); up(&c->d_bslot, bslot);
-  up(&c->d_fact_leaf_ptr, fl_ptr); up(&c->d_fact_leaf, fl);
+  if (e == cudaSuccess) c->gen = gen_program_create(d, &e);
   if (e != cudaSuccess) {
     vael_circuit_destroy(c);
     return cuda_fail(e, "circuit upload");
@@ -390,15 +317,13 @@ extern "C" uint64_t vael_circuit_hash(const vael_circuit_t* c) { return c ? c->h
 // ---------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------
-static void fill_gen(const vael_circuit_t* c, GenParams& G) {
+static GenCall make_call(const vael_circuit_t* c, const float* facts, const int32_t* qidx, int32_t qs, int64_t B,
+                         uint32_t flags) {
+  GenCall G;
   memset(&G, 0, sizeof(G));
-  G.nodes = c->d_nodes; G.edges = c->d_edges; G.world_node = c->d_world_node; G.query_node = c->d_query_node;
+  G.facts = facts; G.qidx = qidx; G.qscalar = qs; G.B = B; G.flags = flags;
   G.qmask = c->d_qmask; G.mask_words = c->mask_words;
-  G.n_nodes = c->n_nodes; G.n_facts = c->n_facts; G.n_worlds = c->n_worlds; G.n_queries = c->n_queries;
-  G.n_levels = c->n_levels; G.semiring = c->semiring; G.norm_node = c->norm_node;
-  for (int L = 0; L <= c->n_levels; ++L) G.level_ptr[L] = c->h_level_ptr[L];
-  G.bslot = c->d_bslot; G.n_bvals = c->n_bvals; G.par_ptr = c->d_par_ptr; G.par_rec = c->d_par_rec;
-  G.fact_leaf_ptr = c->d_fact_leaf_ptr; G.fact_leaf = c->d_fact_leaf;
+  return G;
 }
 
 static int check_common(const vael_circuit_t* c, const float* facts, const int32_t* qidx, int32_t qs, int64_t B,
@@ -447,11 +372,10 @@ extern "C" int vael_circuit_forward(const vael_circuit_t* c, const float* facts,
     CK(adw_forward(c->ad_np, c->ad_na, c->ad_nb, P, flags & VAEL_FLAG_NORMALIZE, flags & VAEL_FLAG_EVIDENCE, c->num_sms, st));
     g_last_kernel = "adw-tma2d";
   } else {
-    GenParams G;
-    fill_gen(c, G);
-    G.facts = facts; G.qidx = qidx; G.qscalar = needq ? qs : -1; G.B = B; G.flags = flags; G.worlds = worlds; G.query = query;
-    if (!generic_fits(G, false)) return fail(VAEL_E_UNSUPPORTED, "circuit too large for the shared-memory tile");
-    CK(generic_forward(G, c->num_sms, st));
+    GenCall G = make_call(c, facts, qidx, needq ? qs : -1, B, flags);
+    G.worlds = worlds; G.query = query;
+    if (!gen_fits(c->gen, false)) return fail(VAEL_E_UNSUPPORTED, "circuit too large for the shared-memory tile");
+    CK(gen_forward(c->gen, G, c->num_sms, st));
     g_last_kernel = "generic-csr";
   }
   g_launches++;
@@ -473,11 +397,10 @@ extern "C" int vael_circuit_queries_all(const vael_circuit_t* c, const float* fa
     g_launches++;
     return VAEL_OK;
   }
-  GenParams G;
-  fill_gen(c, G);
-  G.facts = facts; G.qscalar = -1; G.B = B; G.flags = flags; G.queries_all = queries_all;
-  if (!generic_fits(G, false)) return fail(VAEL_E_UNSUPPORTED, "circuit too large for the shared-memory tile");
-  CK(generic_forward(G, c->num_sms, static_cast<cudaStream_t>(stream)));
+  GenCall G = make_call(c, facts, nullptr, -1, B, flags);
+  G.queries_all = queries_all;
+  if (!gen_fits(c->gen, false)) return fail(VAEL_E_UNSUPPORTED, "circuit too large for the shared-memory tile");
+  CK(gen_forward(c->gen, G, c->num_sms, static_cast<cudaStream_t>(stream)));
   g_last_kernel = "generic-csr";
   g_launches++;
   return VAEL_OK;
@@ -506,12 +429,10 @@ extern "C" int vael_circuit_backward(const vael_circuit_t* c, const float* facts
     CK(adw_backward(c->ad_np, c->ad_na, c->ad_nb, P, flags & VAEL_FLAG_NORMALIZE, c->num_sms, st));
     g_last_kernel = "adw-tma2d";
   } else {
-    GenParams G;
-    fill_gen(c, G);
-    G.facts = facts; G.qidx = qidx; G.qscalar = needq ? qs : -1; G.B = B; G.flags = flags;
+    GenCall G = make_call(c, facts, qidx, needq ? qs : -1, B, flags);
     G.grad_worlds = grad_worlds; G.grad_query = grad_query; G.grad_facts = grad_facts;
-    if (!generic_fits(G, true)) return fail(VAEL_E_UNSUPPORTED, "circuit too large for the shared-memory tile");
-    CK(generic_backward(G, c->num_sms, st));
+    if (!gen_fits(c->gen, true)) return fail(VAEL_E_UNSUPPORTED, "circuit too large for the shared-memory tile");
+    CK(gen_backward(c->gen, G, c->num_sms, st));
     g_last_kernel = "generic-csr";
   }
   g_launches++;

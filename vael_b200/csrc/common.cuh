@@ -93,13 +93,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 __host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// ---- host-side circuit handle ----------------------------------------------
-struct NodeDesc {  // one int4 per node, read with a single broadcast load
-  int32_t kind_n;  // kind | (n_children << 8)
-  int32_t a;       // leaf: fact column; const: float bits; op: child 0 (or edge offset if n_children > 2)
-  int32_t b;       // op: child 1 (n_children == 2)
-  int32_t slot;    // value slot (== node id)
-};
+struct GenProgram;
 
 }  // namespace vael
 
@@ -115,21 +109,9 @@ struct vael_circuit {
   int num_sms;
   int32_t n_facts, n_nodes, n_levels, n_edges, n_worlds, n_queries, semiring, norm_node;
   uint64_t hash;
-  int32_t* h_level_ptr;      // host copy [n_levels+1]
-  // device arrays — forward CSR
-  vael::NodeDesc* d_nodes;   // [n_nodes]
-  int32_t* d_edges;          // [n_edges]
-  int32_t* d_world_node;     // [n_worlds]
-  int32_t* d_query_node;     // [n_queries]
+  vael::GenProgram* gen;     // schedule of the generic level-by-level kernels (circuit_generic.cu)
   uint32_t* d_qmask;         // [n_queries][mask_words] world membership of each query (SUM over world nodes), or null
   int32_t mask_words;
-  // device arrays — backward (transposed CSR: for every node the list of parent edges)
-  int32_t* d_par_ptr;        // [n_nodes+1]
-  int2* d_par_rec;           // [n_edges] {parent node, position of the child inside the parent}
-  int32_t* d_bslot;          // [n_nodes] slot of the node's value in the backward tile, -1 = not kept
-  int32_t n_bvals;
-  int32_t* d_fact_leaf_ptr;  // [n_facts+1] leaf nodes per fact column
-  int32_t* d_fact_leaf;      // leaf node ids
   // structured fast path
   int fast_kind;             // 0 none, 2 / 3 = worlds are the outer product of two / three annotated disjunctions
   int32_t ad_np, ad_na, ad_nb;  // AD sizes (np = leading AD, only for fast_kind 3); fact columns in that order

@@ -58,40 +58,27 @@ cudaError_t adw_backward(int np, int na, int nb, const AdwParams& P, bool norm, 
 
 // ---- circuit_generic.cu ----------------------------------------------------
 constexpr int kMaxLevels = 24;
-struct GenParams {
-  // forward CSR
-  const NodeDesc* nodes;
-  const int32_t* edges;
-  const int32_t* world_node;
-  const int32_t* query_node;
-  const uint32_t* qmask;  // may be null (evidence mode unsupported then)
-  int32_t mask_words;
-  int32_t n_nodes, n_facts, n_worlds, n_queries, n_levels, semiring, norm_node;
-  int32_t level_ptr[kMaxLevels + 1];
-  // batch
+struct GenProgram;  // device-resident schedule of a circuit (ops per level, parent records), built once
+GenProgram* gen_program_create(const vael_circuit_desc_t* d, cudaError_t* err);
+void gen_program_destroy(GenProgram* g);
+struct GenCall {  // the per-call part
   const float* facts;
   const int32_t* qidx;
   int32_t qscalar;
   long long B;
   uint32_t flags;
-  // forward outputs
-  float* worlds;       // [B,W] or null
-  float* query;        // [B] or null
-  float* queries_all;  // [B,Q] or null
-  // backward
+  const uint32_t* qmask;  // [Q][mask_words] or null (evidence mode unsupported then)
+  int32_t mask_words;
+  float* worlds;          // [B,W] or null
+  float* query;           // [B] or null
+  float* queries_all;     // [B,Q] or null
   const float* grad_worlds;
   const float* grad_query;
   float* grad_facts;
-  const int32_t* bslot;          // [n_nodes] value slot in the backward tile, -1 = not kept
-  int32_t n_bvals;
-  const int32_t* par_ptr;        // [n_nodes+1]
-  const int2* par_rec;           // [n_edges] {parent node, position of the child inside the parent}
-  const int32_t* fact_leaf_ptr;  // [F+1]
-  const int32_t* fact_leaf;      // leaf node ids per fact column
 };
-bool generic_fits(const GenParams& P, bool backward);
-cudaError_t generic_forward(const GenParams& P, int num_sms, cudaStream_t st);
-cudaError_t generic_backward(const GenParams& P, int num_sms, cudaStream_t st);
+bool gen_fits(const GenProgram* g, bool backward);
+cudaError_t gen_forward(const GenProgram* g, const GenCall& C, int num_sms, cudaStream_t st);
+cudaError_t gen_backward(const GenProgram* g, const GenCall& C, int num_sms, cudaStream_t st);
 
 // ---- sampling.cu -----------------------------------------------------------
 struct GumbelParams {
