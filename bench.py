@@ -61,6 +61,17 @@ def synthetic_facts(rows, device, seed):
 # ---------------------------------------------------------------------------
 # the reference's CPU path: oracle port of models/vael.py:208-225 + autograd
 # ---------------------------------------------------------------------------
+def host_threads():
+    """Use every host core this process may run on (torchrun exports OMP_NUM_THREADS=1 by default)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    if torch.get_num_threads() != n:
+        torch.set_num_threads(n)
+    return n
+
+
 def cpu_reference_rate(rows, steps, warmup):
     """evals/s of the reference's dense logic path (forward + autograd backward) on the host
     cores, torch CPU with all its threads, on `rows` rows per step."""
@@ -154,6 +165,7 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(1, args.warmup)
+    host_threads()
     rate, dt = cpu_reference_rate(args.cpu_rows, steps, warmup)
     cores = torch.get_num_threads()
     line = {
@@ -251,6 +263,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     distributed = world > 1
     if distributed:
+        os.environ["NCCL_DEBUG"] = os.environ.get("VAEL_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -330,7 +343,7 @@ def run_ours(args):
         e2e = {"value": world * Be * EVALS_PER_ROW / e2e_s, "unit": "evals/s",
                "h2d_bytes_per_step": Be * (80 + 4 + 400 + 4), "d2h_bytes_per_step": Be * (400 + 4 + 80),
                "rows_per_gpu": Be, "ms_per_step": e2e_s * 1e3,
-               "api": "vael_circuit_fwdbwd_host (C-ABI, pinned host buffers, chunked double-buffered copies)"}
+               "api": "vael_circuit_fwdbwd_host (C-ABI, pinned host buffers, 128Ki-row chunks over 4 streams)"}
 
     # ---- secondary probe: VAEL train step (configs[1]), DDP when N > 1 --------------------------------
     train = None
@@ -351,6 +364,7 @@ def run_ours(args):
     # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        host_threads()
         rate, dt = cpu_reference_rate(args.cpu_rows, 8, 2)
         cpu = {"value": rate, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{args.cpu_rows} rows/step x 8 steps ({dt * 1e3:.0f} ms/step), torch CPU fp32 port of "

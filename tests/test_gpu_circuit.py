@@ -148,3 +148,52 @@ def test_unaligned_views_take_the_plain_copy_path(dc, addition_family):
     w_ref, q_ref = fp_interp.forward(circ, facts, query=5)
     np.testing.assert_array_equal(w.cpu().numpy(), w_ref)
     np.testing.assert_array_equal(q.cpu().numpy()[:, 0], q_ref)
+
+
+def test_full_size_properties_and_host_path(dc, addition_family):
+    """BASELINE.json microbenchmark scale (B = 2^21 + 3 rows, 0.8 GB of worlds; the oracle could not finish
+    this): size-independent properties of the reference's closed form (models/vael.py:208-225) — rows sum
+    to 1, world (j,k) = p1[j] * p2[k] bit for bit, query = sum of the member worlds, evidence rows
+    renormalise to 1 and vanish off the evidence, the adjoint is linear and matches its closed form — and
+    the C-ABI host-buffer path (copies inside) returns exactly what the device path does."""
+    import ctypes as C
+    from vael_b200 import _lib
+    from vael_b200.ops import _p, circuit_forward
+    B = (1 << 21) + 3
+    g = torch.Generator(device="cuda").manual_seed(0)
+    p = torch.softmax(3 * torch.randn(B, 2, 10, device="cuda", generator=g), -1) + 1e-5
+    facts = (p / p.sum(-1, keepdim=True)).reshape(B, 20).contiguous().requires_grad_(True)
+    qi = torch.randint(0, 19, (B,), device="cuda", generator=g)
+    w, q = circuit_forward(dc, facts, qi)
+    f3 = facts.detach().reshape(B, 2, 10)
+    assert torch.allclose(w.sum(1), torch.ones(B, device="cuda"), atol=1e-5)
+    assert torch.equal(w.detach().reshape(B, 10, 10), f3[:, 0, :, None] * f3[:, 1, None, :])
+    wq = torch.from_numpy(addition_family.circuit.worlds_queries_matrix().astype(np.float32)).cuda()
+    q_dense = (w.detach().double() * wq.double().T[qi]).sum(1)
+    assert torch.allclose(q.detach()[:, 0].double(), q_dense, rtol=2e-6, atol=1e-12)
+    with torch.no_grad():
+        we, _ = circuit_forward(dc, facts.detach(), qi, evidence=True)
+    assert torch.allclose(we.sum(1), torch.ones(B, device="cuda"), atol=1e-5)
+    assert float((we * (1 - wq.T[qi])).abs().max()) == 0.0
+    gw = torch.randn(B, 100, device="cuda", generator=g)
+    (g1,) = torch.autograd.grad((w * gw).sum(), [facts], retain_graph=True)
+    (g2,) = torch.autograd.grad((w * (3 * gw)).sum(), [facts], retain_graph=True)
+    assert torch.allclose(g2, 3 * g1, rtol=1e-5, atol=1e-6)
+    (gs,) = torch.autograd.grad(w.sum() + q.sum(), [facts], retain_graph=True)   # closed form of d/dp of sum_w + query
+    member = wq.T[qi].reshape(B, 10, 10)
+    expect = torch.cat([f3[:, 1].sum(1, keepdim=True) + (member * f3[:, 1, None, :]).sum(2),
+                        f3[:, 0].sum(1, keepdim=True) + (member * f3[:, 0, :, None]).sum(1)], 1)
+    assert torch.allclose(gs, expect, rtol=1e-5, atol=1e-6)
+
+    # host-buffer entry points on a slice with a ragged chunk tail
+    n = (1 << 17) + 77
+    hf = facts.detach()[:n].cpu().pin_memory(); hq = qi[:n].to(torch.int32).cpu().pin_memory()
+    hgw = gw[:n].cpu().pin_memory(); hgq = torch.ones(n).pin_memory()
+    hw, hqo, hgf = torch.empty(n, 100).pin_memory(), torch.empty(n).pin_memory(), torch.empty(n, 20).pin_memory()
+    _lib.check(dc.lib.vael_circuit_fwdbwd_host(dc.handle, _p(hf), _p(hq), -1, n, _p(hgw), _p(hgq), _p(hw), _p(hqo), _p(hgf), 0))
+    assert torch.equal(hw, w.detach()[:n].cpu()) and torch.equal(hqo, q.detach()[:n, 0].cpu())
+    (gd,) = torch.autograd.grad((w[:n] * gw[:n]).sum() + q[:n].sum(), [facts])
+    assert torch.equal(hgf, gd[:n].cpu())
+    hw2 = torch.empty(n, 100)          # pageable host memory works too
+    _lib.check(dc.lib.vael_circuit_forward_host(dc.handle, _p(hf), None, 9, n, _p(hw2), None, 0))
+    assert torch.equal(hw2, hw)

@@ -440,17 +440,18 @@ extern "C" int vael_circuit_backward(const vael_circuit_t* c, const float* facts
 }
 
 // ---------------------------------------------------------------------------
-// host-buffer variants: chunked, double-buffered over two streams so that the H2D
-// copy of chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1 overlap
+// host-buffer variants: row chunks round-robin over kHostSlots streams (each with its own device
+// buffers) so that the H2D copy of one chunk, the kernels of another and the D2H copy of a third overlap
+// and both PCIe directions stay busy
 // ---------------------------------------------------------------------------
 static int ensure_slots(vael_circuit_t* x) {
   const vael_circuit_t* c = x;
   if (x->chunk_rows) return VAEL_OK;
   const char* env = getenv("VAEL_HOST_CHUNK_ROWS");
-  long long rows = env && *env ? atoll(env) : (1 << 18);
+  long long rows = env && *env ? atoll(env) : (1 << 17);
   if (rows < 32) rows = 32;
   const size_t F = c->n_facts, W = c->n_worlds;
-  for (int s = 0; s < 2; ++s) {
+  for (int s = 0; s < kHostSlots; ++s) {
     auto& S = x->slot[s];
     CK(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
     CK(cudaMalloc(&S.facts, rows * F * 4)); CK(cudaMalloc(&S.gf, rows * F * 4));
@@ -473,7 +474,7 @@ static int host_pipeline(const vael_circuit_t* c, const float* facts_h, const in
   int idx = 0;
   for (int64_t r0 = 0; r0 < B; r0 += x->chunk_rows, ++idx) {
     const int64_t n = (B - r0 < x->chunk_rows) ? (B - r0) : x->chunk_rows;
-    auto& S = x->slot[idx & 1];
+    auto& S = x->slot[idx % kHostSlots];
     CK(cudaMemcpyAsync(S.facts, facts_h + r0 * F, n * F * 4, cudaMemcpyHostToDevice, S.stream));
     if (qidx_h) CK(cudaMemcpyAsync(S.qidx, qidx_h + r0, n * 4, cudaMemcpyHostToDevice, S.stream));
     if (worlds_h || query_h) {
@@ -492,8 +493,7 @@ static int host_pipeline(const vael_circuit_t* c, const float* facts_h, const in
       CK(cudaMemcpyAsync(gf_h + r0 * F, S.gf, n * F * 4, cudaMemcpyDeviceToHost, S.stream));
     }
   }
-  CK(cudaStreamSynchronize(x->slot[0].stream));
-  CK(cudaStreamSynchronize(x->slot[1].stream));
+  for (int s = 0; s < kHostSlots; ++s) CK(cudaStreamSynchronize(x->slot[s].stream));
   return VAEL_OK;
 }
 

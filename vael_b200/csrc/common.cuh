@@ -97,6 +97,8 @@ struct GenProgram;
 
 }  // namespace vael
 
+constexpr int kHostSlots = 4;  // stages of the host-buffer pipeline (one stream each)
+
 // Opaque handle behind vael_circuit_t (include/vael_b200.h)
 struct vael_host_slot {  // one stage of the host-buffer (e2e) pipeline
   cudaStream_t stream;
@@ -120,6 +122,6 @@ struct vael_circuit {
   int32_t* d_qm_idx;
   uint32_t* d_qmask_c;       // fast_kind 3: [n_queries][np][ceil(na*nb/32)] chunked membership masks
   // host-buffer pipeline (allocated lazily by the *_host entry points)
-  vael_host_slot slot[2];
+  vael_host_slot slot[kHostSlots];
   long long chunk_rows;
 };
