@@ -127,19 +127,25 @@ __device__ __forceinline__ void load_chunk_mask(uint32_t* m, const AdwParams& P,
 // ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
-template <int NP, int NA, int NB, bool NORM, bool EVID, int S, int SO>
+// IC = values of the leading AD per stored box: the box is [32 rows, IC*C columns].  IC = 2 makes every
+// row segment 800 B = 25 whole 32-byte sectors (a 400 B segment ends mid-sector), which is worth ~12 % of
+// store bandwidth (scripts/micro/storebench.cu: 5.36 -> 5.91 TB/s at 3 warps/SM); the price is a 2-way
+// bank conflict on the STS.128 (row stride 800 B), on a path that uses ~15 % of the shared-memory bandwidth.
+template <int NP, int NA, int NB, bool NORM, bool EVID, int S, int SO, int IC>
 __global__ void __launch_bounds__(256) adw_forward_kernel(const __grid_constant__ CUtensorMap tm_worlds,
                                                           const AdwParams P) {
   using Sh = AdwShape<NP, NA, NB>;
   constexpr int F = Sh::F, C = Sh::C, MWC = Sh::MWC, FV = Sh::FV, CV = Sh::CV;
-  constexpr int PER_WARP = S * Sh::FACT_BYTES + SO * Sh::CH_BYTES + 128;
+  constexpr int BOX_BYTES = IC * Sh::CH_BYTES;
+  constexpr int PER_WARP = S * Sh::FACT_BYTES + SO * BOX_BYTES + 128;
+  static_assert(NP % IC == 0, "the leading AD must split into whole boxes");
   extern __shared__ __align__(128) uint8_t smem[];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
   uint8_t* wbase = smem + (size_t)warp * PER_WARP;
   uint8_t* out_base = wbase + S * Sh::FACT_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(out_base + SO * Sh::CH_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(out_base + SO * BOX_BYTES);
 
   const long long n_sub = (P.B + kWarp - 1) / kWarp;
   const long long gw = (long long)blockIdx.x * nwarps + warp;
@@ -232,45 +238,47 @@ __global__ void __launch_bounds__(256) adw_forward_kernel(const __grid_constant_
     }
 
 #pragma unroll 1
-    for (int i = 0; i < NP; ++i, ++nchunk) {
-      uint32_t m[MWC];
-      load_chunk_mask<MWC>(m, P, q, i);
-      const float pre = frow[i];
-      float t[NA];
-#pragma unroll
-      for (int j = 0; j < NA; ++j) t[j] = __fmul_rn(pre, pa[j]);
-
+    for (int i = 0; i < NP; i += IC, ++nchunk) {
       const int so = (int)(nchunk % SO);
-      float* orow = reinterpret_cast<float*>(out_base + so * Sh::CH_BYTES) + lane * C;
+      float* orow = reinterpret_cast<float*>(out_base + so * BOX_BYTES) + lane * (IC * C);
       if (P.worlds != nullptr) {
-        // the tensor store issued SO chunks ago must have finished reading this stage
+        // the tensor store issued SO boxes ago must have finished reading this stage
         if (lane == 0) bulk_wait_read<SO - 1>();
         __syncwarp();
       }
 #pragma unroll
-      for (int c = 0; c < C / CV; ++c) {
-        float o[CV];
+      for (int ii = 0; ii < IC; ++ii) {
+        uint32_t m[MWC];
+        load_chunk_mask<MWC>(m, P, q, i + ii);
+        const float pre = frow[i + ii];
+        float t[NA];
 #pragma unroll
-        for (int u = 0; u < CV; ++u) {
-          const int w = c * CV + u;
-          float v = __fmul_rn(t[w / NB], pb[w % NB]);
-          const bool member = (m[w >> 5] >> (w & 31)) & 1u;
-          if constexpr (EVID) {
-            v = member ? v / acc : 0.0f;  // P(w | e) = [w |= e] P(w) / P(e)
-          } else {
-            if (member) acc = __fadd_rn(acc, v);
-            if constexpr (NORM) v = v / z;
+        for (int j = 0; j < NA; ++j) t[j] = __fmul_rn(pre, pa[j]);
+#pragma unroll
+        for (int c = 0; c < C / CV; ++c) {
+          float o[CV];
+#pragma unroll
+          for (int u = 0; u < CV; ++u) {
+            const int w = c * CV + u;
+            float v = __fmul_rn(t[w / NB], pb[w % NB]);
+            const bool member = (m[w >> 5] >> (w & 31)) & 1u;
+            if constexpr (EVID) {
+              v = member ? v / acc : 0.0f;  // P(w | e) = [w |= e] P(w) / P(e)
+            } else {
+              if (member) acc = __fadd_rn(acc, v);
+              if constexpr (NORM) v = v / z;
+            }
+            o[u] = v;
           }
-          o[u] = v;
+          if (P.worlds != nullptr) w_sts<CV>(orow + ii * C + c * CV, o);
         }
-        if (P.worlds != nullptr) w_sts<CV>(orow + c * CV, o);
       }
       if (P.worlds != nullptr) {
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (P.l2_hint >= 1) tma_store_2d_hint(&tm_worlds, out_base + so * Sh::CH_BYTES, i * C, (int)row0, pol);
-          else tma_store_2d(&tm_worlds, out_base + so * Sh::CH_BYTES, i * C, (int)row0);
+          if (P.l2_hint >= 1) tma_store_2d_hint(&tm_worlds, out_base + so * BOX_BYTES, i * C, (int)row0, pol);
+          else tma_store_2d(&tm_worlds, out_base + so * BOX_BYTES, i * C, (int)row0);
           bulk_commit();
         }
       }
@@ -519,18 +527,18 @@ static int adw_env(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
-template <int NP, int NA, int NB, bool NORM, bool EVID, int S, int SO>
+template <int NP, int NA, int NB, bool NORM, bool EVID, int S, int SO, int IC>
 static cudaError_t launch_fwd_cfg(const AdwParams& P0, int num_sms, cudaStream_t st) {
   using Sh = AdwShape<NP, NA, NB>;
-  constexpr int PER_WARP = S * Sh::FACT_BYTES + SO * Sh::CH_BYTES + 128;
+  constexpr int PER_WARP = S * Sh::FACT_BYTES + SO * IC * Sh::CH_BYTES + 128;
   AdwParams P = P0;
   P.l2_hint = l2_hint_env();
   alignas(64) CUtensorMap map;
   memset(&map, 0, sizeof(map));
-  if (P.worlds != nullptr && !make_map(&map, P.worlds, P.B, Sh::W, Sh::C)) return cudaErrorNotSupported;
-  int nw = max(1, min(8, adw_env("VAEL_ADW_FWD_WARPS", 3)));
+  if (P.worlds != nullptr && !make_map(&map, P.worlds, P.B, Sh::W, IC * Sh::C)) return cudaErrorNotSupported;
+  int nw = max(1, min(8, adw_env("VAEL_ADW_FWD_WARPS", 2)));  // fewer, longer store streams measure faster
   while (nw > 1 && nw * PER_WARP > 227 * 1024) --nw;
-  auto kern = adw_forward_kernel<NP, NA, NB, NORM, EVID, S, SO>;
+  auto kern = adw_forward_kernel<NP, NA, NB, NORM, EVID, S, SO, IC>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, nw * PER_WARP);
   if (e != cudaSuccess) return e;
   const long long n_sub = (P.B + kWarp - 1) / kWarp;
@@ -541,12 +549,16 @@ static cudaError_t launch_fwd_cfg(const AdwParams& P0, int num_sms, cudaStream_t
 
 template <int NP, int NA, int NB, bool NORM, bool EVID>
 static cudaError_t launch_fwd(const AdwParams& P, int num_sms, cudaStream_t st) {
-  static const int cfg = adw_env("VAEL_ADW_FWD_STAGES", 23);  // <load stages><store stages>
+  // <load stages><store stages><leading-AD values per box>; measured on B200 (B = 2^20): 231 with 2 warps/SM
+  // 5.68 TB/s, 232 5.63, 222 5.60, 231 with 3 / 4 warps 5.19 / 5.00 (more store streams in flight run slower)
+  static const int cfg = adw_env("VAEL_ADW_FWD_CFG", 231);
   if constexpr (!NORM && !EVID) {
-    if (cfg == 22) return launch_fwd_cfg<NP, NA, NB, NORM, EVID, 2, 2>(P, num_sms, st);
-    if (cfg == 24) return launch_fwd_cfg<NP, NA, NB, NORM, EVID, 2, 4>(P, num_sms, st);
+    if (cfg == 222) return launch_fwd_cfg<NP, NA, NB, NORM, EVID, 2, 2, 2>(P, num_sms, st);
+    if (cfg == 221) return launch_fwd_cfg<NP, NA, NB, NORM, EVID, 2, 2, 1>(P, num_sms, st);
+    if (cfg == 232) return launch_fwd_cfg<NP, NA, NB, NORM, EVID, 2, 3, 2>(P, num_sms, st);
+    if (cfg == 241) return launch_fwd_cfg<NP, NA, NB, NORM, EVID, 2, 4, 1>(P, num_sms, st);
   }
-  return launch_fwd_cfg<NP, NA, NB, NORM, EVID, 2, 3>(P, num_sms, st);
+  return launch_fwd_cfg<NP, NA, NB, NORM, EVID, 2, 3, 1>(P, num_sms, st);
 }
 
 template <int NP, int NA, int NB, bool NORM, int S>
