@@ -534,7 +534,42 @@ def train_probe(args, dev, rank, world, distributed, barrier, max_over_ranks):
     out["eager"] = run(args.train_batch, graphed=False, n=20) if not distributed else None
     if not distributed:
         out["reference_config_B32"] = {"cuda_graph": run(32, True, 200), "eager": run(32, False, 50)}
+        try:
+            out["mario_B32"] = mario_probe(dev)
+        except Exception as exc:
+            out["mario_B32"] = {"error": repr(exc)[:200]}
     return out
+
+
+def mario_probe(dev, B=32, n=30):
+    """BASELINE.json configs[2]: Mario grid-navigation VAEL (two 100x100 RGB frames, 2 x 9 agent-position
+    facts, the compiled move-rule program: 81 worlds, 24 admissible, 4 move queries), reference batch 32."""
+    from vael_b200.mario_task import compile_mario_family, mario_tables
+    from vael_b200.networks import MarioDecoder, MarioEncoder, MarioMLP
+    from vael_b200.train import mario_train_step
+    from vael_b200.vael import MarioVAELModel
+    torch.manual_seed(0)
+    tabs = [torch.from_numpy(t.astype("float32")).to(dev) for t in mario_tables(compile_mario_family((3, 3)))]
+    W_all, WQ_all, W_adm, WQ_adm = tabs
+    model = MarioVAELModel(MarioEncoder(hidden_channels=64, latent_dim=48, dropout=0.0),
+                           MarioDecoder(hidden_channels=64, latent_dim_sub=30, label_dim=9, dropout=0.5),
+                           MarioMLP(18, 18, 32), (18, 30), None, WQ_all, W_all, WQ_adm, W_adm, (3, 3), dropout=0.5,
+                           is_train=True, device=dev).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    x = torch.rand(B, 3, 200, 100, device=dev)
+    moves = torch.eye(4, dtype=torch.long, device=dev)[torch.randint(0, 4, (B,), device=dev)]
+    for _ in range(5):
+        mario_train_step(model, opt, x, moves)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        elbo = mario_train_step(model, opt, x, moves)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return {"value": B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "elbo": float(elbo.item()), "mode": "eager",
+            "config": "Mario VAEL, synthetic 2x(100x100x3) frames, random-init weights, Adam"}
 
 
 if __name__ == "__main__":

@@ -182,3 +182,70 @@ def test_cuda_graphed_train_step_runs_and_learns(cuda_device):
     assert np.mean(losses[-10:]) < np.mean(losses[:10])
     assert any(not torch.equal(a, b) for a, b in zip(before, model.parameters()))
     assert any(not torch.equal(worlds[0], w) for w in worlds[1:5]), "the graph replays the same random numbers"
+
+
+def build_mario_model(device, g):
+    from vael_b200.networks import MarioDecoder, MarioEncoder, MarioMLP
+    from vael_b200.vael import MarioVAELModel
+    torch.manual_seed(0)
+    tabs = {n: torch.from_numpy(g[n].astype(np.float32)).to(device) for n in ("W_all", "WQ_all", "W_adm", "WQ_adm")}
+    # shapes of the reference configuration (config.py:47-51): hidden 64/64/32, latent 18 symbolic + 30 sub-symbolic
+    enc = MarioEncoder(hidden_channels=64, latent_dim=48, dropout=0.0)
+    dec = MarioDecoder(hidden_channels=64, latent_dim_sub=30, label_dim=9, dropout=0.0)
+    model = MarioVAELModel(enc, dec, MarioMLP(18, 18, 32), (18, 30), None, tabs["WQ_all"], tabs["W_all"], tabs["WQ_adm"],
+                           tabs["W_adm"], (3, 3), dropout=None, is_train=True, device=device)
+    return model.to(device), tabs
+
+
+def test_mario_model_forward_backward_matches_reference_composition(cuda_device):
+    """MarioVAELModel.forward + loss + backward (models/vael.py:295-346, utils/mario_utils/train.py:11-65)
+    against the same composition built from the oracle's restatement of the matrix path, injected noise."""
+    from vael_b200.train import mario_loss_function
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = load("mario")
+    B = 8
+    gen = torch.Generator().manual_seed(11)
+    x = torch.rand(B, 3, 200, 100, generator=gen)
+    moves = torch.eye(4, dtype=torch.long)[torch.randint(0, 4, (B,), generator=gen)]
+    eps = torch.randn(B, 48, generator=gen)
+    gumbel = -torch.empty(B, 24).exponential_(generator=gen).log()
+
+    model, _ = build_mario_model(cuda_device, g)
+    model.eval()
+    model.reparam_noise, model.gumbel_noise = eps.cuda(), gumbel.cuda()
+    outs = model(x.cuda(), moves.cuda())
+    res = mario_loss_function(*outs, recon_w=1e-1, kl_w=1e-5, query_w=1.0, sup_w=0.0, rec_loss="LAPLACE")
+    model.zero_grad()
+    res["elbo"].backward()
+    got = {n: p.grad.detach().cpu().clone() for n, p in model.named_parameters()}
+
+    ref, tabs = build_mario_model(torch.device("cpu"), g)
+    ref.load_state_dict({k: v.cpu() for k, v in model.state_dict().items()})
+    ref.eval()
+    x1, x2 = torch.split(x, 100, dim=2)
+    (mu1, lv1), (mu2, lv2) = ref.encoder(x1), ref.encoder(x2)
+    z1, z2 = mu1 + torch.exp(lv1 / 2) * eps, mu2 + torch.exp(lv2 / 2) * eps
+    facts = dense_path.mario_facts(ref.mlp(z1[:, :18]), ref.mlp(z2[:, :18]))
+    worlds = dense_path.mario_worlds(facts, tabs["W_all"])
+    query = dense_path.mario_query_prob(moves, worlds, tabs["WQ_all"])
+    adm = dense_path.mario_admissible_logprob(facts, tabs["W_adm"])
+    world, _, _ = dense_path.gumbel_hard(adm, gumbel)
+    wh = world @ tabs["W_adm"]
+    r1, r2 = ref.decoder(torch.cat([z1[:, 18:], wh[:, :9]], 1)), ref.decoder(torch.cat([z2[:, 18:], wh[:, 9:]], 1))
+    l1, *_ = dense_path.elbo_terms(r1, x1, mu1, lv1, query, 1e-1, 1e-5, 1.0)
+    # frame 2 carries reconstruction + KL only (utils/mario_utils/train.py:49-52)
+    l2 = 1e-1 * (-dense_path.laplace_loglik(r2, x2).mean()) + \
+        1e-5 * torch.mean(-0.5 * torch.sum(1.0 + lv2 - mu2.pow(2) - lv2.exp(), dim=1))
+    (l1 + l2).backward()
+
+    assert rel_err(model.worlds_probs.detach().cpu().numpy(), worlds.detach().numpy(), floor=1e-9) < 2e-4
+    assert rel_err(model.query_prob.detach().cpu().numpy(), query.detach().numpy(), floor=1e-9) < 2e-4
+    assert rel_err(model.adm_worlds_logprob.detach().cpu().numpy(), adm.detach().numpy(), floor=1e-6) < 2e-4
+    assert abs(res["elbo"].item() - (l1 + l2).item()) < 1e-4 * abs((l1 + l2).item())
+    # gradients pass through four (transposed) convolutions over 100x100 frames, computed by cuDNN here and by
+    # the CPU kernels in the reference arm (different algorithms, different summation order): compare every
+    # parameter gradient on the scale of its largest entry
+    for n, p in ref.named_parameters():
+        r = p.grad
+        assert float((got[n] - r).abs().max()) < 2e-3 * float(r.abs().max()) + 1e-9, n

@@ -89,6 +89,18 @@ def train_step(model, optimizer, data, labels, recon_w=1e-1, kl_w=1e-5, query_w=
     return torch.stack([loss.detach(), rl.detach(), kl.detach(), qce.detach()])
 
 
+def mario_train_step(model, optimizer, data, moves, recon_w=1e-1, kl_w=1e-5, query_w=1.0, rec_loss="LAPLACE"):
+    """One optimisation step of the Mario model on a [B,3,200,100] batch of stacked frame pairs with one-hot
+    moves [B,4] (the body of utils/mario_utils/train.py:105-150); returns the detached elbo on the device."""
+    optimizer.zero_grad(set_to_none=True)
+    x1, r1, mu1, lv1, x2, r2, mu2, lv2, q = model(data, moves)
+    out = mario_loss_function(x1, r1, mu1, lv1, x2, r2, mu2, lv2, q, recon_w=recon_w, kl_w=kl_w, query_w=query_w,
+                              sup_w=0.0, rec_loss=rec_loss)
+    out["elbo"].backward()
+    optimizer.step()
+    return out["elbo"].detach()
+
+
 class GraphedTrainStep:
     """The whole optimisation step (forward, ELBO, adjoint, Adam) captured once in a CUDA graph and
     replayed per batch: the B=32 reference configuration is launch-bound (~150 kernels of a few
