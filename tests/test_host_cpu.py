@@ -219,3 +219,54 @@ def test_product_path_has_no_cpu_fallback(addition_family):
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+# ---------------------------------------------------------------------------
+# encoder / decoder / MLP mirrors: checkpoint layout and forward semantics of the reference modules
+# ---------------------------------------------------------------------------
+def _mirror(name, **kw):
+    from vael_b200 import networks
+    return getattr(networks, name)(**kw)
+
+
+def test_network_state_dict_layouts_match_reference_checkpoints():
+    """Names and shapes of every parameter at the shipped widths (what {'model': state_dict} checkpoints
+    of the reference hold, utils/early_stopping.py:53-65)."""
+    import json
+    lay = json.load(open(os.path.join(G, "network_layouts.json")))
+    mine = {
+        "MNISTPairsEncoder": _mirror("MNISTPairsEncoder", hidden_channels=64, latent_dim=23),
+        "MNISTPairsDecoder": _mirror("MNISTPairsDecoder", label_dim=20, hidden_channels=64, latent_dim=8),
+        "MNISTPairsMLP": _mirror("MNISTPairsMLP", in_features=15, n_facts=20),
+        "MarioEncoder": _mirror("MarioEncoder", img_channels=3, hidden_channels=64, latent_dim=48),
+        "MarioDecoder": _mirror("MarioDecoder", img_channels=3, hidden_channels=64, latent_dim_sub=30, label_dim=9),
+        "MarioMLP": _mirror("MarioMLP", in_features=18, n_facts=18, hidden_channels=32),
+    }
+    for name, m in mine.items():
+        got = {k: list(v.shape) for k, v in m.state_dict().items()}
+        assert got == lay[name], name
+    assert sum(p.numel() for n in ("MNISTPairsEncoder", "MNISTPairsDecoder", "MNISTPairsMLP")
+               for p in mine[n].parameters()) == 1848467          # SURVEY.md Appendix B
+    assert sum(p.numel() for n in ("MarioEncoder", "MarioDecoder", "MarioMLP") for p in mine[n].parameters()) == 10354412
+
+
+def test_networks_load_reference_weights_and_reproduce_the_reference_forward():
+    g = np.load(os.path.join(G, "networks.npz"))
+    ctor = {
+        "MNISTPairsEncoder": dict(hidden_channels=4, latent_dim=23),
+        "MNISTPairsDecoder": dict(label_dim=20, hidden_channels=4, latent_dim=8),
+        "MNISTPairsMLP": dict(in_features=15, n_facts=20),
+        "MarioEncoder": dict(img_channels=3, hidden_channels=2, latent_dim=48),
+        "MarioDecoder": dict(img_channels=3, hidden_channels=2, latent_dim_sub=30, label_dim=9),
+        "MarioMLP": dict(in_features=18, n_facts=18, hidden_channels=32),
+    }
+    for name, kw in ctor.items():
+        m = _mirror(name, **kw)
+        sd = {k[len(name) + 3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(name + "/w/")}
+        m.load_state_dict(sd, strict=True)
+        m.eval()
+        with torch.no_grad():
+            y = m(torch.from_numpy(g[name + "/x"]))
+        ys = y if isinstance(y, (tuple, list)) else (y,)
+        for i, t in enumerate(ys):
+            np.testing.assert_allclose(t.numpy(), g[f"{name}/y{i}"], rtol=1e-5, atol=1e-6, err_msg=name)
