@@ -250,3 +250,39 @@ def test_mario_model_forward_backward_matches_reference_composition(cuda_device)
     for n, p in ref.named_parameters():
         r = p.grad
         assert float((got[n] - r).abs().max()) < 2e-2 * float(r.abs().max()) + 1e-9, n
+
+
+def test_reference_style_calls_through_the_problog_shim(cuda_device):
+    """What the reference itself executes, line for line: programs compiled with
+    SDD.create_from(LogicDAG.create_from(LogicFormula.create_from(text))) (mnist_task_VAEL.py:214-216),
+    weights bound as update_semiring_weights does (models/vael.py:227-243) on a FOREIGN semiring object
+    (the oracle's restatement of the reference class: it has no fast-path hooks), sdd.evaluate(semiring=...)
+    (models/vael.py:109,130), extract_* — against the golden written by the reference's GraphSemiring."""
+    from oracle import graph_path
+    from oracle.semiring_port import SemiringPort
+    from vael_b200 import compat
+    from vael_b200.mnist_task import addition_rules, create_facts, define_ProbLog_model
+    compat.install(force=True)
+    from problog.formula import LogicDAG, LogicFormula
+    from problog.logic import Constant, Term
+    from problog.sdd_formula import SDD
+    g = load("graph_path")
+    facts = cu(g["facts"])                                   # [32,2,10]
+    weights = {Term(f"p_{i}{j}"): facts[:, i - 1, j] for i in (1, 2) for j in range(10)}
+    ads = create_facts(2, n_digits=10)
+    keys = [Term("digits")(Constant(j), Constant(k)) for j in range(10) for k in range(10)]
+
+    def run(mode, label):
+        text = define_ProbLog_model(ads, addition_rules(2), label=label, digit_query="digits(X,Y)", mode=mode)
+        sdd = SDD.create_from(LogicDAG.create_from(LogicFormula.create_from(text)))
+        sr = SemiringPort(batch_size=32)
+        sr.set_weights(weights)
+        return sdd.evaluate(semiring=sr)
+
+    res = run("query", 9)
+    assert list(res.keys())[:100] == keys and str(list(res.keys())[-1]) == "addition(img,9)"
+    np.testing.assert_allclose(torch.stack([res[k] for k in keys], 1).cpu().numpy(), g["query_res_worlds"], rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(graph_path.extract_query_probability(res).cpu().numpy(), g["extract_query"], rtol=1e-5)
+    np.testing.assert_allclose(graph_path.extract_worlds_probability(res, keys).cpu().numpy(), g["extract_worlds"], rtol=1e-5, atol=1e-12)
+    res_e = run("evidence", 7)
+    np.testing.assert_allclose(torch.stack([res_e[k] for k in keys], 1).cpu().numpy(), g["evidence_res_worlds"], rtol=1e-5, atol=1e-12)

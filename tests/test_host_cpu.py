@@ -270,3 +270,52 @@ def test_networks_load_reference_weights_and_reproduce_the_reference_forward():
         ys = y if isinstance(y, (tuple, list)) else (y,)
         for i, t in enumerate(ys):
             np.testing.assert_allclose(t.numpy(), g[f"{name}/y{i}"], rtol=1e-5, atol=1e-6, err_msg=name)
+
+
+# ---------------------------------------------------------------------------
+# import shim: the reference's own compile calls end in this repo's compiler
+# ---------------------------------------------------------------------------
+def test_problog_shim_compiles_the_reference_program_text():
+    """SDD.create_from(LogicDAG.create_from(LogicFormula.create_from(text))) as
+    utils/mnist_utils/mnist_task_VAEL.py:214-216 writes it, on the text this repo's generator emits (the
+    next test checks that text against the reference's own generator where the reference tree exists)."""
+    from vael_b200 import compat
+    from vael_b200.mnist_task import addition_rules, create_facts, define_ProbLog_model
+    compat.install(force=True)
+    from problog.formula import LogicDAG, LogicFormula
+    from problog.logic import Constant, Term
+    from problog.program import PrologString
+    from problog.sdd_formula import SDD
+    facts = create_facts(2, n_digits=10)
+    for mode, add in (("query", 9), ("evidence", 7)):
+        text = define_ProbLog_model(facts, addition_rules(2), label=add, digit_query="digits(X,Y)", mode=mode)
+        sdd = SDD.create_from(LogicDAG.create_from(LogicFormula.create_from(PrologString(text))))
+        assert sdd.mode == mode and hasattr(sdd, "evaluate")
+        circ = sdd.pset.circuit
+        assert circ.n_worlds == 100 and circ.n_queries == 1 and circ.n_facts == 20
+        assert [str(a) for a in sdd.view.result_atoms[:100]] == [f"digits({j},{k})" for j in range(10) for k in range(10)]
+        assert sdd.view.result_atoms[0] == Term("digits")(Constant(0), Constant(0))
+        members = circ.worlds_queries_matrix()[:, 0]
+        assert [w for w in range(100) if members[w]] == [w for w in range(100) if w // 10 + w % 10 == add]
+    sdd2 = SDD.create_from(LogicFormula.create_from(text))          # a bare string works too
+    assert sdd2.pset.circuit.sha256() == circ.sha256()
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/utils/mnist_utils/problog_model.py"),
+                    reason="the reference tree exists in the build container only")
+def test_program_text_is_what_the_reference_generator_writes():
+    """utils/mnist_utils/problog_model.py imported UNMODIFIED through the shim: same facts, same program text."""
+    import importlib.util
+    from vael_b200 import compat, mnist_task
+    compat.install(force=True)
+    spec = importlib.util.spec_from_file_location("ref_problog_model", "/root/reference/utils/mnist_utils/problog_model.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    assert ref.create_facts(2, n_digits=10) == mnist_task.create_facts(2, n_digits=10)
+    rules = "addition(X,N) :- digit(X,1,N1), digit(X,2,N2), N is N1 + N2.\ndigits(X,Y):-digit(img,1,X), digit(img,2,Y)."
+    assert rules == mnist_task.addition_rules(2)                     # mnist_task_VAEL.py:206
+    facts = ref.create_facts(2, n_digits=10)
+    for mode in ("query", "evidence"):
+        for add in (0, 9, 18):
+            assert ref.define_ProbLog_model(facts, rules, label=add, digit_query="digits(X,Y)", mode=mode) == \
+                mnist_task.define_ProbLog_model(facts, rules, label=add, digit_query="digits(X,Y)", mode=mode)

@@ -80,7 +80,11 @@ class CompiledProgram:
         if semiring is None:
             raise ValueError("evaluate needs the GraphSemiring carrying the fact weights")
         fam = self.pset.family
-        facts = semiring.fact_matrix(fam.fact_terms)
+        if hasattr(semiring, "fact_matrix"):
+            facts = semiring.fact_matrix(fam.fact_terms)
+        else:  # a foreign semiring (the reference's own GraphSemiring): read the bound leaf weights once
+            from .graph_semiring import GraphSemiring
+            facts = GraphSemiring.fact_matrix(semiring, fam.fact_terms)
         dc = self.pset.device_circuit(facts.device)
         evid = self.view.mode == "evidence"
         q = self.view.query_index if self.view.query_index >= 0 else None
