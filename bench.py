@@ -220,7 +220,7 @@ class ClockSampler:
                 self.samples.append((time.perf_counter(), mhz, rs))
             except Exception:
                 pass
-            time.sleep(0.001)
+            time.sleep(0.0005)
 
     def stop(self, t0, t1):
         if self.nv is None:
@@ -244,7 +244,8 @@ class ClockSampler:
         except Exception:
             mx = None
         return {"sm_mhz": statistics.median(mhz) if mhz else None, "sm_max_mhz": mx, "reasons": reasons,
-                "samples": len(mhz)}
+                "samples": len(mhz), "samples_whole_run": len(self.samples),
+                "sm_mhz_whole_run": statistics.median([s[1] for s in self.samples]) if self.samples else None}
 
 
 # ---------------------------------------------------------------------------
@@ -294,12 +295,12 @@ def run_ours(args):
     def bwd():
         _lib.check(lib.vael_circuit_backward(dc.handle, _p(facts), _p(qidx), -1, B, _p(gw), _p(gq), _p(gf), 0, sp))
 
+    sampler = ClockSampler(local) if rank == 0 else None   # started before warm-up: NVML's first calls are slow
     for _ in range(W):
         fwd(); bwd()
     barrier()
     # ---- timed region: exactly K steps, per-kernel events on the launching stream -------------
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = _lib.launch_count()
     barrier()
     t0 = time.perf_counter()
