@@ -1,0 +1,31 @@
+"""One eager VAEL train step at batch B (default 32) after warm-up: the launch list for ncu."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from vael_b200.mnist_task import build_model_dict, build_worlds_queries_matrix
+from vael_b200.networks import MNISTPairsDecoder, MNISTPairsEncoder, MNISTPairsMLP
+from vael_b200.train import train_step
+from vael_b200.vael import MNISTPairsVAELModel
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+CL = len(sys.argv) > 2 and sys.argv[2] == "cl"
+dev = torch.device("cuda", 0)
+torch.manual_seed(0)
+model = MNISTPairsVAELModel(MNISTPairsEncoder(hidden_channels=64, latent_dim=23), MNISTPairsDecoder(label_dim=20, hidden_channels=64, latent_dim=8),
+                            MNISTPairsMLP(in_features=15, n_facts=20), (15, 8), build_model_dict(2, 10, device=dev),
+                            build_worlds_queries_matrix(2, 10).to(dev), dropout=0.5, is_train=True, device=dev, query_per_row=True).to(dev)
+if CL:
+    model = model.to(memory_format=torch.channels_last)
+opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=CL)
+x = torch.randn(B, 1, 28, 56, device=dev)
+if CL:
+    x = x.contiguous(memory_format=torch.channels_last)
+d = torch.randint(0, 10, (B, 2), device=dev)
+labels = torch.cat([d, d.sum(1, keepdim=True), -torch.ones(B, 1, dtype=torch.long, device=dev)], 1)
+for _ in range(4):
+    train_step(model, opt, x, labels)
+torch.cuda.synchronize()
+torch.cuda.nvtx.range_push("step")
+train_step(model, opt, x, labels)
+torch.cuda.synchronize()
+torch.cuda.nvtx.range_pop()
+print("done")

@@ -7,81 +7,94 @@
 //   qbce  =  BCELoss(q, 1) = mean_b -max(log q, -100)
 //   loss  =  recon_w recon + kl_w kl + query_w qbce
 // HBM-bound: reads recon and x once (2*D floats per row) and writes grad_recon.
-// One CTA per batch row (grid-stride); per-CTA partial sums go to a workspace and
-// the last CTA to finish adds them in index order, so the result is deterministic.
+// The reconstruction term is a sum over ALL pixels of the batch divided by B, so the kernel treats
+// recon / x / grad_recon as one flat stream: every CTA takes a contiguous span of it (128-bit loads, four in
+// flight per thread), the KL and query terms are grid-stride loops over their [B,L] / [B] elements.  Per-CTA
+// partial sums go to a workspace in fp64 and the last CTA to finish adds them in index order, so the
+// result is deterministic.
 #include "params.cuh"
 
 namespace vael {
 
-
 __device__ __forceinline__ float sgn(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }
 
+__device__ __forceinline__ float abs_and_grad4(const float4 x, const float4 r, float gr, float4* g) {
+  const float d0 = r.x - x.x, d1 = r.y - x.y, d2 = r.z - x.z, d3 = r.w - x.w;
+  if (g) *g = make_float4(gr * sgn(d0), gr * sgn(d1), gr * sgn(d2), gr * sgn(d3));
+  return (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
+}
+
 __global__ void __launch_bounds__(256) elbo_terms_kernel(const ElboParams P) {
-  __shared__ float red[2][8];
+  __shared__ double red[3][8];
   __shared__ bool is_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float invB = 1.0f / (float)P.B;
   const float gr = P.recon_w * invB, gk = P.kl_w * invB, gq = P.query_w * invB;
-  const bool vec = (P.D % 4 == 0) && aligned16(P.recon) && aligned16(P.x) &&
+  const long long n = P.B * P.D;
+  const bool vec = (n % 4 == 0) && aligned16(P.recon) && aligned16(P.x) &&
                    (P.grad_recon == nullptr || aligned16(P.grad_recon));
-  double acc_recon = 0.0, acc_kl = 0.0, acc_q = 0.0;  // meaningful in thread 0 only
+  const long long gtid = (long long)blockIdx.x * blockDim.x + tid, gsz = (long long)gridDim.x * blockDim.x;
 
-  for (long long row = blockIdx.x; row < P.B; row += gridDim.x) {
-    const float* xr = P.x + row * P.D;
-    const float* rr = P.recon + row * P.D;
-    float* gr_out = P.grad_recon ? P.grad_recon + row * P.D : nullptr;
-    float s_abs = 0.0f;
-    if (vec) {
-      const float4* x4 = reinterpret_cast<const float4*>(xr);
-      const float4* r4 = reinterpret_cast<const float4*>(rr);
-      float4* g4 = reinterpret_cast<float4*>(gr_out);
-      for (long long i = tid; i < P.D / 4; i += blockDim.x) {
-        const float4 a = __ldg(x4 + i), b = __ldg(r4 + i);
-        const float d0 = b.x - a.x, d1 = b.y - a.y, d2 = b.z - a.z, d3 = b.w - a.w;
-        s_abs += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
-        if (g4) g4[i] = make_float4(gr * sgn(d0), gr * sgn(d1), gr * sgn(d2), gr * sgn(d3));
-      }
-    } else {
-      for (long long i = tid; i < P.D; i += blockDim.x) {
-        const float d = __ldg(rr + i) - __ldg(xr + i);
-        s_abs += fabsf(d);
-        if (gr_out) gr_out[i] = gr * sgn(d);
-      }
-    }
-    float s_kl = 0.0f;
-    for (int l = tid; l < P.L; l += blockDim.x) {
-      const float m = __ldg(P.mu + row * P.L + l), lv = __ldg(P.logvar + row * P.L + l);
-      const float ev = expf(lv);
-      s_kl += 1.0f + lv - m * m - ev;
-      if (P.grad_mu) P.grad_mu[row * P.L + l] = gk * m;
-      if (P.grad_logvar) P.grad_logvar[row * P.L + l] = gk * 0.5f * (ev - 1.0f);
-    }
+  // ---- sum |x - recon| over the whole batch; grad_recon = recon_w / B * sign(recon - x) ----
+  float s_abs = 0.0f;
+  if (vec) {
+    const long long n4 = n / 4;
+    const long long span = (n4 + gridDim.x - 1) / gridDim.x;   // contiguous float4 span of this CTA
+    const long long beg = (long long)blockIdx.x * span, end = min(n4, beg + span);
+    const float4* x4 = reinterpret_cast<const float4*>(P.x);
+    const float4* r4 = reinterpret_cast<const float4*>(P.recon);
+    float4* g4 = reinterpret_cast<float4*>(P.grad_recon);
+    long long i = beg + tid;
+    for (; i + 3 * 256 < end; i += 4 * 256) {
+      float4 a[4], b[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s_abs += __shfl_xor_sync(0xffffffffu, s_abs, o);
-      s_kl += __shfl_xor_sync(0xffffffffu, s_kl, o);
+      for (int u = 0; u < 4; ++u) { a[u] = __ldg(x4 + i + u * 256); b[u] = __ldg(r4 + i + u * 256); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s_abs += abs_and_grad4(a[u], b[u], gr, g4 ? g4 + i + u * 256 : nullptr);
     }
-    if (lane == 0) { red[0][warp] = s_abs; red[1][warp] = s_kl; }
-    __syncthreads();
-    if (tid == 0) {
-      float ta = 0.0f, tk = 0.0f;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ta += red[0][w]; tk += red[1][w]; }
-      acc_recon += (double)((float)P.D * 0.69314718055994531f + ta);
-      acc_kl += (double)(-0.5f * tk);
-      if (P.query_prob != nullptr) {
-        const float q = __ldg(P.query_prob + row);
-        acc_q += (double)(-fmaxf(logf(q), -100.0f));
-        // torch binary_cross_entropy backward with target 1: (q - 1) / max((1 - q) q, 1e-12)
-        if (P.grad_query) P.grad_query[row] = gq * (q - 1.0f) / fmaxf((1.0f - q) * q, 1e-12f);
-      }
+    for (; i < end; i += 256) s_abs += abs_and_grad4(__ldg(x4 + i), __ldg(r4 + i), gr, g4 ? g4 + i : nullptr);
+  } else {
+    for (long long i = gtid; i < n; i += gsz) {
+      const float d = __ldg(P.recon + i) - __ldg(P.x + i);
+      s_abs += fabsf(d);
+      if (P.grad_recon) P.grad_recon[i] = gr * sgn(d);
     }
-    __syncthreads();
+  }
+  // ---- KL over [B,L] ----
+  float s_kl = 0.0f;
+  for (long long i = gtid; i < P.B * P.L; i += gsz) {
+    const float m = __ldg(P.mu + i), lv = __ldg(P.logvar + i);
+    const float ev = expf(lv);
+    s_kl += 1.0f + lv - m * m - ev;
+    if (P.grad_mu) P.grad_mu[i] = gk * m;
+    if (P.grad_logvar) P.grad_logvar[i] = gk * 0.5f * (ev - 1.0f);
+  }
+  // ---- query BCE over [B] ----
+  float s_q = 0.0f;
+  if (P.query_prob != nullptr) {
+    for (long long i = gtid; i < P.B; i += gsz) {
+      const float q = __ldg(P.query_prob + i);
+      s_q += -fmaxf(logf(q), -100.0f);
+      // torch binary_cross_entropy backward with target 1: (q - 1) / max((1 - q) q, 1e-12)
+      if (P.grad_query) P.grad_query[i] = gq * (q - 1.0f) / fmaxf((1.0f - q) * q, 1e-12f);
+    }
   }
 
+  double da = (double)s_abs, dk = (double)s_kl, dq = (double)s_q;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    da += __shfl_xor_sync(0xffffffffu, da, o);
+    dk += __shfl_xor_sync(0xffffffffu, dk, o);
+    dq += __shfl_xor_sync(0xffffffffu, dq, o);
+  }
+  if (lane == 0) { red[0][warp] = da; red[1][warp] = dk; red[2][warp] = dq; }
+  __syncthreads();
   if (tid == 0) {
-    P.partials[blockIdx.x * 3 + 0] = acc_recon;
-    P.partials[blockIdx.x * 3 + 1] = acc_kl;
-    P.partials[blockIdx.x * 3 + 2] = acc_q;
+    double ta = 0.0, tk = 0.0, tq = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ta += red[0][w]; tk += red[1][w]; tq += red[2][w]; }
+    P.partials[blockIdx.x * 3 + 0] = ta;
+    P.partials[blockIdx.x * 3 + 1] = tk;
+    P.partials[blockIdx.x * 3 + 2] = tq;
     __threadfence();
     const unsigned int done = atomicAdd(P.counter, 1u);
     is_last = (done == gridDim.x - 1);
@@ -96,7 +109,9 @@ __global__ void __launch_bounds__(256) elbo_terms_kernel(const ElboParams P) {
       k += part[b * 3 + 1];
       q += part[b * 3 + 2];
     }
-    const float recon = (float)(r / (double)P.B), kl = (float)(k / (double)P.B), qb = (float)(q / (double)P.B);
+    // recon = mean_b ( D log 2 + sum_pix |x - recon| )
+    const float recon = (float)((double)P.D * 0.69314718055994531 + r / (double)P.B);
+    const float kl = (float)(-0.5 * k / (double)P.B), qb = (float)(q / (double)P.B);
     P.terms[1] = recon;
     P.terms[2] = kl;
     P.terms[3] = qb;
@@ -111,7 +126,9 @@ size_t elbo_workspace_bytes() { return 16 + (size_t)kElboMaxGrid * 3 * sizeof(do
 cudaError_t elbo_terms(ElboParams P, void* workspace, int num_sms, cudaStream_t st) {
   P.counter = reinterpret_cast<unsigned int*>(workspace);
   P.partials = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(workspace) + 16);
-  const int grid = (int)max(1LL, min(P.B, (long long)min(kElboMaxGrid, num_sms * 8)));
+  // enough CTAs to fill the chip, never more than one per 1024 float4s of the pixel stream
+  const long long work = max(1LL, (P.B * P.D) / 4096);
+  const int grid = (int)max(1LL, min(work, (long long)min(kElboMaxGrid, num_sms * 8)));
   elbo_terms_kernel<<<grid, 256, 0, st>>>(P);
   return cudaGetLastError();
 }

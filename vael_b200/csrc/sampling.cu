@@ -26,9 +26,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 }
 // Gumbel(0,1) = -log(E), E ~ Exp(1) = -log(U), U in (0,1]  (torch: -empty.exponential_().log())
 __device__ __forceinline__ float gumbel_from_bits(uint32_t bits) {
+  // the noise only has to be Gumbel-distributed, not bit-reproducible against a CPU libm: fast logarithms
   const float u = (static_cast<float>(bits >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0,1]
-  const float e = fmaxf(-logf(u), 1.17549435e-38f);
-  return -logf(e);
+  const float e = fmaxf(-__logf(u), 1.17549435e-38f);
+  return -__logf(e);
 }
 
 
@@ -42,21 +43,22 @@ __global__ void __launch_bounds__(256) gumbel_forward_kernel(const GumbelParams 
     float z[ITEMS];
     float mx = -INFINITY;
     int arg = 0x7fffffff;
+    uint32_t rnd[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
       const int e = lane + j * kWarp;
       z[j] = -INFINITY;
+      if (P.noise == nullptr && (j & 3) == 0) {
+        // one Philox4x32-10 call = the four random words of this lane's items j..j+3 (worlds lane + 32 j'):
+        // counter = (row, lane | block of four items), key = seed
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)(lane | ((j >> 2) << 5)), 0u),
+                                      make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+        rnd[0] = r.x; rnd[1] = r.y; rnd[2] = r.z; rnd[3] = r.w;
+      }
       if (e < P.W) {
         const float s = __ldg(P.scores + row * P.W + e);
         const float logit = P.is_log ? s : logf(s);
-        float g;
-        if (P.noise != nullptr) {
-          g = __ldg(P.noise + row * P.W + e);
-        } else {
-          const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)e, 0u),
-                                        make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
-          g = gumbel_from_bits(r.x);
-        }
+        const float g = (P.noise != nullptr) ? __ldg(P.noise + row * P.W + e) : gumbel_from_bits(rnd[j & 3]);
         z[j] = (logit + g) * inv_tau;
         if (z[j] > mx) { mx = z[j]; arg = e; }
       }
@@ -77,10 +79,11 @@ __global__ void __launch_bounds__(256) gumbel_forward_kernel(const GumbelParams 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     float ys_arg = 0.0f;
+    const float inv_sum = 1.0f / sum;
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
       const int e = lane + j * kWarp;
-      const float ys = z[j] / sum;
+      const float ys = z[j] * inv_sum;
       if (e < P.W) {
         if (P.y_soft != nullptr) P.y_soft[row * P.W + e] = ys;
         if (e == arg) ys_arg = ys;
@@ -198,8 +201,105 @@ cudaError_t gumbel_backward(const GumbelParams& P, int num_sms, cudaStream_t st)
 
 // ---------------------------------------------------------------------------
 // facts head: per group softmax, + eps, / detached sum   (models/vael.py:159-177)
-// one thread per (row, group); a group is `group` contiguous floats
+//
+// Structured kernels for the shapes VAEL uses (NG groups of N logits, N*NG floats per row): one warp per
+// 32-row tile, the contiguous [32, NG*N] tile is staged in shared memory with coalesced 128-bit accesses,
+// lane <-> row works on registers (compile-time indices), results go back through the same tile.
+// HBM-bound: 2 * NG*N*4 bytes per row forward, 3 * NG*N*4 backward (logits re-read, softmax recomputed).
+// Any other shape takes the generic one-thread-per-(row, group) kernels below.
 // ---------------------------------------------------------------------------
+template <int NG, int N>
+__device__ __forceinline__ void facts_row(const float* x, float eps, float* y, float* zs) {
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    float mx = x[g * N];
+#pragma unroll
+    for (int i = 1; i < N; ++i) mx = fmaxf(mx, x[g * N + i]);
+    float e[N], s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { e[i] = expf(x[g * N + i] - mx); s += e[i]; }
+    float zsum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { y[g * N + i] = e[i] / s; zsum += y[g * N + i] + eps; }
+    zs[g] = zsum;
+  }
+}
+
+template <int NG, int N, bool BWD>
+__global__ void __launch_bounds__(256) facts_tile_kernel(const float* __restrict__ logits,
+                                                         const float* __restrict__ grad_facts, long long B,
+                                                         float eps, float* __restrict__ out) {
+  constexpr int F = NG * N;
+  constexpr int PITCH = F | 1;  // odd pitch: lane <-> row accesses of the staged tile are conflict-free
+  extern __shared__ float tile_s[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* xs = tile_s + (size_t)warp * (BWD ? 2 : 1) * kWarp * PITCH;
+  float* gs = xs + kWarp * PITCH;
+  const long long n_sub = (B + kWarp - 1) / kWarp;
+  for (long long sub = (long long)blockIdx.x * nwarps + warp; sub < n_sub; sub += (long long)gridDim.x * nwarps) {
+    const long long row0 = sub * kWarp;
+    const int rows = (int)min((long long)kWarp, B - row0);
+    const int n = rows * F;
+    __syncwarp();
+    for (int i = lane; i < kWarp * F; i += kWarp) {   // coalesced: the tile is one contiguous span
+      const int r = i / F, c = i - r * F;               // F is a compile-time constant: mul-shift, no division
+      xs[r * PITCH + c] = (i < n) ? __ldg(logits + row0 * F + i) : 0.0f;
+      if (BWD) gs[r * PITCH + c] = (i < n) ? __ldg(grad_facts + row0 * F + i) : 0.0f;
+    }
+    __syncwarp();
+    float x[F], y[F], zs[NG];
+#pragma unroll
+    for (int c = 0; c < F; ++c) x[c] = xs[lane * PITCH + c];
+    facts_row<NG, N>(x, eps, y, zs);
+    if (!BWD) {
+#pragma unroll
+      for (int c = 0; c < F; ++c) xs[lane * PITCH + c] = (y[c] + eps) / zs[c / N];
+    } else {
+      // f = (y + eps) / Z with Z detached  ->  dL/dy_i = gf_i / Z ; softmax: dx_i = y_i (dy_i - sum_j y_j dy_j)
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        float dy[N], dot = 0.0f;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { dy[i] = gs[lane * PITCH + g * N + i] / zs[g]; dot = fmaf(y[g * N + i], dy[i], dot); }
+#pragma unroll
+        for (int i = 0; i < N; ++i) xs[lane * PITCH + g * N + i] = y[g * N + i] * (dy[i] - dot);
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += kWarp) {
+      const int r = i / F, c = i - r * F;
+      out[row0 * F + i] = xs[r * PITCH + c];
+    }
+  }
+}
+
+template <int NG, int N, bool BWD>
+static cudaError_t launch_facts_tile(const float* logits, const float* gf, long long B, float eps, float* out, int num_sms,
+                                     cudaStream_t st) {
+  constexpr int PITCH = (NG * N) | 1;
+  const int nw = 8;
+  const size_t smem = (size_t)nw * (BWD ? 2 : 1) * kWarp * PITCH * sizeof(float);
+  const long long n_sub = (B + kWarp - 1) / kWarp;
+  const int grid = (int)max(1LL, min((n_sub + nw - 1) / nw, (long long)num_sms * 4));
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(facts_tile_kernel<NG, N, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  facts_tile_kernel<NG, N, BWD><<<grid, nw * 32, smem, st>>>(logits, gf, B, eps, out);
+  return cudaGetLastError();
+}
+
+template <bool BWD>
+static bool facts_tile_dispatch(const float* logits, const float* gf, long long B, int n_groups, int group, float eps,
+                                float* out, int num_sms, cudaStream_t st, cudaError_t* err) {
+  if (n_groups == 2 && group == 10) { *err = launch_facts_tile<2, 10, BWD>(logits, gf, B, eps, out, num_sms, st); return true; }
+  if (n_groups == 3 && group == 10) { *err = launch_facts_tile<3, 10, BWD>(logits, gf, B, eps, out, num_sms, st); return true; }
+  if (n_groups == 2 && group == 9) { *err = launch_facts_tile<2, 9, BWD>(logits, gf, B, eps, out, num_sms, st); return true; }
+  if (n_groups == 1 && group == 9) { *err = launch_facts_tile<1, 9, BWD>(logits, gf, B, eps, out, num_sms, st); return true; }
+  return false;
+}
+
+// generic shapes: one thread per (row, group); a group is `group` contiguous floats
 __global__ void __launch_bounds__(256) facts_forward_kernel(const float* __restrict__ logits, long long n_groups_total,
                                                             int group, float eps, float* __restrict__ facts) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -247,6 +347,8 @@ __global__ void __launch_bounds__(256) facts_backward_kernel(const float* __rest
 
 cudaError_t facts_forward(const float* logits, long long B, int n_groups, int group, float eps, float* facts,
                           int num_sms, cudaStream_t st) {
+  cudaError_t e;
+  if (facts_tile_dispatch<false>(logits, nullptr, B, n_groups, group, eps, facts, num_sms, st, &e)) return e;
   const long long total = B * n_groups;
   const int grid = (int)max(1LL, min((total + 255) / 256, (long long)num_sms * 8));
   facts_forward_kernel<<<grid, 256, 0, st>>>(logits, total, group, eps, facts);
@@ -254,6 +356,8 @@ cudaError_t facts_forward(const float* logits, long long B, int n_groups, int gr
 }
 cudaError_t facts_backward(const float* logits, const float* grad_facts, long long B, int n_groups, int group,
                            float eps, float* grad_logits, int num_sms, cudaStream_t st) {
+  cudaError_t e;
+  if (facts_tile_dispatch<true>(logits, grad_facts, B, n_groups, group, eps, grad_logits, num_sms, st, &e)) return e;
   const long long total = B * n_groups;
   const int grid = (int)max(1LL, min((total + 255) / 256, (long long)num_sms * 8));
   facts_backward_kernel<<<grid, 256, 0, st>>>(logits, grad_facts, total, group, eps, grad_logits);

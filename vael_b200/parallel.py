@@ -66,3 +66,30 @@ def local_normaliser_note() -> str:
     (models/vael.py:263-266).  Under data parallelism that is the local shard's sum: it only
     shifts the Gumbel logits by a constant, so no collective is added for it."""
     return "shard-local"
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[str]:
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (sysfs `local_cpulist` of its PCI
+    function) BEFORE it allocates pinned host buffers: first-touch then places them next to the GPU's root
+    port, which is what the host-buffer (e2e) path needs when eight ranks stream over PCIe at once.
+    Returns the cpulist used, or None when the topology is not visible (containers may hide sysfs)."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        addr = f"{getattr(p, 'pci_domain_id', 0):04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{addr}/local_cpulist") as fh:
+            cpulist = fh.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpulist
+    except Exception:
+        return None

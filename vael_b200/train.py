@@ -114,13 +114,14 @@ class GraphedTrainStep:
     The optimizer must be capturable (torch.optim.Adam(..., capturable=True)).
     """
 
-    def __init__(self, model, optimizer, data_shape, labels_shape=None, device=None, warmup=3, **loss_kw):
+    def __init__(self, model, optimizer, data_shape, labels_shape=None, device=None, warmup=3,
+                 memory_format=torch.contiguous_format, **loss_kw):
         device = torch.device(device) if device is not None else next(model.parameters()).device
         if device.type != "cuda":
             raise RuntimeError("vael_b200: CUDA graphs need a CUDA device")
         self.model, self.optimizer, self.loss_kw = model, optimizer, loss_kw
         B = data_shape[0]
-        self.data = torch.zeros(data_shape, device=device)
+        self.data = torch.zeros(data_shape, device=device).contiguous(memory_format=memory_format)
         self.labels = torch.zeros(labels_shape or (B, 4), dtype=torch.long, device=device)
         model.graph_safe_rng = True
         side = torch.cuda.Stream(device=device)
