@@ -6,16 +6,24 @@
 // batch row (the reference's batch-wide `.any()` identity shortcuts, utils/graph_semiring.py:27-49,
 // are a documented divergence: see DESIGN.md "Parity domain").
 //
-// Execution model: a CTA owns a tile of 32 batch rows; lane <-> row.  Node values live in
-// shared memory node-major / row-minor (val[node][33]): every warp-wide access touches 32
-// consecutive words (conflict-free whatever the circuit shape; the odd pitch keeps the
-// transposed reads of the output phase conflict-free too).  The circuit is turned ONCE, at
-// vael_circuit_create, into a schedule: one 16-byte op per node with the children already
-// converted to shared-memory word offsets, ops sorted by kind inside each level.  Warps take
-// the ops of a level in groups of four; a group of four binary products / sums (the bulk of a
-// compiled program) runs as eight independent shared-memory loads, four FP ops, four stores —
-// no per-node branching — and the warps meet at one barrier per level.  Batch-major global
-// tensors are transposed on the way in/out with coalesced accesses (lane <-> world for [B,W]).
+// Execution model.  A CTA owns a tile of T = 32 R batch rows (R = 1, 2 or 4, chosen per circuit from its
+// shared-memory footprint).  A lane holds R rows (lane, lane + 32, ...) as one float / float2 / float4, so
+// node values live in shared memory node-major as val[node][lane] vectors: every warp-wide access is one
+// conflict-free LDS/STS of 32 consecutive vectors whatever the circuit shape, and one decoded op does R
+// rows' worth of arithmetic per lane — the interpreter's decode cost is amortised over 32 R rows.  The
+// circuit is turned ONCE, at vael_circuit_create, into a schedule: one 16-byte op per node with the
+// children already converted to shared-memory byte offsets, ops sorted by kind inside each level.  Warps
+// take the ops of a level in groups of four; a group of four binary products / sums (the bulk of a
+// compiled program) runs as eight independent shared-memory loads, 4 R FP ops, four stores — no per-node
+// branching — and the warps meet at one barrier per level.
+//
+// Batch-major global tensors never meet the node-major layout in global memory: a [T, K] tile of a
+// row-major [B, K] tensor is one contiguous span, moved by ONE bulk copy (cp.async.bulk, SASS UBLKCP)
+// between HBM and a row-major staging tile in shared memory (row-by-row bulk copies for column chunks of
+// wide tensors), loads completing on an mbarrier and prefetched one tile ahead, stores draining while the
+// next tile computes.  The row-major <-> node-major transposition happens shared-to-shared with 128-bit
+// accesses (lane <-> row on both sides).  Unaligned bases, K % 4 != 0 chunks and the tail tile take a
+// plain coalesced copy through the same staging tile.
 //
 // The backward is the reverse sweep in GATHER form over per-child parent records (built at
 // creation, dead cones — nodes no output depends on — pruned), so it needs no atomics, no
@@ -28,9 +36,6 @@
 
 namespace vael {
 
-constexpr int PITCH = 33;
-constexpr int PB = PITCH * 4;  // bytes per node row; every offset in the schedule is a BYTE offset into the tile
-
 enum : int {
   OP_LEAF_POS = 0, OP_LEAF_NEG, OP_CONST, OP_MUL2, OP_ADD2, OP_COMPL2, OP_COPY, OP_COMPL1, OP_PRODN, OP_SUMN,
   OP_COMPLN, OP_IDENT_ONE, OP_IDENT_ZERO
@@ -39,14 +44,21 @@ enum : int {
 enum : int { PR_ADD = 0, PR_SUB, PR_MUL_SIB, PR_MUL_SIBS, PR_LSE };
 
 // ---- device-resident schedule ------------------------------------------------
+// Every offset in the schedule is a BYTE offset of a node row inside a value / adjoint tile whose rows are
+// 128 R bytes; the forward and the backward kernel may run with different R (rf, rb).
 struct GenProgram {
   int32_t n_nodes, n_facts, n_worlds, n_queries, n_levels, semiring, norm_node, n_bvals;
+  int32_t rf, rb;          // rows per lane of the forward / backward kernel
+  int32_t cf, cb;          // staged columns per chunk: worlds (forward) / grad_worlds (backward)
+  int32_t cq;              // column capacity of the forward staging tile (>= cf; queries_all chunks)
+  int32_t leaf_levels_f[2], leaf_levels_b;  // levels [0, leaf_levels) hold every leaf op of the schedule
+  int32_t n_levels_f[2];   // levels of the forward schedule up to its last non-empty one
   // forward.  The value tile has n_nodes + 2 rows: the last two hold the constants 0 and 1 the padded
   // child lists point at.
-  int4* ops;               // {dst, a, b, kind | nc << 8}; n-ary ops: a = first edge (multiple of 4), b = padded length
+  int4* ops;               // {dst, a, b, kind | nc << 8}; leaves: a = fact column; n-ary ops: a = first edge (multiple of 4), b = padded length
   int32_t* edges;          // child offsets of the n-ary ops
-  int32_t op_level_ptr[kMaxLevels + 1];
-  int32_t* world_off;      // [W]
+  int32_t op_level_ptr[2][kMaxLevels + 1];  // [0]: every node; [1]: without the cone only the normaliser needs
+  int32_t* world_off;      // [W] (padded to a multiple of 4)
   int32_t* query_off;      // [Q]
   // backward: forward values of the nodes the adjoint needs (slot space, + the two constant rows), then the
   // reverse sweep over the adjoint tile (n_nodes rows + one scratch row for the padding records)
@@ -57,10 +69,11 @@ struct GenProgram {
   int4* crec;              // live children, level by level: {adj off, first record, n records, flags}
   int32_t cl_ptr[kMaxLevels + 1];
   int2* prec;              // parent records {parent adj off << 1 | kind, x} (+ one more int2 for kinds 3, 4)
-  int32_t* wseed_off;      // [W] adjoint offsets of the world nodes
-  int32_t* qseed_off;      // [Q] adjoint offsets of the query nodes
-  int32_t* zero_off;       // adjoint rows to clear per tile (query nodes that are not world nodes)
-  int32_t n_zero;
+  int32_t* wseed_off;      // [W] adjoint offsets of the world nodes (padded to a multiple of 4)
+  int32_t* qseed_off;      // [Q] adjoint offsets of the query nodes, | 1 when the node is also a world node
+  int32_t* qonly_off;      // adjoint rows of the query nodes that are not world nodes (seeded by assignment)
+  int32_t n_qonly;
+  int32_t q_world_any;     // some query node is also a world node (its seed is added after the world seeds)
   int2* leaf_rec;          // per fact column: live leaves {adj off, +1 / -1}
   int32_t* leaf_ptr;       // [F+1]
   size_t fwd_smem, bwd_smem;
@@ -73,42 +86,146 @@ struct GenArgs {
   GenCall C;
 };
 
-// value of row `idx` (lane or batch row) of the node at byte offset `off`
-__device__ __forceinline__ float& VB(float* base, int off, int idx) {
-  return *reinterpret_cast<float*>(reinterpret_cast<char*>(base + idx) + off);
+// ---- R rows per lane ----------------------------------------------------------------------------------
+template <int R> struct VecT;
+template <> struct VecT<1> { float v[1]; };
+template <> struct __align__(8) VecT<2> { float v[2]; };
+template <> struct __align__(16) VecT<4> { float v[4]; };
+
+// `lb` = tile base + lane * R floats; `off` = byte offset of the node row
+template <int R>
+__device__ __forceinline__ VecT<R> ldv(const float* lb, int off) {
+  return *reinterpret_cast<const VecT<R>*>(reinterpret_cast<const char*>(lb) + off);
 }
-__device__ __forceinline__ float VB(const float* base, int off, int idx) {
-  return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(base + idx) + off);
+template <int R>
+__device__ __forceinline__ void stv(float* lb, int off, const VecT<R>& x) {
+  *reinterpret_cast<VecT<R>*>(reinterpret_cast<char*>(lb) + off) = x;
+}
+template <int R>
+__device__ __forceinline__ VecT<R> vfill(float c) {
+  VecT<R> o;
+#pragma unroll
+  for (int j = 0; j < R; ++j) o.v[j] = c;
+  return o;
+}
+template <int R>
+__device__ __forceinline__ VecT<R> vmul_rn(const VecT<R>& a, const VecT<R>& b) {
+  VecT<R> o;
+#pragma unroll
+  for (int j = 0; j < R; ++j) o.v[j] = __fmul_rn(a.v[j], b.v[j]);
+  return o;
+}
+template <int R>
+__device__ __forceinline__ VecT<R> vadd_rn(const VecT<R>& a, const VecT<R>& b) {
+  VecT<R> o;
+#pragma unroll
+  for (int j = 0; j < R; ++j) o.v[j] = __fadd_rn(a.v[j], b.v[j]);
+  return o;
+}
+template <int R>
+__device__ __forceinline__ VecT<R> vcompl_rn(const VecT<R>& a) {
+  VecT<R> o;
+#pragma unroll
+  for (int j = 0; j < R; ++j) o.v[j] = __fsub_rn(1.0f, a.v[j]);
+  return o;
+}
+template <int R>
+__device__ __forceinline__ VecT<R> vfma(const VecT<R>& a, const VecT<R>& b, const VecT<R>& c) {
+  VecT<R> o;
+#pragma unroll
+  for (int j = 0; j < R; ++j) o.v[j] = fmaf(a.v[j], b.v[j], c.v[j]);
+  return o;
+}
+
+// ---- staged I/O: [rows, cc] chunk (columns c0 .. c0+cc) of a row-major [B, K] tensor <-> stage[r * cc + c] ----
+// mode 0: plain coalesced copy by all threads; 1: the chunk is the whole contiguous tile, one bulk copy;
+// 2: one bulk copy per row.  The mode is CTA-uniform.
+__device__ __forceinline__ int io_mode(const void* g, int rows, int T, int K, int c0, int cc) {
+  if (!aligned16(g) || rows != T) return 0;
+  if (cc == K) return 1;  // T * K * 4 bytes: a multiple of 128
+  if (((K | c0 | cc) & 3) == 0) return 2;
+  return 0;
+}
+// returns true when the data arrives asynchronously on `bar` (wait on it), false when the caller only needs a
+// __syncthreads() before reading the stage
+__device__ __forceinline__ bool stage_load(float* stage, const float* g, long long row0, int rows, int T, int K,
+                                           int c0, int cc, uint64_t* bar, float fill) {
+  const int mode = io_mode(g, rows, T, K, c0, cc);
+  const uint32_t bytes = (uint32_t)T * cc * 4u;
+  if (mode == 1) {
+    if (threadIdx.x == 0) {
+      mbar_arrive_expect_tx(bar, bytes);
+      bulk_g2s(stage, g + row0 * K, bytes, bar);
+    }
+    return true;
+  }
+  if (mode == 2) {
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, bytes);
+    for (int r = threadIdx.x; r < T; r += blockDim.x) bulk_g2s(stage + r * cc, g + (row0 + r) * K + c0, cc * 4u, bar);
+    return true;
+  }
+  for (int r = threadIdx.x / cc, c = threadIdx.x - r * cc; r < T;) {
+    stage[r * cc + c] = (r < rows) ? __ldg(g + (row0 + r) * K + c0 + c) : fill;
+    c += blockDim.x;
+    while (c >= cc) { c -= cc; ++r; }
+  }
+  return false;
+}
+// every thread has executed fence_proxy_async() + __syncthreads() after the last write to `stage`
+__device__ __forceinline__ void stage_store(const float* stage, float* g, long long row0, int rows, int T, int K,
+                                            int c0, int cc) {
+  const int mode = io_mode(g, rows, T, K, c0, cc);
+  if (mode == 1) {
+    if (threadIdx.x == 0) {
+      bulk_s2g(g + row0 * K, stage, (uint32_t)T * cc * 4u);
+      bulk_commit();
+    }
+  } else if (mode == 2) {
+    for (int r = threadIdx.x; r < T; r += blockDim.x) bulk_s2g(g + (row0 + r) * K + c0, stage + r * cc, cc * 4u);
+    bulk_commit();
+  } else {
+    for (int r = threadIdx.x / cc, c = threadIdx.x - r * cc; r < rows;) {
+      g[(row0 + r) * K + c0 + c] = stage[r * cc + c];
+      c += blockDim.x;
+      while (c >= cc) { c -= cc; ++r; }
+    }
+  }
 }
 
 // ---- forward op execution (any kind; the grouped fast paths are in run_level) ------------------
-template <bool LOG>
-__device__ __forceinline__ float exec_op(const int4 d, const float* fs, const float* val, const int32_t* edges,
-                                         int lane) {
+template <int R, bool LOG>
+__device__ __forceinline__ VecT<R> leaf_value(const float* fs, int F, int col, bool neg, int lane) {
+  VecT<R> o;
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    float p = fs[(lane + 32 * j) * F + col];
+    if (neg) p = __fsub_rn(1.0f, p);
+    o.v[j] = LOG ? logf(p) : p;
+  }
+  return o;
+}
+
+template <int R, bool LOG>
+__device__ __forceinline__ VecT<R> exec_op(const int4 d, const float* fs, int F, const float* vl,
+                                           const int32_t* edges, int lane) {
   const int kind = d.w & 0xff, nc = d.w >> 8;
   switch (kind) {
-    case OP_LEAF_POS: {
-      const float p = VB(fs, d.y, lane);
-      return LOG ? logf(p) : p;
-    }
-    case OP_LEAF_NEG: {
-      const float p = __fsub_rn(1.0f, VB(fs, d.y, lane));
-      return LOG ? logf(p) : p;
-    }
-    case OP_CONST: return __int_as_float(d.y);
+    case OP_LEAF_POS: return leaf_value<R, LOG>(fs, F, d.y, false, lane);
+    case OP_LEAF_NEG: return leaf_value<R, LOG>(fs, F, d.y, true, lane);
+    case OP_CONST: return vfill<R>(__int_as_float(d.y));
     case OP_MUL2: {
-      const float x = VB(val, d.y, lane), y = VB(val, d.z, lane);
-      return LOG ? __fadd_rn(x, y) : __fmul_rn(x, y);
+      const VecT<R> x = ldv<R>(vl, d.y), y = ldv<R>(vl, d.z);
+      return LOG ? vadd_rn<R>(x, y) : vmul_rn<R>(x, y);
     }
-    case OP_COPY: return VB(val, d.y, lane);
-    case OP_COMPL1: return __fsub_rn(1.0f, VB(val, d.y, lane));
-    case OP_IDENT_ONE: return LOG ? 0.0f : 1.0f;
-    case OP_IDENT_ZERO: return LOG ? -INFINITY : 0.0f;
+    case OP_COPY: return ldv<R>(vl, d.y);
+    case OP_COMPL1: return vcompl_rn<R>(ldv<R>(vl, d.y));
+    case OP_IDENT_ONE: return vfill<R>(LOG ? 0.0f : 1.0f);
+    case OP_IDENT_ZERO: return vfill<R>(LOG ? -INFINITY : 0.0f);
     case OP_PRODN: {
-      float acc = VB(val, __ldg(edges + d.y), lane);
+      VecT<R> acc = ldv<R>(vl, __ldg(edges + d.y));
       for (int e = 1; e < nc; ++e) {
-        const float v = VB(val, __ldg(edges + d.y + e), lane);
-        acc = LOG ? __fadd_rn(acc, v) : __fmul_rn(acc, v);
+        const VecT<R> v = ldv<R>(vl, __ldg(edges + d.y + e));
+        acc = LOG ? vadd_rn<R>(acc, v) : vmul_rn<R>(acc, v);
       }
       return acc;
     }
@@ -116,295 +233,465 @@ __device__ __forceinline__ float exec_op(const int4 d, const float* fs, const fl
   }
   // sums (ADD2 / SUMN) and complements (COMPL2 / COMPLN)
   if constexpr (!LOG) {
-    float acc;
+    VecT<R> acc;
     if (kind == OP_ADD2 || kind == OP_COMPL2) {
-      acc = __fadd_rn(VB(val, d.y, lane), VB(val, d.z, lane));
+      acc = vadd_rn<R>(ldv<R>(vl, d.y), ldv<R>(vl, d.z));
     } else {
-      acc = VB(val, __ldg(edges + d.y), lane);
-      for (int e = 1; e < nc; ++e) acc = __fadd_rn(acc, VB(val, __ldg(edges + d.y + e), lane));
+      acc = ldv<R>(vl, __ldg(edges + d.y));
+      for (int e = 1; e < nc; ++e) acc = vadd_rn<R>(acc, ldv<R>(vl, __ldg(edges + d.y + e)));
     }
-    return (kind == OP_COMPL2 || kind == OP_COMPLN) ? __fsub_rn(1.0f, acc) : acc;
+    return (kind == OP_COMPL2 || kind == OP_COMPLN) ? vcompl_rn<R>(acc) : acc;
   } else {  // logsumexp (COMPL is rejected for the log semiring at circuit creation)
-    float mx = -INFINITY;
+    VecT<R> mx = vfill<R>(-INFINITY);
     for (int e = 0; e < nc; ++e) {
       const int c = (kind == OP_ADD2) ? (e == 0 ? d.y : d.z) : __ldg(edges + d.y + e);
-      mx = fmaxf(mx, VB(val, c, lane));
+      const VecT<R> v = ldv<R>(vl, c);
+#pragma unroll
+      for (int j = 0; j < R; ++j) mx.v[j] = fmaxf(mx.v[j], v.v[j]);
     }
-    if (mx == -INFINITY) return -INFINITY;
-    float s = 0.0f;
+    VecT<R> s = vfill<R>(0.0f);
     for (int e = 0; e < nc; ++e) {
       const int c = (kind == OP_ADD2) ? (e == 0 ? d.y : d.z) : __ldg(edges + d.y + e);
-      s += expf(VB(val, c, lane) - mx);
+      const VecT<R> v = ldv<R>(vl, c);
+#pragma unroll
+      for (int j = 0; j < R; ++j) s.v[j] += expf(v.v[j] - mx.v[j]);
     }
-    return mx + logf(s);
+    VecT<R> o;
+#pragma unroll
+    for (int j = 0; j < R; ++j) o.v[j] = (mx.v[j] == -INFINITY) ? -INFINITY : mx.v[j] + logf(s.v[j]);
+    return o;
   }
 }
 
-// One level of ops.  Warps take the ops in groups of four (levels are padded to a multiple of four with copies
-// of their last op: recomputing a node is harmless).  A group whose four ops have the same kind runs branch-free:
-// eight independent shared-memory loads, four FP ops, four stores for binary ops; four left folds side by side
-// for n-ary ones (each fold sequential in CSR order, so the result is bit-exact; the four child lists of such a
-// group are padded to one length with pointers to the constant-0 / constant-1 rows).
-template <bool LOG>
-__device__ __forceinline__ void run_level(const int4* __restrict__ ops, const int32_t* __restrict__ edges, int beg,
-                                          int end, const float* fs, float* val, int warp, int nwarps, int lane) {
-  for (int g = beg + 4 * warp; g < end; g += 4 * nwarps) {
-    int4 d[4];
+// One level of ops.  The schedule lays the ops of a level out in groups of four of the same kind (levels are
+// padded to a multiple of four with copies of their last op: recomputing a node is harmless; the four child lists
+// of a group of n-ary ops are padded to one length with pointers to the constant-0 / constant-1 rows).  Warps take
+// G = 4 / R ops at a time — with R rows per lane one op already carries R independent chains — and fetch the next
+// group's records before executing the current one.  A group whose ops have the same kind runs branch-free: 2 G
+// independent shared-memory loads, G R FP ops, G stores for binary ops; G left folds side by side for n-ary ones
+// (each fold sequential in CSR order, so the result is bit-exact).
+template <int R, int G, bool LOG>
+__device__ __forceinline__ void exec_group(const int4 (&d)[G], const int32_t* __restrict__ edges, const float* fs, int F,
+                                           float* vl, int lane) {
+  const int k0 = d[0].w & 0xff;
+  bool same = true;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) d[u] = __ldg(ops + g + u);
-    const int k0 = d[0].w & 0xff;
-    const bool same = (d[1].w & 0xff) == k0 && (d[2].w & 0xff) == k0 && (d[3].w & 0xff) == k0;
-    if (same && k0 == OP_MUL2) {
-      float x[4], y[4];
+  for (int u = 1; u < G; ++u) same = same && (d[u].w & 0xff) == k0;
+  if (same && (k0 == OP_MUL2 || (!LOG && k0 == OP_ADD2))) {
+    VecT<R> x[G], y[G];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { x[u] = VB(val, d[u].y, lane); y[u] = VB(val, d[u].z, lane); }
+    for (int u = 0; u < G; ++u) { x[u] = ldv<R>(vl, d[u].y); y[u] = ldv<R>(vl, d[u].z); }
+    const bool adds = LOG || k0 == OP_ADD2;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) VB(val, d[u].x, lane) = LOG ? __fadd_rn(x[u], y[u]) : __fmul_rn(x[u], y[u]);
-    } else if (!LOG && same && k0 == OP_ADD2) {
-      float x[4], y[4];
+    for (int u = 0; u < G; ++u) stv<R>(vl, d[u].x, adds ? vadd_rn<R>(x[u], y[u]) : vmul_rn<R>(x[u], y[u]));
+    return;
+  }
+  if (same && k0 <= OP_LEAF_NEG) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { x[u] = VB(val, d[u].y, lane); y[u] = VB(val, d[u].z, lane); }
+    for (int u = 0; u < G; ++u) stv<R>(vl, d[u].x, leaf_value<R, LOG>(fs, F, d[u].y, k0 == OP_LEAF_NEG, lane));
+    return;
+  }
+  if (same && (k0 == OP_PRODN || (!LOG && k0 == OP_SUMN))) {
+    bool same_len = true;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) VB(val, d[u].x, lane) = __fadd_rn(x[u], y[u]);
-    } else if (same && k0 <= OP_LEAF_NEG) {
-      float p[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) p[u] = VB(fs, d[u].y, lane);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float v = k0 == OP_LEAF_NEG ? __fsub_rn(1.0f, p[u]) : p[u];
-        VB(val, d[u].x, lane) = LOG ? logf(v) : v;
-      }
-    } else if (same && (k0 == OP_PRODN || (!LOG && k0 == OP_SUMN))) {
+    for (int u = 1; u < G; ++u) same_len = same_len && d[u].z == d[0].z;
+    if (same_len) {
       const bool adds = LOG || k0 == OP_SUMN;     // log-semiring product = sum of logs
-      const int len = d[0].z;                     // group-uniform padded length (multiple of four)
-      float acc[4];
+      const int len = d[0].z;                     // padded length (multiple of four)
+      VecT<R> acc[G];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) acc[u] = adds ? 0.0f : 1.0f;  // 0 + x and 1 * x are exact
+      for (int u = 0; u < G; ++u) acc[u] = vfill<R>(adds ? 0.0f : 1.0f);  // 0 + x and 1 * x are exact
       for (int e = 0; e < len; e += 4) {
-        int4 c[4];
+        int4 c[G];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) c[u] = __ldg(reinterpret_cast<const int4*>(edges + d[u].y + e));
+        for (int u = 0; u < G; ++u) c[u] = __ldg(reinterpret_cast<const int4*>(edges + d[u].y + e));
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float v0 = VB(val, c[u].x, lane), v1 = VB(val, c[u].y, lane), v2 = VB(val, c[u].z, lane),
-                      v3 = VB(val, c[u].w, lane);
+        for (int u = 0; u < G; ++u) {
+          const VecT<R> v0 = ldv<R>(vl, c[u].x), v1 = ldv<R>(vl, c[u].y), v2 = ldv<R>(vl, c[u].z),
+                        v3 = ldv<R>(vl, c[u].w);
           if (adds) {
-            acc[u] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc[u], v0), v1), v2), v3);
+            acc[u] = vadd_rn<R>(vadd_rn<R>(vadd_rn<R>(vadd_rn<R>(acc[u], v0), v1), v2), v3);
           } else {
-            acc[u] = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(acc[u], v0), v1), v2), v3);
+            acc[u] = vmul_rn<R>(vmul_rn<R>(vmul_rn<R>(vmul_rn<R>(acc[u], v0), v1), v2), v3);
           }
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) VB(val, d[u].x, lane) = acc[u];
-    } else {
-      for (int u = 0; u < 4; ++u) VB(val, d[u].x, lane) = exec_op<LOG>(d[u], fs, val, edges, lane);
+      for (int u = 0; u < G; ++u) stv<R>(vl, d[u].x, acc[u]);
+      return;
     }
   }
+#pragma unroll
+  for (int u = 0; u < G; ++u) stv<R>(vl, d[u].x, exec_op<R, LOG>(d[u], fs, F, vl, edges, lane));
 }
 
-// transposed load of the facts tile: global [rows,F] row-major -> fs[f][r]; warps take rows, lanes take fact
-// columns (a row is F contiguous floats, consecutive rows are contiguous: every sector is fully used)
-__device__ __forceinline__ void load_facts_tile(float* fs, const float* facts, long long row0, int rows, int F,
-                                                int warp, int nwarps, int lane) {
-  const float* src = facts + (row0 + warp) * F + lane;
-  float* dst = fs + lane * PITCH + warp;
-  const int sstep = nwarps * F;
-  for (int r = warp; r < kWarp; r += nwarps, src += sstep, dst += nwarps) {
-    for (int f = lane, k = 0; f < F; f += kWarp, k += kWarp)
-      dst[k * PITCH] = (r < rows) ? __ldg(src + k) : 0.5f;  // padding rows get a harmless in-domain value
+template <int R, bool LOG>
+__device__ __forceinline__ void run_level(const int4* __restrict__ ops, const int32_t* __restrict__ edges, int beg,
+                                          int end, const float* fs, int F, float* vl, int warp, int nwarps,
+                                          int lane) {
+  constexpr int G = 4 / R;
+  int g = beg + G * warp;
+  if (g >= end) return;
+  int4 d[G];
+#pragma unroll
+  for (int u = 0; u < G; ++u) d[u] = __ldg(ops + g + u);
+  while (true) {
+    const int gn = g + G * nwarps;
+    int4 dn[G];
+    if (gn < end) {
+#pragma unroll
+      for (int u = 0; u < G; ++u) dn[u] = __ldg(ops + gn + u);
+    }
+    exec_group<R, G, LOG>(d, edges, fs, F, vl, lane);
+    if (gn >= end) break;
+#pragma unroll
+    for (int u = 0; u < G; ++u) d[u] = dn[u];
+    g = gn;
   }
 }
 
 // the two constant rows behind the node rows (written once per CTA; nothing ever overwrites them)
-__device__ __forceinline__ void init_const_rows(float* val, int n_rows) {
-  if (threadIdx.x < kWarp) {
-    val[n_rows * PITCH + threadIdx.x] = 0.0f;
-    val[(n_rows + 1) * PITCH + threadIdx.x] = 1.0f;
+__device__ __forceinline__ void init_const_rows(float* val, int n_rows, int T) {
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    val[n_rows * T + i] = 0.0f;
+    val[(n_rows + 1) * T + i] = 1.0f;
   }
 }
 
 // ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
-template <bool LOG>
+template <int R, bool LOG>
 __global__ void __launch_bounds__(512) generic_forward_kernel(const GenArgs A) {
+  constexpr int T = 32 * R;
   const GenProgram& P = A.G;
   const GenCall& C = A.C;
-  extern __shared__ __align__(16) float gsm[];
-  float* fs = gsm;                        // [F][PITCH]
-  float* val = gsm + P.n_facts * PITCH;   // [n_nodes + 2][PITCH]
-  __shared__ float es[kWarp];             // evidence mode: P(e) per row
-  __shared__ int eq[kWarp];               //                query index per row (-1 = none)
+  extern __shared__ __align__(16) unsigned char gsm_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(gsm_raw);        // facts tile
+  float* val = reinterpret_cast<float*>(gsm_raw + 16);          // [n_nodes + 2][T]
+  float* fs = val + (P.n_nodes + 2) * T;                        // [T][F] row-major staging
+  float* out = fs + T * P.n_facts;                              // [T][<= cf] row-major staging
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const long long n_tiles = (C.B + kWarp - 1) / kWarp;
+  float* vl = val + lane * R;
+  const long long n_tiles = (C.B + T - 1) / T;
   const bool norm = (C.flags & VAEL_FLAG_NORMALIZE) && P.norm_node >= 0;
   const bool evid = (C.flags & VAEL_FLAG_EVIDENCE) != 0;
-  const int zoff = P.norm_node * PB;
-  const int W = P.n_worlds;
-  init_const_rows(val, P.n_nodes);
+  const int zoff = P.norm_node * (T * 4);
+  const int W = P.n_worlds, F = P.n_facts, Q = P.n_queries;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  init_const_rows(val, P.n_nodes, T);
+  __syncthreads();
 
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long row0 = tile * kWarp;
-    const int rows = (int)min((long long)kWarp, C.B - row0);
-    load_facts_tile(fs, C.facts, row0, rows, P.n_facts, warp, nwarps, lane);
-    __syncthreads();
-    for (int L = 0; L < P.n_levels; ++L) {
-      run_level<LOG>(P.ops, P.edges, P.op_level_ptr[L], P.op_level_ptr[L + 1], fs, val, warp, nwarps, lane);
+  // forward schedule: every node when Z is asked for, else without the cone only the normaliser needs
+  const int sch = norm ? 0 : 1;
+  const int32_t* lptr = P.op_level_ptr[sch];
+  const int n_lev = P.n_levels_f[sch], leaf_lev = P.leaf_levels_f[sch];
+  const bool need_q = C.query != nullptr || evid;
+
+  long long tile = blockIdx.x;
+  bool f_async = false;
+  uint32_t ph = 0;
+  if (tile < n_tiles)
+    f_async = stage_load(fs, C.facts, tile * T, (int)min((long long)T, C.B - tile * T), T, F, 0, F, bar, 0.5f);
+
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const long long row0 = tile * T;
+    const int rows = (int)min((long long)T, C.B - row0);
+    // per-row query index (lane <-> rows lane + 32 j), requested before the levels so that its HBM latency hides
+    int32_t qrow[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int r = lane + 32 * j;
+      qrow[j] = (need_q && r < rows) ? (C.qidx ? __ldg(C.qidx + row0 + r) : C.qscalar) : -1;
+    }
+    if (f_async) { mbar_wait(bar, ph); ph ^= 1; } else __syncthreads();
+    for (int L = 0; L < n_lev; ++L) {
+      run_level<R, LOG>(P.ops, P.edges, lptr[L], lptr[L + 1], fs, F, vl, warp, nwarps, lane);
+      if (L == n_lev - 1) bulk_wait_read<0>();   // the previous tile's stores have finished reading the staging tile
       __syncthreads();
+      if (L == leaf_lev - 1) {  // the facts tile is consumed: fetch the next one behind the remaining levels
+        const long long nt = tile + gridDim.x;
+        if (nt < n_tiles)
+          f_async = stage_load(fs, C.facts, nt * T, (int)min((long long)T, C.B - nt * T), T, F, 0, F, bar, 0.5f);
+      }
     }
 
-    // ---- outputs: lane <-> world (chunks of 32 worlds), warps take rows; 128-byte coalesced stores ----
-    if (C.worlds != nullptr) {
-      if (evid) {  // per-row evidence value and query index, staged once per tile
-        if (warp == 0) {
-          const long long row = row0 + lane;
-          const int32_t q = (lane < rows) ? (C.qidx ? __ldg(C.qidx + row) : C.qscalar) : -1;
-          const bool qok = q >= 0 && q < P.n_queries;
-          es[lane] = qok ? VB(val, __ldg(P.query_off + q), lane) : 0.0f;
-          eq[lane] = qok ? q : -1;
-        }
-        __syncthreads();
+    VecT<R> z = vfill<R>(1.0f);
+    if (norm) z = ldv<R>(vl, zoff);
+    float qv[R];   // value of the row's query node (0 when the row has no valid query)
+    if (need_q) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        if (qrow[j] < 0 || qrow[j] >= Q) qrow[j] = -1;
+        qv[j] = qrow[j] >= 0 ? vl[(__ldg(P.query_off + qrow[j]) >> 2) + j] : 0.0f;
       }
-      const size_t ostep = (size_t)nwarps * W;
-      for (int e0 = 0; e0 < W; e0 += kWarp) {
-        const int e = e0 + lane;
-        if (e < W) {
-          const float* v = reinterpret_cast<const float*>(reinterpret_cast<const char*>(val) + __ldg(P.world_off + e)) + warp;
-          float* o = C.worlds + (row0 + warp) * W + e;
-          if (!norm && !evid) {
-#pragma unroll 4
-            for (int r = warp; r < rows; r += nwarps, v += nwarps, o += ostep) *o = *v;
-          } else if (!evid) {
-            const float* zr = reinterpret_cast<const float*>(reinterpret_cast<const char*>(val) + zoff) + warp;
-            for (int r = warp; r < rows; r += nwarps, v += nwarps, zr += nwarps, o += ostep) *o = *v / *zr;
-          } else {
-            for (int r = warp; r < rows; r += nwarps, v += nwarps, o += ostep) {
-              const int q = eq[r];
-              const uint32_t mword = q >= 0 ? __ldg(C.qmask + (long long)q * C.mask_words + (e0 >> 5)) : 0u;
-              *o = ((mword >> lane) & 1u) ? *v / es[r] : 0.0f;
+    }
+    if (C.query != nullptr && warp == nwarps - 1) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const int r = lane + 32 * j;
+        if (r < rows) C.query[row0 + r] = norm ? qv[j] / z.v[j] : qv[j];
+      }
+    }
+
+    // ---- worlds: node-major -> row-major staging (chunks of cf columns) -> bulk store ----
+    bool stored = false;
+    if (C.worlds != nullptr) {
+      for (int c0 = 0; c0 < W; c0 += P.cf) {
+        const int cc = min(P.cf, W - c0);
+        if (stored) {   // the staging tile is still being read by the previous chunk's store
+          bulk_wait_read<0>();
+          __syncthreads();
+        }
+        if ((cc & 3) == 0) {
+          for (int g = warp; g < (cc >> 2); g += nwarps) {
+            const int w = c0 + 4 * g;
+            const int4 off = __ldg(reinterpret_cast<const int4*>(P.world_off + w));
+            const VecT<R> a0 = ldv<R>(vl, off.x), a1 = ldv<R>(vl, off.y), a2 = ldv<R>(vl, off.z), a3 = ldv<R>(vl, off.w);
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+              float4 o = make_float4(a0.v[j], a1.v[j], a2.v[j], a3.v[j]);
+              if (evid) {
+                const uint32_t mword = qrow[j] >= 0 ? __ldg(C.qmask + (long long)qrow[j] * C.mask_words + (w >> 5)) : 0u;
+                const uint32_t m = mword >> (w & 31);
+                o.x = (m & 1u) ? o.x / qv[j] : 0.0f;
+                o.y = (m & 2u) ? o.y / qv[j] : 0.0f;
+                o.z = (m & 4u) ? o.z / qv[j] : 0.0f;
+                o.w = (m & 8u) ? o.w / qv[j] : 0.0f;
+              } else if (norm) {
+                o.x = o.x / z.v[j]; o.y = o.y / z.v[j]; o.z = o.z / z.v[j]; o.w = o.w / z.v[j];
+              }
+              *reinterpret_cast<float4*>(out + (lane + 32 * j) * cc + 4 * g) = o;
+            }
+          }
+        } else {
+          for (int c = warp; c < cc; c += nwarps) {
+            const int w = c0 + c;
+            const VecT<R> a = ldv<R>(vl, __ldg(P.world_off + w));
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+              float o = a.v[j];
+              if (evid) {
+                const uint32_t mword = qrow[j] >= 0 ? __ldg(C.qmask + (long long)qrow[j] * C.mask_words + (w >> 5)) : 0u;
+                o = ((mword >> (w & 31)) & 1u) ? o / qv[j] : 0.0f;
+              } else if (norm) {
+                o = o / z.v[j];
+              }
+              out[(lane + 32 * j) * cc + c] = o;
             }
           }
         }
+        fence_proxy_async();
+        __syncthreads();
+        stage_store(out, C.worlds, row0, rows, T, W, c0, cc);
+        stored = true;
       }
     }
+    // ---- every query node of every row ----
     if (C.queries_all != nullptr) {
-      for (int r = warp; r < rows; r += nwarps) {
-        const long long row = row0 + r;
-        const float z = norm ? VB(val, zoff, r) : 1.0f;
-        for (int q = lane; q < P.n_queries; q += kWarp) {
-          float v = VB(val, __ldg(P.query_off + q), r);
-          if (norm) v = v / z;
-          C.queries_all[row * P.n_queries + q] = v;
+      const int qchunk = Q <= P.cq ? Q : (P.cq & ~3);
+      for (int c0 = 0; c0 < Q; c0 += qchunk) {
+        const int cc = min(qchunk, Q - c0);
+        if (stored) {
+          bulk_wait_read<0>();
+          __syncthreads();
         }
+        for (int c = warp; c < cc; c += nwarps) {
+          const VecT<R> a = ldv<R>(vl, __ldg(P.query_off + c0 + c));
+#pragma unroll
+          for (int j = 0; j < R; ++j) out[(lane + 32 * j) * cc + c] = norm ? a.v[j] / z.v[j] : a.v[j];
+        }
+        fence_proxy_async();
+        __syncthreads();
+        stage_store(out, C.queries_all, row0, rows, T, Q, c0, cc);
+        stored = true;
       }
     }
-    if (C.query != nullptr && warp == nwarps - 1 && lane < rows) {
-      const long long row = row0 + lane;
-      const int32_t q = C.qidx ? __ldg(C.qidx + row) : C.qscalar;
-      float v = 0.0f;
-      if (q >= 0 && q < P.n_queries) {
-        v = VB(val, __ldg(P.query_off + q), lane);
-        if (norm) v = v / VB(val, zoff, lane);
-      }
-      C.query[row] = v;
-    }
-    __syncthreads();
+    // every read of the value tile lies before the barrier in front of the last store; without a store the
+    // tile still has to be released for the next tile's leaves
+    if (!stored) __syncthreads();
   }
+  bulk_wait_all<0>();
 }
 
 // ---------------------------------------------------------------------------
 // backward: forward values of the nodes the adjoint needs, then the reverse sweep
 // ---------------------------------------------------------------------------
-template <bool LOG>
-__device__ __forceinline__ float apply_rec(float a, const int2* __restrict__ prec, int i, const float* val,
-                                           const float* adj, const int32_t* __restrict__ bedges, int lane) {
+template <int R, bool LOG>
+__device__ __forceinline__ VecT<R> apply_rec(VecT<R> a, const int2* __restrict__ prec, int i, const float* vl,
+                                             const float* al, const int32_t* __restrict__ bedges) {
   const int2 rec = __ldg(prec + i);
   const int kind = rec.x & 7;
-  const float ap = VB(adj, rec.x >> 1 & ~3, lane);
+  const VecT<R> ap = ldv<R>(al, rec.x >> 1 & ~3);
   switch (kind) {
-    case PR_ADD: return a + ap;
-    case PR_SUB: return a - ap;
-    case PR_MUL_SIB: return fmaf(ap, VB(val, rec.y, lane), a);
+    case PR_ADD: {
+#pragma unroll
+      for (int j = 0; j < R; ++j) a.v[j] += ap.v[j];
+      return a;
+    }
+    case PR_SUB: {
+#pragma unroll
+      for (int j = 0; j < R; ++j) a.v[j] -= ap.v[j];
+      return a;
+    }
+    case PR_MUL_SIB: return vfma<R>(ap, ldv<R>(vl, rec.y), a);
     case PR_MUL_SIBS: {  // product of the other children of an n-ary product
       const int2 ext = __ldg(prec + i + 1);
       const int nc = ext.y & 0xffff, pos = ext.y >> 16;
-      float sib = 1.0f;
+      VecT<R> sib = vfill<R>(1.0f);
       for (int e = 0; e < nc; ++e)
-        if (e != pos) sib *= VB(val, __ldg(bedges + ext.x + e), lane);
-      return fmaf(ap, sib, a);
+        if (e != pos) {
+          const VecT<R> v = ldv<R>(vl, __ldg(bedges + ext.x + e));
+#pragma unroll
+          for (int j = 0; j < R; ++j) sib.v[j] *= v.v[j];
+        }
+      return vfma<R>(ap, sib, a);
     }
     default: {  // PR_LSE: softmax weight of the child inside a logsumexp parent
       const int2 ext = __ldg(prec + i + 1);
-      const float vc = VB(val, rec.y, lane), vp = VB(val, ext.x, lane);
-      return fmaf(ap, (vp == -INFINITY) ? 0.0f : expf(vc - vp), a);
+      const VecT<R> vc = ldv<R>(vl, rec.y), vp = ldv<R>(vl, ext.x);
+#pragma unroll
+      for (int j = 0; j < R; ++j) a.v[j] = fmaf(ap.v[j], (vp.v[j] == -INFINITY) ? 0.0f : expf(vc.v[j] - vp.v[j]), a.v[j]);
+      return a;
     }
   }
 }
 
-template <bool LOG>
+template <int R, bool LOG>
 __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) {
+  constexpr int T = 32 * R;
   const GenProgram& P = A.G;
   const GenCall& C = A.C;
-  extern __shared__ __align__(16) float gsm[];
-  float* fs = gsm;                               // [F][PITCH]
-  float* val = fs + P.n_facts * PITCH;           // [n_bvals + 2][PITCH]
-  float* adj = val + (P.n_bvals + 2) * PITCH;    // [n_nodes + 1][PITCH]
+  extern __shared__ __align__(16) unsigned char gsm_raw[];
+  uint64_t* bar_f = reinterpret_cast<uint64_t*>(gsm_raw);       // facts tile
+  uint64_t* bar_g = bar_f + 1;                                  // grad_worlds chunk
+  float* val = reinterpret_cast<float*>(gsm_raw + 16);          // [n_bvals + 2][T]
+  float* adj = val + (P.n_bvals + 2) * T;                       // [n_nodes + 1][T]
+  float* fs = adj + (P.n_nodes + 1) * T;                        // [T][F] facts staging
+  float* gfs = fs + T * P.n_facts;                              // [T][F] grad_facts staging
+  float* gws = gfs + T * P.n_facts;                             // [T][<= cb] grad_worlds staging
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const long long n_tiles = (C.B + kWarp - 1) / kWarp;
+  float* vl = val + lane * R;
+  float* al = adj + lane * R;
+  const long long n_tiles = (C.B + T - 1) / T;
   const bool norm = (C.flags & VAEL_FLAG_NORMALIZE) && P.norm_slot_off >= 0;
-  const int W = P.n_worlds, F = P.n_facts;
-  init_const_rows(val, P.n_bvals);
+  const int W = P.n_worlds, F = P.n_facts, Q = P.n_queries;
+  const bool have_gw = C.grad_worlds != nullptr;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_f, 1);
+    mbar_init(bar_g, 1);
+    fence_mbar_init();
+  }
+  init_const_rows(val, P.n_bvals, T);
+  __syncthreads();
 
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long row0 = tile * kWarp;
-    const int rows = (int)min((long long)kWarp, C.B - row0);
-    load_facts_tile(fs, C.facts, row0, rows, F, warp, nwarps, lane);
-    for (int i = threadIdx.x; i < P.n_zero * kWarp; i += blockDim.x) VB(adj, __ldg(P.zero_off + (i >> 5)), i & 31) = 0.0f;
-    __syncthreads();
+  long long tile = blockIdx.x;
+  bool f_async = false, g_async = false;
+  uint32_t ph_f = 0, ph_g = 0;
+  if (tile < n_tiles) {
+    const int rows = (int)min((long long)T, C.B - tile * T);
+    f_async = stage_load(fs, C.facts, tile * T, rows, T, F, 0, F, bar_f, 0.5f);
+    if (have_gw) g_async = stage_load(gws, C.grad_worlds, tile * T, rows, T, W, 0, min(P.cb, W), bar_g, 0.0f);
+  }
+
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const long long row0 = tile * T;
+    const int rows = (int)min((long long)T, C.B - row0);
+    const long long nt = tile + gridDim.x;
+    const int nrows = (int)min((long long)T, C.B - nt * T);
+    // per-row query seed (lane <-> rows lane + 32 j), requested first so that its HBM latency hides
+    int32_t qrow[R];
+    float gq[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int r = lane + 32 * j;
+      const bool on = C.grad_query != nullptr && r < rows;
+      qrow[j] = on ? (C.qidx ? __ldg(C.qidx + row0 + r) : C.qscalar) : -1;
+      gq[j] = on ? __ldg(C.grad_query + row0 + r) : 0.0f;
+    }
+    if (f_async) { mbar_wait(bar_f, ph_f); ph_f ^= 1; } else __syncthreads();
 
     for (int L = 0; L < P.n_levels; ++L) {
       if (P.bop_level_ptr[L + 1] > P.bop_level_ptr[L]) {
-        run_level<LOG>(P.bops, P.bedges, P.bop_level_ptr[L], P.bop_level_ptr[L + 1], fs, val, warp, nwarps, lane);
+        run_level<R, LOG>(P.bops, P.bedges, P.bop_level_ptr[L], P.bop_level_ptr[L + 1], fs, F, vl, warp, nwarps, lane);
         __syncthreads();
       }
+      if (!LOG && L == P.leaf_levels_b - 1 && nt < n_tiles)
+        f_async = stage_load(fs, C.facts, nt * T, nrows, T, F, 0, F, bar_f, 0.5f);
+    }
+    if (!LOG && P.leaf_levels_b == 0 && nt < n_tiles) {
+      __syncthreads();   // every thread is past its wait on the facts barrier
+      f_async = stage_load(fs, C.facts, nt * T, nrows, T, F, 0, F, bar_f, 0.5f);
     }
 
-    // seed the world adjoints from the upstream gradient (assignment: no zero-fill needed);
-    // lane <-> world, warps take rows: 128-byte coalesced loads
-    {
-      const size_t gstep = (size_t)nwarps * W;
-      for (int e0 = 0; e0 < W; e0 += kWarp) {
-        const int e = e0 + lane;
-        if (e < W) {
-          float* a = reinterpret_cast<float*>(reinterpret_cast<char*>(adj) + __ldg(P.wseed_off + e)) + warp;
-          if (C.grad_worlds == nullptr) {
-            for (int r = warp; r < kWarp; r += nwarps, a += nwarps) *a = 0.0f;
-          } else {
-            const float* gsrc = C.grad_worlds + (row0 + warp) * W + e;
-            if (!norm) {
-#pragma unroll 4
-              for (int r = warp; r < kWarp; r += nwarps, a += nwarps, gsrc += gstep) *a = (r < rows) ? __ldg(gsrc) : 0.0f;
-            } else {
-              for (int r = warp; r < kWarp; r += nwarps, a += nwarps, gsrc += gstep)
-                *a = (r < rows) ? __ldg(gsrc) / VB(val, P.norm_slot_off, r) : 0.0f;
+    // ---- seeds.  Query nodes that are not world nodes: assigned (no zero-fill of the adjoint tile) ----
+    VecT<R> zv = vfill<R>(1.0f);
+    if (norm) zv = ldv<R>(vl, P.norm_slot_off);
+    int32_t qoff[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      qoff[j] = (qrow[j] >= 0 && qrow[j] < Q) ? __ldg(P.qseed_off + qrow[j]) : -1;
+      if (norm) gq[j] = gq[j] / zv.v[j];
+    }
+    for (int i = warp; i < P.n_qonly; i += nwarps) {
+      const int32_t off = __ldg(P.qonly_off + i);
+      VecT<R> a;
+#pragma unroll
+      for (int j = 0; j < R; ++j) a.v[j] = (qoff[j] == off) ? gq[j] : 0.0f;
+      stv<R>(al, off, a);
+    }
+    // ---- world adjoints from the upstream gradient: row-major staging -> node-major (assignment) ----
+    if (!have_gw) {
+      for (int w = warp; w < W; w += nwarps) stv<R>(al, __ldg(P.wseed_off + w), vfill<R>(0.0f));
+      __syncthreads();
+    } else {
+      for (int c0 = 0; c0 < W; c0 += P.cb) {
+        const int cc = min(P.cb, W - c0);
+        if (g_async) { mbar_wait(bar_g, ph_g); ph_g ^= 1; } else __syncthreads();
+        if ((cc & 3) == 0) {
+          for (int g = warp; g < (cc >> 2); g += nwarps) {
+            const int w = c0 + 4 * g;
+            const int4 off = __ldg(reinterpret_cast<const int4*>(P.wseed_off + w));
+            VecT<R> a0, a1, a2, a3;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+              float4 gv = *reinterpret_cast<const float4*>(gws + (lane + 32 * j) * cc + 4 * g);
+              if (norm) { gv.x = gv.x / zv.v[j]; gv.y = gv.y / zv.v[j]; gv.z = gv.z / zv.v[j]; gv.w = gv.w / zv.v[j]; }
+              a0.v[j] = gv.x; a1.v[j] = gv.y; a2.v[j] = gv.z; a3.v[j] = gv.w;
             }
+            stv<R>(al, off.x, a0); stv<R>(al, off.y, a1); stv<R>(al, off.z, a2); stv<R>(al, off.w, a3);
           }
+        } else {
+          for (int c = warp; c < cc; c += nwarps) {
+            VecT<R> a;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+              const float gv = gws[(lane + 32 * j) * cc + c];
+              a.v[j] = norm ? gv / zv.v[j] : gv;
+            }
+            stv<R>(al, __ldg(P.wseed_off + c0 + c), a);
+          }
+        }
+        __syncthreads();   // chunk consumed: the staging tile is free, the seeds are visible
+        // next chunk of this tile, or the first chunk of the next tile (behind the reverse sweep)
+        if (c0 + P.cb < W) {
+          g_async = stage_load(gws, C.grad_worlds, row0, rows, T, W, c0 + P.cb, min(P.cb, W - c0 - P.cb), bar_g, 0.0f);
+        } else if (nt < n_tiles) {
+          g_async = stage_load(gws, C.grad_worlds, nt * T, nrows, T, W, 0, min(P.cb, W), bar_g, 0.0f);
         }
       }
     }
-    __syncthreads();
-    if (C.grad_query != nullptr && warp == 0 && lane < rows) {
-      const long long row = row0 + lane;
-      const int32_t q = C.qidx ? __ldg(C.qidx + row) : C.qscalar;
-      if (q >= 0 && q < P.n_queries) {
-        float g = __ldg(C.grad_query + row);
-        if (norm) g = g / VB(val, P.norm_slot_off, lane);
-        VB(adj, __ldg(P.qseed_off + q), lane) += g;
+    if (P.q_world_any && C.grad_query != nullptr) {   // query nodes that are world nodes: added to the world seed
+      if (warp == 0) {
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (qoff[j] >= 0 && (qoff[j] & 1)) al[((qoff[j] & ~1) >> 2) + j] += gq[j];
       }
+      __syncthreads();
     }
-    __syncthreads();
 
     // reverse sweep, gather form: adj[c] = seed[c] + sum over live parents p of adj[p] * d val[p] / d val[c].
     // Children come in groups of four of the same shape (same record count and kinds; levels padded with
@@ -418,9 +705,9 @@ __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) 
         const bool same = cr[1].z == cr[0].z && cr[2].z == cr[0].z && cr[3].z == cr[0].z && cr[1].w == cr[0].w &&
                           cr[2].w == cr[0].w && cr[3].w == cr[0].w;
         if (same && !(cr[0].w & CR_WIDE)) {
-          float a[4];
+          VecT<R> a[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) a[u] = (cr[0].w & CR_SEEDED) ? VB(adj, cr[u].x, lane) : 0.0f;
+          for (int u = 0; u < 4; ++u) a[u] = (cr[0].w & CR_SEEDED) ? ldv<R>(al, cr[u].x) : vfill<R>(0.0f);
           const int uk = cr[0].w >> CR_UNIFORM_SHIFT, n = cr[0].z;
           if (uk == 1 + PR_MUL_SIB) {
             for (int r = 0; r < n; ++r) {
@@ -428,66 +715,71 @@ __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) 
 #pragma unroll
               for (int u = 0; u < 4; ++u) rec[u] = __ldg(P.prec + cr[u].y + r);
 #pragma unroll
-              for (int u = 0; u < 4; ++u) a[u] = fmaf(VB(adj, rec[u].x >> 1 & ~3, lane), VB(val, rec[u].y, lane), a[u]);
+              for (int u = 0; u < 4; ++u) a[u] = vfma<R>(ldv<R>(al, rec[u].x >> 1 & ~3), ldv<R>(vl, rec[u].y), a[u]);
             }
           } else if (uk == 1 + PR_ADD) {
             for (int r = 0; r < n; ++r) {
 #pragma unroll
-              for (int u = 0; u < 4; ++u) a[u] += VB(adj, __ldg(&P.prec[cr[u].y + r].x) >> 1 & ~3, lane);
+              for (int u = 0; u < 4; ++u) {
+                const VecT<R> ap = ldv<R>(al, __ldg(&P.prec[cr[u].y + r].x) >> 1 & ~3);
+#pragma unroll
+                for (int j = 0; j < R; ++j) a[u].v[j] += ap.v[j];
+              }
             }
           } else {
             for (int r = 0; r < n; ++r) {
 #pragma unroll
-              for (int u = 0; u < 4; ++u) a[u] = apply_rec<LOG>(a[u], P.prec, cr[u].y + r, val, adj, P.bedges, lane);
+              for (int u = 0; u < 4; ++u) a[u] = apply_rec<R, LOG>(a[u], P.prec, cr[u].y + r, vl, al, P.bedges);
             }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) VB(adj, cr[u].x, lane) = a[u];
+          for (int u = 0; u < 4; ++u) stv<R>(al, cr[u].x, a[u]);
         } else {
           for (int u = 0; u < 4; ++u) {
-            float a = (cr[u].w & CR_SEEDED) ? VB(adj, cr[u].x, lane) : 0.0f;
+            VecT<R> a = (cr[u].w & CR_SEEDED) ? ldv<R>(al, cr[u].x) : vfill<R>(0.0f);
             for (int r = 0, i = cr[u].y; r < cr[u].z; ++r) {
               const int k = __ldg(&P.prec[i].x) & 7;
-              a = apply_rec<LOG>(a, P.prec, i, val, adj, P.bedges, lane);
+              a = apply_rec<R, LOG>(a, P.prec, i, vl, al, P.bedges);
               i += (k == PR_MUL_SIBS || k == PR_LSE) ? 2 : 1;
             }
-            VB(adj, cr[u].x, lane) = a;
+            stv<R>(al, cr[u].x, a);
           }
         }
       }
+      if (L == 0) bulk_wait_read<0>();   // the previous tile's store has finished reading the grad_facts staging
+      __syncthreads();
+    }
+    if (P.n_levels < 2) {
+      bulk_wait_read<0>();
       __syncthreads();
     }
 
-    // live leaves -> grad_facts[row, f]: lanes take fact columns, warps take rows
-    for (int f = lane; f < F; f += kWarp) {
+    // ---- live leaves -> grad_facts staging (lane <-> row, warps take fact columns) -> bulk store ----
+    for (int f = warp; f < F; f += nwarps) {
       const int kb = __ldg(P.leaf_ptr + f), ke = __ldg(P.leaf_ptr + f + 1);
-      float* o = C.grad_facts + (row0 + warp) * F + f;
-      const size_t ostep = (size_t)nwarps * F;
-      if (!LOG && ke - kb == 1) {  // the usual case: one (positive) literal per fact
-        const int2 lr = __ldg(P.leaf_rec + kb);
-        const float* a = reinterpret_cast<const float*>(reinterpret_cast<const char*>(adj) + lr.x) + warp;
-        const float sgn = lr.y < 0 ? -1.0f : 1.0f;
-#pragma unroll 4
-        for (int r = warp; r < rows; r += nwarps, a += nwarps, o += ostep) *o = sgn * *a;
-      } else {
-        for (int r = warp; r < rows; r += nwarps, o += ostep) {
-          float g = 0.0f;
-          for (int k = kb; k < ke; ++k) {
-            const int2 lr = __ldg(P.leaf_rec + k);
-            const float a = VB(adj, lr.x, r);
-            if (!LOG) {
-              g += lr.y < 0 ? -a : a;
-            } else {
-              const float pf = fs[f * PITCH + r];
-              g += lr.y < 0 ? -a / (1.0f - pf) : a / pf;
-            }
+      VecT<R> g = vfill<R>(0.0f);
+      for (int k = kb; k < ke; ++k) {
+        const int2 lr = __ldg(P.leaf_rec + k);
+        const VecT<R> a = ldv<R>(al, lr.x);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          if (!LOG) {
+            g.v[j] += lr.y < 0 ? -a.v[j] : a.v[j];
+          } else {
+            const float pf = fs[(lane + 32 * j) * F + f];
+            g.v[j] += lr.y < 0 ? -a.v[j] / (1.0f - pf) : a.v[j] / pf;
           }
-          *o = g;
         }
       }
+#pragma unroll
+      for (int j = 0; j < R; ++j) gfs[(lane + 32 * j) * F + f] = g.v[j];
     }
+    fence_proxy_async();
     __syncthreads();
+    stage_store(gfs, C.grad_facts, row0, rows, T, F, 0, F);
+    if (LOG && nt < n_tiles) f_async = stage_load(fs, C.facts, nt * T, nrows, T, F, 0, F, bar_f, 0.5f);
   }
+  bulk_wait_all<0>();
 }
 
 // ---------------------------------------------------------------------------
@@ -507,7 +799,7 @@ void gen_program_destroy(GenProgram* g) {
   if (!g) return;
   cudaFree(g->ops); cudaFree(g->edges); cudaFree(g->world_off); cudaFree(g->query_off); cudaFree(g->bops);
   cudaFree(g->bedges); cudaFree(g->crec); cudaFree(g->prec); cudaFree(g->wseed_off); cudaFree(g->qseed_off);
-  cudaFree(g->zero_off); cudaFree(g->leaf_rec); cudaFree(g->leaf_ptr);
+  cudaFree(g->qonly_off); cudaFree(g->leaf_rec); cudaFree(g->leaf_ptr);
   delete g;
 }
 
@@ -526,7 +818,7 @@ HostOp make_op(const vael_circuit_desc_t* d, int n, OffFn off) {
   h.op = make_int4(off(n), 0, 0, 0);
   auto kind = [&](int code) { h.op.w = code | (nc << 8); };
   if (k == VAEL_NODE_LEAF_POS || k == VAEL_NODE_LEAF_NEG) {
-    h.op.y = d->node_arg[n] * PB;
+    h.op.y = d->node_arg[n];
     kind(k == VAEL_NODE_LEAF_POS ? OP_LEAF_POS : OP_LEAF_NEG);
   } else if (k == VAEL_NODE_CONST) {
     const float v = d->const_val[d->node_arg[n]];
@@ -583,6 +875,31 @@ void emit_level(std::vector<HostOp>& lvl, bool is_log, int zero_off, int one_off
 }
 }  // namespace
 
+
+// Rows per lane (R) and staged chunk width for one kernel: the largest R whose tile — `node_rows` value /
+// adjoint rows of 128 R bytes, `n_small` [T, F] staging tiles and one [T, chunk] staging tile — fits one CTA's
+// shared memory with the whole [T, W] tensor staged at once; circuits too wide for that run R = 1 with
+// column chunks.  VAEL_GEN_R forces R (experiments).
+constexpr size_t kSmemLimit = (size_t)227 * 1024 - 64;
+static size_t tile_smem(size_t node_rows, int F, int n_small, int cols, int R) {
+  return 16 + (size_t)128 * R * (node_rows + (size_t)n_small * F + cols);
+}
+static bool choose_tile(size_t node_rows, int F, int n_small, int W, int Q, int* R_out, int* chunk, int* cap,
+                        size_t* smem) {
+  static const int forced = [] { const char* v = getenv("VAEL_GEN_R"); return (v && *v) ? atoi(v) : 0; }();
+  const int wcols = std::max(W, 1), qcols = std::min(std::max(Q, 1), 32);
+  for (int R = 4; R >= 1; R >>= 1) {
+    if (forced && R != forced && R != 1) continue;
+    const size_t s = tile_smem(node_rows, F, n_small, std::max(wcols, qcols), R);
+    if (s <= kSmemLimit) { *R_out = R; *chunk = wcols; *cap = std::max(wcols, qcols); *smem = s; return true; }
+  }
+  const size_t fixed = tile_smem(node_rows, F, n_small, 0, 1);
+  if (fixed + 128 * 32 > kSmemLimit) { *R_out = 1; *chunk = *cap = 32; *smem = fixed + 128 * 32; return false; }
+  const int cols = (int)std::min<size_t>((kSmemLimit - fixed) / 128, (size_t)wcols) & ~3;
+  *R_out = 1; *chunk = *cap = cols; *smem = tile_smem(node_rows, F, n_small, cols, 1);
+  return true;
+}
+
 GenProgram* gen_program_create(const vael_circuit_desc_t* d, cudaError_t* err) {
   GenProgram* g = new GenProgram();
   memset(g, 0, sizeof(*g));
@@ -592,18 +909,37 @@ GenProgram* gen_program_create(const vael_circuit_desc_t* d, cudaError_t* err) {
   const int N = d->n_nodes;
 
   // ---- forward schedule ----
+  choose_tile((size_t)N + 2, d->n_facts, 1, d->n_worlds, d->n_queries, &g->rf, &g->cf, &g->cq,
+              &g->fwd_smem);
+  const int PBF = 128 * g->rf;
+  // two schedules: [0] every node; [1] only the cones of the world and query nodes (what a call without
+  // VAEL_FLAG_NORMALIZE needs: the normaliser's private cone is skipped)
+  std::vector<char> out_cone(N, 0);
+  for (int w = 0; w < d->n_worlds; ++w) out_cone[d->world_node[w]] = 1;
+  for (int q = 0; q < d->n_queries; ++q) out_cone[d->query_node[q]] = 1;
+  for (int n = N - 1; n >= 0; --n)
+    if (out_cone[n])
+      for (int e = d->child_ptr[n]; e < d->child_ptr[n + 1]; ++e) out_cone[d->child_idx[e]] = 1;
   std::vector<int4> ops;
   std::vector<int32_t> edges;
-  for (int L = 0; L < d->n_levels; ++L) {
-    g->op_level_ptr[L] = (int)ops.size();
-    std::vector<HostOp> lvl;
-    for (int n = d->level_ptr[L]; n < d->level_ptr[L + 1]; ++n) lvl.push_back(make_op(d, n, [](int x) { return x * PB; }));
-    emit_level(lvl, is_log, N * PB, (N + 1) * PB, ops, edges);
+  for (int sch = 0; sch < 2; ++sch) {
+    g->leaf_levels_f[sch] = 1;
+    g->n_levels_f[sch] = 1;
+    for (int L = 0; L < d->n_levels; ++L) {
+      g->op_level_ptr[sch][L] = (int)ops.size();
+      std::vector<HostOp> lvl;
+      for (int n = d->level_ptr[L]; n < d->level_ptr[L + 1]; ++n)
+        if (sch == 0 || out_cone[n]) lvl.push_back(make_op(d, n, [&](int x) { return x * PBF; }));
+      if (!lvl.empty()) g->n_levels_f[sch] = L + 1;
+      for (const HostOp& h : lvl)
+        if ((h.op.w & 0xff) <= OP_LEAF_NEG) g->leaf_levels_f[sch] = L + 1;
+      emit_level(lvl, is_log, N * PBF, (N + 1) * PBF, ops, edges);
+    }
+    g->op_level_ptr[sch][d->n_levels] = (int)ops.size();
   }
-  g->op_level_ptr[d->n_levels] = (int)ops.size();
-  std::vector<int32_t> world_off(d->n_worlds), query_off(d->n_queries);
-  for (int w = 0; w < d->n_worlds; ++w) world_off[w] = d->world_node[w] * PB;
-  for (int q = 0; q < d->n_queries; ++q) query_off[q] = d->query_node[q] * PB;
+  std::vector<int32_t> world_off((d->n_worlds + 3) / 4 * 4, 0), query_off(d->n_queries);
+  for (int w = 0; w < d->n_worlds; ++w) world_off[w] = d->world_node[w] * PBF;
+  for (int q = 0; q < d->n_queries; ++q) query_off[q] = d->query_node[q] * PBF;
 
   // ---- which node values does the adjoint need?  children of products (siblings), everything under the
   // normaliser, and for the log semiring sums and their children (softmax weights) ----
@@ -626,17 +962,25 @@ GenProgram* gen_program_create(const vael_circuit_desc_t* d, cudaError_t* err) {
   std::vector<int32_t> bslot(N, -1);
   for (int n = 0; n < N; ++n)
     if (need[n]) bslot[n] = g->n_bvals++;
+  int unused_cap = 0;
+  choose_tile((size_t)g->n_bvals + 2 + N + 1, d->n_facts, 2, d->n_worlds, 0, &g->rb, &g->cb, &unused_cap,
+              &g->bwd_smem);
+  const int PBB = 128 * g->rb;
   std::vector<int4> bops;
   std::vector<int32_t> bedges;
   for (int L = 0; L < d->n_levels; ++L) {
     g->bop_level_ptr[L] = (int)bops.size();
     std::vector<HostOp> lvl;
     for (int n = d->level_ptr[L]; n < d->level_ptr[L + 1]; ++n)
-      if (need[n]) lvl.push_back(make_op(d, n, [&](int x) { return bslot[x] * PB; }));
-    emit_level(lvl, is_log, g->n_bvals * PB, (g->n_bvals + 1) * PB, bops, bedges);
+      if (need[n]) lvl.push_back(make_op(d, n, [&](int x) { return bslot[x] * PBB; }));
+    emit_level(lvl, is_log, g->n_bvals * PBB, (g->n_bvals + 1) * PBB, bops, bedges);
   }
   g->bop_level_ptr[d->n_levels] = (int)bops.size();
-  g->norm_slot_off = g->norm_node >= 0 ? bslot[g->norm_node] * PB : -1;
+  g->leaf_levels_b = 0;
+  for (int L = 0; L < d->n_levels; ++L)
+    for (int i = g->bop_level_ptr[L]; i < g->bop_level_ptr[L + 1]; ++i)
+      if ((bops[i].w & 0xff) <= OP_LEAF_NEG) g->leaf_levels_b = L + 1;
+  g->norm_slot_off = g->norm_node >= 0 ? bslot[g->norm_node] * PBB : -1;
 
   // ---- liveness: a node carries an adjoint iff it is an output (world / query node) or feeds a live node ----
   std::vector<char> seed(N, 0), live(N, 0), is_world(N, 0);
@@ -659,13 +1003,13 @@ GenProgram* gen_program_create(const vael_circuit_desc_t* d, cudaError_t* err) {
     g->cl_ptr[L] = (int)crec.size();
     for (int c = d->level_ptr[L]; c < d->level_ptr[L + 1]; ++c) {
       if (!live[c] || parents[c].empty()) continue;
-      int4 cr = make_int4(c * PB, (int)prec.size(), (int)parents[c].size(), seed[c] ? CR_SEEDED : 0);
+      int4 cr = make_int4(c * PBB, (int)prec.size(), (int)parents[c].size(), seed[c] ? CR_SEEDED : 0);
       int uniform = -1;
       bool first = true;
       for (auto& pr : parents[c]) {
         const int p = pr.first, pos = pr.second;
         const int k = d->node_kind[p], cb = d->child_ptr[p], nc = d->child_ptr[p + 1] - cb;
-        const int padj = (p * PB) << 1;
+        const int padj = (p * PBB) << 1;
         int kind;
         if (!is_log) {
           if (k == VAEL_NODE_SUM) { kind = PR_ADD; prec.push_back(make_int2(padj | kind, 0)); }
@@ -673,20 +1017,20 @@ GenProgram* gen_program_create(const vael_circuit_desc_t* d, cudaError_t* err) {
           else if (nc == 1) { kind = PR_ADD; prec.push_back(make_int2(padj | kind, 0)); }
           else if (nc == 2) {
             kind = PR_MUL_SIB;
-            prec.push_back(make_int2(padj | kind, bslot[d->child_idx[cb + 1 - pos]] * PB));
+            prec.push_back(make_int2(padj | kind, bslot[d->child_idx[cb + 1 - pos]] * PBB));
           } else {
             kind = PR_MUL_SIBS;
             prec.push_back(make_int2(padj | kind, 0));
             prec.push_back(make_int2((int)bedges.size(), nc | (pos << 16)));
-            for (int e = 0; e < nc; ++e) bedges.push_back(bslot[d->child_idx[cb + e]] * PB);
+            for (int e = 0; e < nc; ++e) bedges.push_back(bslot[d->child_idx[cb + e]] * PBB);
             cr.w |= CR_WIDE;
           }
         } else {
           if (k == VAEL_NODE_PROD) { kind = PR_ADD; prec.push_back(make_int2(padj | kind, 0)); }
           else {
             kind = PR_LSE;
-            prec.push_back(make_int2(padj | kind, bslot[c] * PB));
-            prec.push_back(make_int2(bslot[p] * PB, 0));
+            prec.push_back(make_int2(padj | kind, bslot[c] * PBB));
+            prec.push_back(make_int2(bslot[p] * PBB, 0));
             cr.w |= CR_WIDE;
           }
         }
@@ -700,18 +1044,22 @@ GenProgram* gen_program_create(const vael_circuit_desc_t* d, cudaError_t* err) {
     std::stable_sort(crec.begin() + g->cl_ptr[L], crec.end(), [](const int4& a, const int4& b) {
       return a.w != b.w ? a.w < b.w : a.z < b.z;
     });
-    while ((crec.size() - g->cl_ptr[L]) % 4) crec.push_back(make_int4(N * PB, 0, 0, 0));
+    while ((crec.size() - g->cl_ptr[L]) % 4) crec.push_back(make_int4(N * PBB, 0, 0, 0));
   }
   g->cl_ptr[d->n_levels] = (int)crec.size();
 
-  std::vector<int32_t> wseed(d->n_worlds), qseed(d->n_queries), zero_off;
-  for (int w = 0; w < d->n_worlds; ++w) wseed[w] = d->world_node[w] * PB;
+  std::vector<int32_t> wseed((d->n_worlds + 3) / 4 * 4, N * PBB), qseed(d->n_queries), qonly;
+  for (int w = 0; w < d->n_worlds; ++w) wseed[w] = d->world_node[w] * PBB;
   for (int q = 0; q < d->n_queries; ++q) {
-    qseed[q] = d->query_node[q] * PB;
-    if (!is_world[d->query_node[q]] && std::find(zero_off.begin(), zero_off.end(), qseed[q]) == zero_off.end())
-      zero_off.push_back(qseed[q]);
+    qseed[q] = d->query_node[q] * PBB;
+    if (is_world[d->query_node[q]]) {
+      qseed[q] |= 1;
+      g->q_world_any = 1;
+    } else if (std::find(qonly.begin(), qonly.end(), qseed[q]) == qonly.end()) {
+      qonly.push_back(qseed[q]);
+    }
   }
-  g->n_zero = (int)zero_off.size();
+  g->n_qonly = (int)qonly.size();
   std::vector<int32_t> leaf_ptr(d->n_facts + 1, 0);
   std::vector<int2> leaf_rec;
   for (int f = 0; f < d->n_facts; ++f) {
@@ -719,19 +1067,17 @@ GenProgram* gen_program_create(const vael_circuit_desc_t* d, cudaError_t* err) {
       const int k = d->node_kind[n];
       if ((k == VAEL_NODE_LEAF_POS || k == VAEL_NODE_LEAF_NEG) && d->node_arg[n] == f && live[n] &&
           (seed[n] || !parents[n].empty()))
-        leaf_rec.push_back(make_int2(n * PB, k == VAEL_NODE_LEAF_NEG ? -1 : 1));
+        leaf_rec.push_back(make_int2(n * PBB, k == VAEL_NODE_LEAF_NEG ? -1 : 1));
     }
     leaf_ptr[f + 1] = (int32_t)leaf_rec.size();
   }
 
-  g->fwd_smem = (size_t)(d->n_facts + N + 2) * PB;
-  g->bwd_smem = (size_t)(d->n_facts + g->n_bvals + 2 + N + 1) * PB;
 
   cudaError_t e = cudaSuccess;
   e = up(&g->ops, ops, e); e = up(&g->edges, edges, e); e = up(&g->world_off, world_off, e);
   e = up(&g->query_off, query_off, e); e = up(&g->bops, bops, e); e = up(&g->bedges, bedges, e);
   e = up(&g->crec, crec, e); e = up(&g->prec, prec, e); e = up(&g->wseed_off, wseed, e);
-  e = up(&g->qseed_off, qseed, e); e = up(&g->zero_off, zero_off, e); e = up(&g->leaf_rec, leaf_rec, e);
+  e = up(&g->qseed_off, qseed, e); e = up(&g->qonly_off, qonly, e); e = up(&g->leaf_rec, leaf_rec, e);
   e = up(&g->leaf_ptr, leaf_ptr, e);
   if (err) *err = e;
   if (e != cudaSuccess) {
@@ -745,21 +1091,22 @@ GenProgram* gen_program_create(const vael_circuit_desc_t* d, cudaError_t* err) {
 // host launchers
 // ---------------------------------------------------------------------------
 bool gen_fits(const GenProgram* g, bool backward) {
-  return (backward ? g->bwd_smem : g->fwd_smem) <= (size_t)227 * 1024;
+  return (backward ? g->bwd_smem : g->fwd_smem) <= kSmemLimit && (backward ? g->cb : g->cf) >= 4;
 }
 
 template <typename K>
-static cudaError_t launch_generic(K kern, const GenProgram* g, const GenCall& C, size_t smem, int num_sms,
+static cudaError_t launch_generic(K kern, const GenProgram* g, const GenCall& C, size_t smem, int R, int num_sms,
                                   cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  // CTAs per SM by shared memory; warps per CTA so that an SM holds ~24 warps (latency hiding without
+  // CTAs per SM by shared memory; warps per CTA so that an SM holds ~`want` warps (latency hiding without
   // tensor-core-style pipelining: every warp is an independent interpreter of its share of a level)
   int per_sm = (int)std::min<size_t>(16, ((size_t)227 * 1024) / (smem + 1024));
   per_sm = std::max(1, per_sm);
   static const int want = [] { const char* v = getenv("VAEL_GEN_WARPS_PER_SM"); return (v && *v) ? atoi(v) : 24; }();
   int nw = std::max(1, std::min(16, (want + per_sm - 1) / per_sm));
-  const long long n_tiles = (C.B + kWarp - 1) / kWarp;
+  const int T = 32 * R;
+  const long long n_tiles = (C.B + T - 1) / T;
   const long long grid = std::min<long long>(n_tiles, (long long)num_sms * per_sm);
   GenArgs A;
   A.G = *g;
@@ -768,15 +1115,27 @@ static cudaError_t launch_generic(K kern, const GenProgram* g, const GenCall& C,
   return cudaGetLastError();
 }
 
+template <bool LOG>
+static cudaError_t gen_forward_r(const GenProgram* g, const GenCall& C, int num_sms, cudaStream_t st) {
+  switch (g->rf) {
+    case 4: return launch_generic(generic_forward_kernel<4, LOG>, g, C, g->fwd_smem, 4, num_sms, st);
+    case 2: return launch_generic(generic_forward_kernel<2, LOG>, g, C, g->fwd_smem, 2, num_sms, st);
+    default: return launch_generic(generic_forward_kernel<1, LOG>, g, C, g->fwd_smem, 1, num_sms, st);
+  }
+}
+template <bool LOG>
+static cudaError_t gen_backward_r(const GenProgram* g, const GenCall& C, int num_sms, cudaStream_t st) {
+  switch (g->rb) {
+    case 4: return launch_generic(generic_backward_kernel<4, LOG>, g, C, g->bwd_smem, 4, num_sms, st);
+    case 2: return launch_generic(generic_backward_kernel<2, LOG>, g, C, g->bwd_smem, 2, num_sms, st);
+    default: return launch_generic(generic_backward_kernel<1, LOG>, g, C, g->bwd_smem, 1, num_sms, st);
+  }
+}
 cudaError_t gen_forward(const GenProgram* g, const GenCall& C, int num_sms, cudaStream_t st) {
-  if (g->semiring == VAEL_SEMIRING_LOG)
-    return launch_generic(generic_forward_kernel<true>, g, C, g->fwd_smem, num_sms, st);
-  return launch_generic(generic_forward_kernel<false>, g, C, g->fwd_smem, num_sms, st);
+  return g->semiring == VAEL_SEMIRING_LOG ? gen_forward_r<true>(g, C, num_sms, st) : gen_forward_r<false>(g, C, num_sms, st);
 }
 cudaError_t gen_backward(const GenProgram* g, const GenCall& C, int num_sms, cudaStream_t st) {
-  if (g->semiring == VAEL_SEMIRING_LOG)
-    return launch_generic(generic_backward_kernel<true>, g, C, g->bwd_smem, num_sms, st);
-  return launch_generic(generic_backward_kernel<false>, g, C, g->bwd_smem, num_sms, st);
+  return g->semiring == VAEL_SEMIRING_LOG ? gen_backward_r<true>(g, C, num_sms, st) : gen_backward_r<false>(g, C, num_sms, st);
 }
 
 }  // namespace vael
