@@ -57,17 +57,20 @@ struct GenProgram {
   // child lists point at.
   int4* ops;               // {dst, a, b, kind | nc << 8}; leaves: a = fact column; n-ary ops: a = first edge (multiple of 4), b = padded length
   int32_t* edges;          // child offsets of the n-ary ops
-  int32_t op_level_ptr[2][kMaxLevels + 1];  // [0]: every node; [1]: without the cone only the normaliser needs
+  int4* segs;              // runs of equal op kind inside a level: {kind, first op, end, 0}
+  int32_t seg_level_ptr[2][kMaxLevels + 1];  // [0]: every node; [1]: without the cone only the normaliser needs
   int32_t* world_off;      // [W] (padded to a multiple of 4)
   int32_t* query_off;      // [Q]
   // backward: forward values of the nodes the adjoint needs (slot space, + the two constant rows), then the
   // reverse sweep over the adjoint tile (n_nodes rows + one scratch row for the padding records)
   int4* bops;
   int32_t* bedges;
-  int32_t bop_level_ptr[kMaxLevels + 1];
+  int4* bsegs;
+  int32_t bseg_level_ptr[kMaxLevels + 1];
   int32_t norm_slot_off;   // byte offset of Z in the slot space, or -1
   int4* crec;              // live children, level by level: {adj off, first record, n records, flags}
-  int32_t cl_ptr[kMaxLevels + 1];
+  int4* csegs;             // runs of children of the same shape inside a level: {flags, first child, end, n records}
+  int32_t cseg_level_ptr[kMaxLevels + 1];
   int2* prec;              // parent records {parent adj off << 1 | kind, x} (+ one more int2 for kinds 3, 4)
   int32_t* wseed_off;      // [W] adjoint offsets of the world nodes (padded to a multiple of 4)
   int32_t* qseed_off;      // [Q] adjoint offsets of the query nodes, | 1 when the node is also a world node
@@ -92,15 +95,44 @@ template <> struct VecT<1> { float v[1]; };
 template <> struct __align__(8) VecT<2> { float v[2]; };
 template <> struct __align__(16) VecT<4> { float v[4]; };
 
-// `lb` = tile base + lane * R floats; `off` = byte offset of the node row
-template <int R>
-__device__ __forceinline__ VecT<R> ldv(const float* lb, int off) {
-  return *reinterpret_cast<const VecT<R>*>(reinterpret_cast<const char*>(lb) + off);
+// Node rows are addressed with 32-bit shared-window addresses (`lb` = tile base + lane * 4 R bytes, `off` = byte
+// offset of the node row) through ld/st.shared directly: one IADD + one LDS/STS per access.
+template <int R> __device__ __forceinline__ VecT<R> ldv(uint32_t lb, int off);
+template <> __device__ __forceinline__ VecT<1> ldv<1>(uint32_t lb, int off) {
+  VecT<1> x;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x.v[0]) : "r"(lb + off));
+  return x;
 }
-template <int R>
-__device__ __forceinline__ void stv(float* lb, int off, const VecT<R>& x) {
-  *reinterpret_cast<VecT<R>*>(reinterpret_cast<char*>(lb) + off) = x;
+template <> __device__ __forceinline__ VecT<2> ldv<2>(uint32_t lb, int off) {
+  VecT<2> x;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x.v[0]), "=f"(x.v[1]) : "r"(lb + off));
+  return x;
 }
+template <> __device__ __forceinline__ VecT<4> ldv<4>(uint32_t lb, int off) {
+  VecT<4> x;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(x.v[0]), "=f"(x.v[1]), "=f"(x.v[2]), "=f"(x.v[3])
+               : "r"(lb + off));
+  return x;
+}
+template <int R> __device__ __forceinline__ void stv(uint32_t lb, int off, const VecT<R>& x);
+template <> __device__ __forceinline__ void stv<1>(uint32_t lb, int off, const VecT<1>& x) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(lb + off), "f"(x.v[0]) : "memory");
+}
+template <> __device__ __forceinline__ void stv<2>(uint32_t lb, int off, const VecT<2>& x) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(lb + off), "f"(x.v[0]), "f"(x.v[1]) : "memory");
+}
+template <> __device__ __forceinline__ void stv<4>(uint32_t lb, int off, const VecT<4>& x) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lb + off), "f"(x.v[0]), "f"(x.v[1]), "f"(x.v[2]),
+               "f"(x.v[3])
+               : "memory");
+}
+__device__ __forceinline__ float lds1(uint32_t a) {
+  float x;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(a));
+  return x;
+}
+__device__ __forceinline__ void sts1(uint32_t a, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); }
 template <int R>
 __device__ __forceinline__ VecT<R> vfill(float c) {
   VecT<R> o;
@@ -192,26 +224,27 @@ __device__ __forceinline__ void stage_store(const float* stage, float* g, long l
   }
 }
 
-// ---- forward op execution (any kind; the grouped fast paths are in run_level) ------------------
+// ---- forward op execution --------------------------------------------------------------------------
+// `fl` = shared address of this lane's first row in the row-major facts staging tile (base + lane * F * 4)
 template <int R, bool LOG>
-__device__ __forceinline__ VecT<R> leaf_value(const float* fs, int F, int col, bool neg, int lane) {
+__device__ __forceinline__ VecT<R> leaf_value(uint32_t fl, int F, int col, bool neg) {
   VecT<R> o;
 #pragma unroll
   for (int j = 0; j < R; ++j) {
-    float p = fs[(lane + 32 * j) * F + col];
+    float p = lds1(fl + (32 * j * F + col) * 4);
     if (neg) p = __fsub_rn(1.0f, p);
     o.v[j] = LOG ? logf(p) : p;
   }
   return o;
 }
 
+// any op kind (the slow path: kinds without a tight loop in run_level)
 template <int R, bool LOG>
-__device__ __forceinline__ VecT<R> exec_op(const int4 d, const float* fs, int F, const float* vl,
-                                           const int32_t* edges, int lane) {
+__device__ __noinline__ VecT<R> exec_op(const int4 d, uint32_t fl, int F, uint32_t vl, const int32_t* edges) {
   const int kind = d.w & 0xff, nc = d.w >> 8;
   switch (kind) {
-    case OP_LEAF_POS: return leaf_value<R, LOG>(fs, F, d.y, false, lane);
-    case OP_LEAF_NEG: return leaf_value<R, LOG>(fs, F, d.y, true, lane);
+    case OP_LEAF_POS: return leaf_value<R, LOG>(fl, F, d.y, false);
+    case OP_LEAF_NEG: return leaf_value<R, LOG>(fl, F, d.y, true);
     case OP_CONST: return vfill<R>(__int_as_float(d.y));
     case OP_MUL2: {
       const VecT<R> x = ldv<R>(vl, d.y), y = ldv<R>(vl, d.z);
@@ -263,90 +296,96 @@ __device__ __forceinline__ VecT<R> exec_op(const int4 d, const float* fs, int F,
   }
 }
 
-// One level of ops.  The schedule lays the ops of a level out in groups of four of the same kind (levels are
-// padded to a multiple of four with copies of their last op: recomputing a node is harmless; the four child lists
-// of a group of n-ary ops are padded to one length with pointers to the constant-0 / constant-1 rows).  Warps take
-// G = 4 / R ops at a time — with R rows per lane one op already carries R independent chains — and fetch the next
-// group's records before executing the current one.  A group whose ops have the same kind runs branch-free: 2 G
-// independent shared-memory loads, G R FP ops, G stores for binary ops; G left folds side by side for n-ary ones
-// (each fold sequential in CSR order, so the result is bit-exact).
-template <int R, int G, bool LOG>
-__device__ __forceinline__ void exec_group(const int4 (&d)[G], const int32_t* __restrict__ edges, const float* fs, int F,
-                                           float* vl, int lane) {
-  const int k0 = d[0].w & 0xff;
-  bool same = true;
+// One level of ops.  The schedule sorts the ops of a level by kind and describes every run of equal kind as a
+// SEGMENT {kind, first op, end}; the kind is decoded once per segment and the segment's ops are then swept by
+// a tight loop specialised for that kind — warps take G = 4 / R ops at a time (with R rows per lane one op
+// already carries R independent chains), the last group of a segment re-executes the segment's last op instead
+// of branching (recomputing a node is harmless).  Binary ops: 2 G independent shared-memory loads, G R FP ops,
+// G stores.  N-ary folds: child lists padded to a multiple of four with pointers to the constant-0 / constant-1
+// rows and fetched 128 bits at a time, every fold sequential in CSR order (bit-exact).
+template <int R, int G, bool ADD>
+__device__ __forceinline__ void seg_binary(const int4* __restrict__ ops, int beg, int end, uint32_t vl, int warp,
+                                           int nwarps) {
+  for (int i = beg + G * warp; i < end; i += G * nwarps) {
+    int4 d[G];
 #pragma unroll
-  for (int u = 1; u < G; ++u) same = same && (d[u].w & 0xff) == k0;
-  if (same && (k0 == OP_MUL2 || (!LOG && k0 == OP_ADD2))) {
+    for (int u = 0; u < G; ++u) d[u] = __ldg(ops + min(i + u, end - 1));
     VecT<R> x[G], y[G];
 #pragma unroll
     for (int u = 0; u < G; ++u) { x[u] = ldv<R>(vl, d[u].y); y[u] = ldv<R>(vl, d[u].z); }
-    const bool adds = LOG || k0 == OP_ADD2;
 #pragma unroll
-    for (int u = 0; u < G; ++u) stv<R>(vl, d[u].x, adds ? vadd_rn<R>(x[u], y[u]) : vmul_rn<R>(x[u], y[u]));
-    return;
+    for (int u = 0; u < G; ++u) stv<R>(vl, d[u].x, ADD ? vadd_rn<R>(x[u], y[u]) : vmul_rn<R>(x[u], y[u]));
   }
-  if (same && k0 <= OP_LEAF_NEG) {
+}
+template <int R, int G, bool ADD>
+__device__ __forceinline__ void seg_fold(const int4* __restrict__ ops, const int32_t* __restrict__ edges, int beg,
+                                         int end, uint32_t vl, int warp, int nwarps) {
+  for (int i = beg + G * warp; i < end; i += G * nwarps) {
+    int4 d[G];
+    int len = 0;
 #pragma unroll
-    for (int u = 0; u < G; ++u) stv<R>(vl, d[u].x, leaf_value<R, LOG>(fs, F, d[u].y, k0 == OP_LEAF_NEG, lane));
-    return;
-  }
-  if (same && (k0 == OP_PRODN || (!LOG && k0 == OP_SUMN))) {
-    bool same_len = true;
+    for (int u = 0; u < G; ++u) {
+      d[u] = __ldg(ops + min(i + u, end - 1));
+      len = max(len, d[u].z);    // padded length (multiple of four); shorter lists stop early
+    }
+    VecT<R> acc[G];
 #pragma unroll
-    for (int u = 1; u < G; ++u) same_len = same_len && d[u].z == d[0].z;
-    if (same_len) {
-      const bool adds = LOG || k0 == OP_SUMN;     // log-semiring product = sum of logs
-      const int len = d[0].z;                     // padded length (multiple of four)
-      VecT<R> acc[G];
+    for (int u = 0; u < G; ++u) acc[u] = vfill<R>(ADD ? 0.0f : 1.0f);  // 0 + x and 1 * x are exact
+    for (int e = 0; e < len; e += 4) {
 #pragma unroll
-      for (int u = 0; u < G; ++u) acc[u] = vfill<R>(adds ? 0.0f : 1.0f);  // 0 + x and 1 * x are exact
-      for (int e = 0; e < len; e += 4) {
-        int4 c[G];
-#pragma unroll
-        for (int u = 0; u < G; ++u) c[u] = __ldg(reinterpret_cast<const int4*>(edges + d[u].y + e));
-#pragma unroll
-        for (int u = 0; u < G; ++u) {
-          const VecT<R> v0 = ldv<R>(vl, c[u].x), v1 = ldv<R>(vl, c[u].y), v2 = ldv<R>(vl, c[u].z),
-                        v3 = ldv<R>(vl, c[u].w);
-          if (adds) {
-            acc[u] = vadd_rn<R>(vadd_rn<R>(vadd_rn<R>(vadd_rn<R>(acc[u], v0), v1), v2), v3);
-          } else {
-            acc[u] = vmul_rn<R>(vmul_rn<R>(vmul_rn<R>(vmul_rn<R>(acc[u], v0), v1), v2), v3);
-          }
+      for (int u = 0; u < G; ++u) {
+        if (G > 1 && e >= d[u].z) continue;
+        const int4 c = __ldg(reinterpret_cast<const int4*>(edges + d[u].y + e));
+        const VecT<R> v0 = ldv<R>(vl, c.x), v1 = ldv<R>(vl, c.y), v2 = ldv<R>(vl, c.z), v3 = ldv<R>(vl, c.w);
+        if (ADD) {
+          acc[u] = vadd_rn<R>(vadd_rn<R>(vadd_rn<R>(vadd_rn<R>(acc[u], v0), v1), v2), v3);
+        } else {
+          acc[u] = vmul_rn<R>(vmul_rn<R>(vmul_rn<R>(vmul_rn<R>(acc[u], v0), v1), v2), v3);
         }
       }
-#pragma unroll
-      for (int u = 0; u < G; ++u) stv<R>(vl, d[u].x, acc[u]);
-      return;
     }
-  }
 #pragma unroll
-  for (int u = 0; u < G; ++u) stv<R>(vl, d[u].x, exec_op<R, LOG>(d[u], fs, F, vl, edges, lane));
+    for (int u = 0; u < G; ++u) stv<R>(vl, d[u].x, acc[u]);
+  }
 }
 
 template <int R, bool LOG>
-__device__ __forceinline__ void run_level(const int4* __restrict__ ops, const int32_t* __restrict__ edges, int beg,
-                                          int end, const float* fs, int F, float* vl, int warp, int nwarps,
-                                          int lane) {
+__device__ __forceinline__ void run_level(const int4* __restrict__ segs, int sbeg, int send,
+                                          const int4* __restrict__ ops, const int32_t* __restrict__ edges, uint32_t fl,
+                                          int F, uint32_t vl, int warp, int nwarps) {
   constexpr int G = 4 / R;
-  int g = beg + G * warp;
-  if (g >= end) return;
-  int4 d[G];
-#pragma unroll
-  for (int u = 0; u < G; ++u) d[u] = __ldg(ops + g + u);
-  while (true) {
-    const int gn = g + G * nwarps;
-    int4 dn[G];
-    if (gn < end) {
-#pragma unroll
-      for (int u = 0; u < G; ++u) dn[u] = __ldg(ops + gn + u);
+  for (int s = sbeg; s < send; ++s) {
+    const int4 sg = __ldg(segs + s);
+    const int beg = sg.y, end = sg.z;
+    switch (sg.x) {
+      case OP_LEAF_POS:
+      case OP_LEAF_NEG:
+        for (int i = beg + warp; i < end; i += nwarps) {
+          const int4 d = __ldg(ops + i);
+          stv<R>(vl, d.x, leaf_value<R, LOG>(fl, F, d.y, sg.x == OP_LEAF_NEG));
+        }
+        break;
+      case OP_MUL2:
+        if (LOG) seg_binary<R, G, true>(ops, beg, end, vl, warp, nwarps);
+        else seg_binary<R, G, false>(ops, beg, end, vl, warp, nwarps);
+        break;
+      case OP_PRODN:
+        if (LOG) seg_fold<R, G, true>(ops, edges, beg, end, vl, warp, nwarps);
+        else seg_fold<R, G, false>(ops, edges, beg, end, vl, warp, nwarps);
+        break;
+      default:
+        if (!LOG && sg.x == OP_ADD2) {
+          seg_binary<R, G, true>(ops, beg, end, vl, warp, nwarps);
+        } else if (!LOG && sg.x == OP_SUMN) {
+          seg_fold<R, G, true>(ops, edges, beg, end, vl, warp, nwarps);
+        } else {
+          for (int i = beg + warp; i < end; i += nwarps) {
+            const int4 d = __ldg(ops + i);
+            stv<R>(vl, d.x, exec_op<R, LOG>(d, fl, F, vl, edges));
+          }
+        }
+        break;
     }
-    exec_group<R, G, LOG>(d, edges, fs, F, vl, lane);
-    if (gn >= end) break;
-#pragma unroll
-    for (int u = 0; u < G; ++u) d[u] = dn[u];
-    g = gn;
   }
 }
 
@@ -372,7 +411,8 @@ __global__ void __launch_bounds__(512) generic_forward_kernel(const GenArgs A) {
   float* fs = val + (P.n_nodes + 2) * T;                        // [T][F] row-major staging
   float* out = fs + T * P.n_facts;                              // [T][<= cf] row-major staging
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  float* vl = val + lane * R;
+  const uint32_t vl = smem_u32(val) + lane * (4 * R);
+  const uint32_t fl = smem_u32(fs) + lane * (4 * P.n_facts);
   const long long n_tiles = (C.B + T - 1) / T;
   const bool norm = (C.flags & VAEL_FLAG_NORMALIZE) && P.norm_node >= 0;
   const bool evid = (C.flags & VAEL_FLAG_EVIDENCE) != 0;
@@ -387,7 +427,7 @@ __global__ void __launch_bounds__(512) generic_forward_kernel(const GenArgs A) {
 
   // forward schedule: every node when Z is asked for, else without the cone only the normaliser needs
   const int sch = norm ? 0 : 1;
-  const int32_t* lptr = P.op_level_ptr[sch];
+  const int32_t* lptr = P.seg_level_ptr[sch];
   const int n_lev = P.n_levels_f[sch], leaf_lev = P.leaf_levels_f[sch];
   const bool need_q = C.query != nullptr || evid;
 
@@ -409,7 +449,7 @@ __global__ void __launch_bounds__(512) generic_forward_kernel(const GenArgs A) {
     }
     if (f_async) { mbar_wait(bar, ph); ph ^= 1; } else __syncthreads();
     for (int L = 0; L < n_lev; ++L) {
-      run_level<R, LOG>(P.ops, P.edges, lptr[L], lptr[L + 1], fs, F, vl, warp, nwarps, lane);
+      run_level<R, LOG>(P.segs, lptr[L], lptr[L + 1], P.ops, P.edges, fl, F, vl, warp, nwarps);
       if (L == n_lev - 1) bulk_wait_read<0>();   // the previous tile's stores have finished reading the staging tile
       __syncthreads();
       if (L == leaf_lev - 1) {  // the facts tile is consumed: fetch the next one behind the remaining levels
@@ -426,7 +466,7 @@ __global__ void __launch_bounds__(512) generic_forward_kernel(const GenArgs A) {
 #pragma unroll
       for (int j = 0; j < R; ++j) {
         if (qrow[j] < 0 || qrow[j] >= Q) qrow[j] = -1;
-        qv[j] = qrow[j] >= 0 ? vl[(__ldg(P.query_off + qrow[j]) >> 2) + j] : 0.0f;
+        qv[j] = qrow[j] >= 0 ? lds1(vl + __ldg(P.query_off + qrow[j]) + 4 * j) : 0.0f;
       }
     }
     if (C.query != nullptr && warp == nwarps - 1) {
@@ -521,8 +561,8 @@ __global__ void __launch_bounds__(512) generic_forward_kernel(const GenArgs A) {
 // backward: forward values of the nodes the adjoint needs, then the reverse sweep
 // ---------------------------------------------------------------------------
 template <int R, bool LOG>
-__device__ __forceinline__ VecT<R> apply_rec(VecT<R> a, const int2* __restrict__ prec, int i, const float* vl,
-                                             const float* al, const int32_t* __restrict__ bedges) {
+__device__ __forceinline__ VecT<R> apply_rec(VecT<R> a, const int2* __restrict__ prec, int i, uint32_t vl,
+                                             uint32_t al, const int32_t* __restrict__ bedges) {
   const int2 rec = __ldg(prec + i);
   const int kind = rec.x & 7;
   const VecT<R> ap = ldv<R>(al, rec.x >> 1 & ~3);
@@ -574,8 +614,9 @@ __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) 
   float* gfs = fs + T * P.n_facts;                              // [T][F] grad_facts staging
   float* gws = gfs + T * P.n_facts;                             // [T][<= cb] grad_worlds staging
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  float* vl = val + lane * R;
-  float* al = adj + lane * R;
+  const uint32_t vl = smem_u32(val) + lane * (4 * R);
+  const uint32_t al = smem_u32(adj) + lane * (4 * R);
+  const uint32_t fl = smem_u32(fs) + lane * (4 * P.n_facts);
   const long long n_tiles = (C.B + T - 1) / T;
   const bool norm = (C.flags & VAEL_FLAG_NORMALIZE) && P.norm_slot_off >= 0;
   const int W = P.n_worlds, F = P.n_facts, Q = P.n_queries;
@@ -615,8 +656,8 @@ __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) 
     if (f_async) { mbar_wait(bar_f, ph_f); ph_f ^= 1; } else __syncthreads();
 
     for (int L = 0; L < P.n_levels; ++L) {
-      if (P.bop_level_ptr[L + 1] > P.bop_level_ptr[L]) {
-        run_level<R, LOG>(P.bops, P.bedges, P.bop_level_ptr[L], P.bop_level_ptr[L + 1], fs, F, vl, warp, nwarps, lane);
+      if (P.bseg_level_ptr[L + 1] > P.bseg_level_ptr[L]) {
+        run_level<R, LOG>(P.bsegs, P.bseg_level_ptr[L], P.bseg_level_ptr[L + 1], P.bops, P.bedges, fl, F, vl, warp, nwarps);
         __syncthreads();
       }
       if (!LOG && L == P.leaf_levels_b - 1 && nt < n_tiles)
@@ -688,61 +729,65 @@ __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) 
       if (warp == 0) {
 #pragma unroll
         for (int j = 0; j < R; ++j)
-          if (qoff[j] >= 0 && (qoff[j] & 1)) al[((qoff[j] & ~1) >> 2) + j] += gq[j];
+          if (qoff[j] >= 0 && (qoff[j] & 1)) {
+            const uint32_t a = al + (qoff[j] & ~1) + 4 * j;
+            sts1(a, lds1(a) + gq[j]);
+          }
       }
       __syncthreads();
     }
 
     // reverse sweep, gather form: adj[c] = seed[c] + sum over live parents p of adj[p] * d val[p] / d val[c].
-    // Children come in groups of four of the same shape (same record count and kinds; levels padded with
-    // records that write a scratch row), so four accumulation chains are in flight per warp.
+    // The children of a level are sorted by shape (record count and kinds) and every run of one shape is a
+    // segment {flags, first child, end, n records}: the shape is decoded once per segment, the children are then
+    // swept G = 4 / R at a time (G R accumulation chains in flight per warp; the last group of a segment
+    // recomputes the segment's last child instead of branching).
+    constexpr int G = 4 / R;
     for (int L = P.n_levels - 2; L >= 0; --L) {
-      const int beg = P.cl_ptr[L], end = P.cl_ptr[L + 1];
-      for (int g = beg + 4 * warp; g < end; g += 4 * nwarps) {
-        int4 cr[4];
+      for (int sgi = P.cseg_level_ptr[L]; sgi < P.cseg_level_ptr[L + 1]; ++sgi) {
+        const int4 sg = __ldg(P.csegs + sgi);
+        const int beg = sg.y, end = sg.z, n = sg.w, uk = sg.x >> CR_UNIFORM_SHIFT;
+        const bool seeded = sg.x & CR_SEEDED;
+        if (!(sg.x & CR_WIDE) && (uk == 1 + PR_MUL_SIB || uk == 1 + PR_ADD)) {
+          for (int i = beg + G * warp; i < end; i += G * nwarps) {
+            int4 cr[G];
+            VecT<R> a[G];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) cr[u] = __ldg(P.crec + g + u);
-        const bool same = cr[1].z == cr[0].z && cr[2].z == cr[0].z && cr[3].z == cr[0].z && cr[1].w == cr[0].w &&
-                          cr[2].w == cr[0].w && cr[3].w == cr[0].w;
-        if (same && !(cr[0].w & CR_WIDE)) {
-          VecT<R> a[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) a[u] = (cr[0].w & CR_SEEDED) ? ldv<R>(al, cr[u].x) : vfill<R>(0.0f);
-          const int uk = cr[0].w >> CR_UNIFORM_SHIFT, n = cr[0].z;
-          if (uk == 1 + PR_MUL_SIB) {
-            for (int r = 0; r < n; ++r) {
-              int2 rec[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) rec[u] = __ldg(P.prec + cr[u].y + r);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) a[u] = vfma<R>(ldv<R>(al, rec[u].x >> 1 & ~3), ldv<R>(vl, rec[u].y), a[u]);
+            for (int u = 0; u < G; ++u) {
+              cr[u] = __ldg(P.crec + min(i + u, end - 1));
+              a[u] = seeded ? ldv<R>(al, cr[u].x) : vfill<R>(0.0f);
             }
-          } else if (uk == 1 + PR_ADD) {
-            for (int r = 0; r < n; ++r) {
+            if (uk == 1 + PR_MUL_SIB) {
+              for (int r = 0; r < n; ++r) {
+                int2 rec[G];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const VecT<R> ap = ldv<R>(al, __ldg(&P.prec[cr[u].y + r].x) >> 1 & ~3);
+                for (int u = 0; u < G; ++u) rec[u] = __ldg(P.prec + cr[u].y + r);
 #pragma unroll
-                for (int j = 0; j < R; ++j) a[u].v[j] += ap.v[j];
+                for (int u = 0; u < G; ++u) a[u] = vfma<R>(ldv<R>(al, rec[u].x >> 1 & ~3), ldv<R>(vl, rec[u].y), a[u]);
+              }
+            } else {
+              for (int r = 0; r < n; ++r) {
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                  const VecT<R> ap = ldv<R>(al, __ldg(&P.prec[cr[u].y + r].x) >> 1 & ~3);
+#pragma unroll
+                  for (int j = 0; j < R; ++j) a[u].v[j] += ap.v[j];
+                }
               }
             }
-          } else {
-            for (int r = 0; r < n; ++r) {
 #pragma unroll
-              for (int u = 0; u < 4; ++u) a[u] = apply_rec<R, LOG>(a[u], P.prec, cr[u].y + r, vl, al, P.bedges);
-            }
+            for (int u = 0; u < G; ++u) stv<R>(al, cr[u].x, a[u]);
           }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) stv<R>(al, cr[u].x, a[u]);
         } else {
-          for (int u = 0; u < 4; ++u) {
-            VecT<R> a = (cr[u].w & CR_SEEDED) ? ldv<R>(al, cr[u].x) : vfill<R>(0.0f);
-            for (int r = 0, i = cr[u].y; r < cr[u].z; ++r) {
-              const int k = __ldg(&P.prec[i].x) & 7;
-              a = apply_rec<R, LOG>(a, P.prec, i, vl, al, P.bedges);
-              i += (k == PR_MUL_SIBS || k == PR_LSE) ? 2 : 1;
+          for (int i = beg + warp; i < end; i += nwarps) {
+            const int4 cr = __ldg(P.crec + i);
+            VecT<R> a = seeded ? ldv<R>(al, cr.x) : vfill<R>(0.0f);
+            for (int r = 0, k = cr.y; r < cr.z; ++r) {
+              const int kind = __ldg(&P.prec[k].x) & 7;
+              a = apply_rec<R, LOG>(a, P.prec, k, vl, al, P.bedges);
+              k += (kind == PR_MUL_SIBS || kind == PR_LSE) ? 2 : 1;
             }
-            stv<R>(al, cr[u].x, a);
+            stv<R>(al, cr.x, a);
           }
         }
       }
@@ -766,7 +811,7 @@ __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) 
           if (!LOG) {
             g.v[j] += lr.y < 0 ? -a.v[j] : a.v[j];
           } else {
-            const float pf = fs[(lane + 32 * j) * F + f];
+            const float pf = lds1(fl + (32 * j * F + f) * 4);
             g.v[j] += lr.y < 0 ? -a.v[j] / (1.0f - pf) : a.v[j] / pf;
           }
         }
@@ -797,6 +842,7 @@ static cudaError_t up(T** dptr, const std::vector<T>& h, cudaError_t prev) {
 
 void gen_program_destroy(GenProgram* g) {
   if (!g) return;
+  cudaFree(g->segs); cudaFree(g->bsegs); cudaFree(g->csegs);
   cudaFree(g->ops); cudaFree(g->edges); cudaFree(g->world_off); cudaFree(g->query_off); cudaFree(g->bops);
   cudaFree(g->bedges); cudaFree(g->crec); cudaFree(g->prec); cudaFree(g->wseed_off); cudaFree(g->qseed_off);
   cudaFree(g->qonly_off); cudaFree(g->leaf_rec); cudaFree(g->leaf_ptr);
@@ -840,38 +886,29 @@ HostOp make_op(const vael_circuit_desc_t* d, int n, OffFn off) {
   return h;
 }
 
-// Sort the ops of one level by kind (then fan-in), pad the level to a multiple of four, lay out the child lists:
-// every list starts at a multiple of four; the four lists of a group of same-kind n-ary ops are padded to one
-// length with pointers to the constant row that is the identity of the fold (zero_off / one_off).
+// Sort the ops of one level by kind (then fan-in), describe every run of one kind as a segment, lay out the child
+// lists: every list starts at a multiple of four and is padded to a multiple of four with pointers to the constant
+// row that is the identity of the fold (zero_off / one_off).
 void emit_level(std::vector<HostOp>& lvl, bool is_log, int zero_off, int one_off, std::vector<int4>& ops,
-                std::vector<int32_t>& edges) {
+                std::vector<int32_t>& edges, std::vector<int4>& segs) {
   if (lvl.empty()) return;
   std::stable_sort(lvl.begin(), lvl.end(), [](const HostOp& a, const HostOp& b) {
     return (a.op.w & 0xff) != (b.op.w & 0xff) ? (a.op.w & 0xff) < (b.op.w & 0xff) : (a.op.w >> 8) < (b.op.w >> 8);
   });
-  while (lvl.size() % 4) lvl.push_back(lvl.back());
-  for (size_t g = 0; g < lvl.size(); g += 4) {
-    const int k0 = lvl[g].op.w & 0xff;
-    bool same = true;
-    size_t len = 0;
-    for (int u = 0; u < 4; ++u) {
-      same = same && (lvl[g + u].op.w & 0xff) == k0;
-      len = std::max(len, (lvl[g + u].kids.size() + 3) / 4 * 4);
+  for (HostOp& h : lvl) {
+    const int code = h.op.w & 0xff;
+    if (!h.kids.empty()) {
+      const int pad = (code == OP_PRODN && !is_log) ? one_off : zero_off;
+      const size_t len = (h.kids.size() + 3) / 4 * 4;
+      h.op.y = (int)edges.size();
+      h.op.z = (int)len;
+      for (size_t e = 0; e < len; ++e) edges.push_back(e < h.kids.size() ? h.kids[e] : pad);
     }
-    const bool fold = same && (k0 == OP_PRODN || (!is_log && k0 == OP_SUMN));
-    for (int u = 0; u < 4; ++u) {
-      HostOp& h = lvl[g + u];
-      if (!h.kids.empty()) {
-        const int code = h.op.w & 0xff;
-        const int pad = (code == OP_PRODN && !is_log) ? one_off : zero_off;
-        const size_t mylen = fold ? len : (h.kids.size() + 3) / 4 * 4;
-        h.op.y = (int)edges.size();
-        h.op.z = (int)mylen;
-        for (size_t e = 0; e < mylen; ++e) edges.push_back(e < h.kids.size() ? h.kids[e] : pad);
-      }
-      ops.push_back(h.op);
-    }
+    if (segs.empty() || segs.back().x != code || segs.back().w != 0) segs.push_back(make_int4(code, (int)ops.size(), 0, 0));
+    ops.push_back(h.op);
+    segs.back().z = (int)ops.size();
   }
+  segs.back().w = 1;   // closed: the next level starts a new segment even when it continues the same kind
 }
 }  // namespace
 
@@ -886,12 +923,25 @@ static size_t tile_smem(size_t node_rows, int F, int n_small, int cols, int R) {
 }
 static bool choose_tile(size_t node_rows, int F, int n_small, int W, int Q, int* R_out, int* chunk, int* cap,
                         size_t* smem) {
-  static const int forced = [] { const char* v = getenv("VAEL_GEN_R"); return (v && *v) ? atoi(v) : 0; }();
+  // measured on B200 (2-digit circuit): R = 2 with ~24 warps per SM is as fast as R = 4 forward and faster
+  // backward (more CTAs per SM cover each other's level barriers); VAEL_GEN_R = 4 / 1 forces another width
+  static const int forced = [] { const char* v = getenv("VAEL_GEN_R"); return (v && *v) ? atoi(v) : 2; }();
+  // VAEL_GEN_CTAS = n: size the tile for n resident CTAs per SM, chunking the staged columns if need be
+  static const int ctas = [] { const char* v = getenv("VAEL_GEN_CTAS"); return (v && *v) ? std::max(1, atoi(v)) : 1; }();
+  const size_t limit = ctas > 1 ? ((size_t)227 * 1024) / ctas - 1024 - 64 : kSmemLimit;
   const int wcols = std::max(W, 1), qcols = std::min(std::max(Q, 1), 32);
   for (int R = 4; R >= 1; R >>= 1) {
     if (forced && R != forced && R != 1) continue;
     const size_t s = tile_smem(node_rows, F, n_small, std::max(wcols, qcols), R);
-    if (s <= kSmemLimit) { *R_out = R; *chunk = wcols; *cap = std::max(wcols, qcols); *smem = s; return true; }
+    if (s <= limit) { *R_out = R; *chunk = wcols; *cap = std::max(wcols, qcols); *smem = s; return true; }
+    if (ctas > 1 && (W & 3) == 0) {   // chunked staging at this R: at least 32 columns per chunk
+      const size_t fixed = tile_smem(node_rows, F, n_small, 0, R);
+      if (fixed + (size_t)128 * R * 32 <= limit) {
+        const int cols = (int)std::min<size_t>((limit - fixed) / (128 * R), (size_t)wcols) & ~3;
+        *R_out = R; *chunk = *cap = cols; *smem = tile_smem(node_rows, F, n_small, cols, R);
+        return true;
+      }
+    }
   }
   const size_t fixed = tile_smem(node_rows, F, n_small, 0, 1);
   if (fixed + 128 * 32 > kSmemLimit) { *R_out = 1; *chunk = *cap = 32; *smem = fixed + 128 * 32; return false; }
@@ -920,22 +970,22 @@ GenProgram* gen_program_create(const vael_circuit_desc_t* d, cudaError_t* err) {
   for (int n = N - 1; n >= 0; --n)
     if (out_cone[n])
       for (int e = d->child_ptr[n]; e < d->child_ptr[n + 1]; ++e) out_cone[d->child_idx[e]] = 1;
-  std::vector<int4> ops;
+  std::vector<int4> ops, segs;
   std::vector<int32_t> edges;
   for (int sch = 0; sch < 2; ++sch) {
     g->leaf_levels_f[sch] = 1;
     g->n_levels_f[sch] = 1;
     for (int L = 0; L < d->n_levels; ++L) {
-      g->op_level_ptr[sch][L] = (int)ops.size();
+      g->seg_level_ptr[sch][L] = (int)segs.size();
       std::vector<HostOp> lvl;
       for (int n = d->level_ptr[L]; n < d->level_ptr[L + 1]; ++n)
         if (sch == 0 || out_cone[n]) lvl.push_back(make_op(d, n, [&](int x) { return x * PBF; }));
       if (!lvl.empty()) g->n_levels_f[sch] = L + 1;
       for (const HostOp& h : lvl)
         if ((h.op.w & 0xff) <= OP_LEAF_NEG) g->leaf_levels_f[sch] = L + 1;
-      emit_level(lvl, is_log, N * PBF, (N + 1) * PBF, ops, edges);
+      emit_level(lvl, is_log, N * PBF, (N + 1) * PBF, ops, edges, segs);
     }
-    g->op_level_ptr[sch][d->n_levels] = (int)ops.size();
+    g->seg_level_ptr[sch][d->n_levels] = (int)segs.size();
   }
   std::vector<int32_t> world_off((d->n_worlds + 3) / 4 * 4, 0), query_off(d->n_queries);
   for (int w = 0; w < d->n_worlds; ++w) world_off[w] = d->world_node[w] * PBF;
@@ -966,20 +1016,19 @@ GenProgram* gen_program_create(const vael_circuit_desc_t* d, cudaError_t* err) {
   choose_tile((size_t)g->n_bvals + 2 + N + 1, d->n_facts, 2, d->n_worlds, 0, &g->rb, &g->cb, &unused_cap,
               &g->bwd_smem);
   const int PBB = 128 * g->rb;
-  std::vector<int4> bops;
+  std::vector<int4> bops, bsegs;
   std::vector<int32_t> bedges;
+  g->leaf_levels_b = 0;
   for (int L = 0; L < d->n_levels; ++L) {
-    g->bop_level_ptr[L] = (int)bops.size();
+    g->bseg_level_ptr[L] = (int)bsegs.size();
     std::vector<HostOp> lvl;
     for (int n = d->level_ptr[L]; n < d->level_ptr[L + 1]; ++n)
       if (need[n]) lvl.push_back(make_op(d, n, [&](int x) { return bslot[x] * PBB; }));
-    emit_level(lvl, is_log, g->n_bvals * PBB, (g->n_bvals + 1) * PBB, bops, bedges);
+    for (const HostOp& h : lvl)
+      if ((h.op.w & 0xff) <= OP_LEAF_NEG) g->leaf_levels_b = L + 1;
+    emit_level(lvl, is_log, g->n_bvals * PBB, (g->n_bvals + 1) * PBB, bops, bedges, bsegs);
   }
-  g->bop_level_ptr[d->n_levels] = (int)bops.size();
-  g->leaf_levels_b = 0;
-  for (int L = 0; L < d->n_levels; ++L)
-    for (int i = g->bop_level_ptr[L]; i < g->bop_level_ptr[L + 1]; ++i)
-      if ((bops[i].w & 0xff) <= OP_LEAF_NEG) g->leaf_levels_b = L + 1;
+  g->bseg_level_ptr[d->n_levels] = (int)bsegs.size();
   g->norm_slot_off = g->norm_node >= 0 ? bslot[g->norm_node] * PBB : -1;
 
   // ---- liveness: a node carries an adjoint iff it is an output (world / query node) or feeds a live node ----
@@ -997,10 +1046,11 @@ GenProgram* gen_program_create(const vael_circuit_desc_t* d, cudaError_t* err) {
       for (int e = d->child_ptr[p]; e < d->child_ptr[p + 1]; ++e)
         parents[d->child_idx[e]].push_back({p, e - d->child_ptr[p]});
 
-  std::vector<int4> crec;
+  std::vector<int4> crec, csegs;
   std::vector<int2> prec;
   for (int L = 0; L < d->n_levels; ++L) {
-    g->cl_ptr[L] = (int)crec.size();
+    g->cseg_level_ptr[L] = (int)csegs.size();
+    const size_t lvl_beg = crec.size();
     for (int c = d->level_ptr[L]; c < d->level_ptr[L + 1]; ++c) {
       if (!live[c] || parents[c].empty()) continue;
       int4 cr = make_int4(c * PBB, (int)prec.size(), (int)parents[c].size(), seed[c] ? CR_SEEDED : 0);
@@ -1040,13 +1090,17 @@ GenProgram* gen_program_create(const vael_circuit_desc_t* d, cudaError_t* err) {
       if (uniform >= 0) cr.w |= (1 + uniform) << CR_UNIFORM_SHIFT;
       crec.push_back(cr);
     }
-    // children with the same shape next to each other -> homogeneous groups of four; pad with scratch writers
-    std::stable_sort(crec.begin() + g->cl_ptr[L], crec.end(), [](const int4& a, const int4& b) {
+    // children with the same shape next to each other -> one segment per shape
+    std::stable_sort(crec.begin() + lvl_beg, crec.end(), [](const int4& a, const int4& b) {
       return a.w != b.w ? a.w < b.w : a.z < b.z;
     });
-    while ((crec.size() - g->cl_ptr[L]) % 4) crec.push_back(make_int4(N * PBB, 0, 0, 0));
+    for (size_t i = lvl_beg; i < crec.size(); ++i) {
+      if (i == lvl_beg || csegs.back().x != crec[i].w || csegs.back().w != crec[i].z)
+        csegs.push_back(make_int4(crec[i].w, (int)i, 0, crec[i].z));
+      csegs.back().z = (int)i + 1;
+    }
   }
-  g->cl_ptr[d->n_levels] = (int)crec.size();
+  g->cseg_level_ptr[d->n_levels] = (int)csegs.size();
 
   std::vector<int32_t> wseed((d->n_worlds + 3) / 4 * 4, N * PBB), qseed(d->n_queries), qonly;
   for (int w = 0; w < d->n_worlds; ++w) wseed[w] = d->world_node[w] * PBB;
@@ -1074,7 +1128,8 @@ GenProgram* gen_program_create(const vael_circuit_desc_t* d, cudaError_t* err) {
 
 
   cudaError_t e = cudaSuccess;
-  e = up(&g->ops, ops, e); e = up(&g->edges, edges, e); e = up(&g->world_off, world_off, e);
+  e = up(&g->ops, ops, e); e = up(&g->edges, edges, e); e = up(&g->segs, segs, e); e = up(&g->bsegs, bsegs, e);
+  e = up(&g->csegs, csegs, e); e = up(&g->world_off, world_off, e);
   e = up(&g->query_off, query_off, e); e = up(&g->bops, bops, e); e = up(&g->bedges, bedges, e);
   e = up(&g->crec, crec, e); e = up(&g->prec, prec, e); e = up(&g->wseed_off, wseed, e);
   e = up(&g->qseed_off, qseed, e); e = up(&g->qonly_off, qonly, e); e = up(&g->leaf_rec, leaf_rec, e);
