@@ -342,9 +342,26 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_s = max_over_ranks((time.perf_counter() - te0) / ke)
         assert torch.equal(hw[:4096], worlds[:4096].cpu()), "e2e path and device path disagree"
+        # what the link can do: the same bytes as plain pinned copies, both directions at once on two streams
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        d_up = torch.empty_like(hgw, device=dev); d_dn = torch.empty_like(hw, device=dev)
+        torch.cuda.synchronize()
+        tp0 = time.perf_counter()
+        for _ in range(3):
+            with torch.cuda.stream(s_up):
+                d_up.copy_(hgw, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                hw.copy_(d_dn, non_blocking=True)
+        torch.cuda.synchronize()
+        link_gbs = Be * 400 / ((time.perf_counter() - tp0) / 3) / 1e9
+        del d_up, d_dn
         e2e = {"value": world * Be * EVALS_PER_ROW / e2e_s, "unit": "evals/s",
                "h2d_bytes_per_step": Be * (80 + 4 + 400 + 4), "d2h_bytes_per_step": Be * (400 + 4 + 80),
                "rows_per_gpu": Be, "ms_per_step": e2e_s * 1e3, "cpu_affinity": numa,
+               "link": {"achieved_GBs_each_way": Be * 488 / e2e_s / 1e9, "pinned_copy_both_ways_GBs_each_way": link_gbs,
+                        "frac": (Be * 488 / e2e_s / 1e9) / link_gbs,
+                        "what": "PCIe-bound: bytes each way / step time against plain pinned cudaMemcpyAsync "
+                                "running H2D and D2H concurrently on this box"},
                "api": "vael_circuit_fwdbwd_host (C-ABI, pinned host buffers, 128Ki-row chunks over 4 streams)"}
 
     # ---- secondary probe: VAEL train step (configs[1]), DDP when N > 1 --------------------------------

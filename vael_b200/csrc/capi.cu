@@ -292,14 +292,19 @@ extern "C" int vael_circuit_create(const vael_circuit_desc_t* d, vael_circuit_t*
   auto up = [&](auto** dp, const auto& v) { if (e == cudaSuccess) e = upload(dp, v); };
   if (masks_ok) {
     up(&c->d_qmask, qmask);
+    // member worlds of every query node in world order, as byte offsets of the world rows of the all-queries
+    // kernel's world-major tile ([W + 1][32] floats); every list is padded to a multiple of four with the
+    // offset of the all-zero row W
     std::vector<int32_t> qm_ptr(d->n_queries + 1, 0), qm_idx;
     for (int q = 0; q < d->n_queries; ++q) {
       for (int w = 0; w < d->n_worlds; ++w)
-        if ((qmask[(size_t)q * c->mask_words + (w >> 5)] >> (w & 31)) & 1u) qm_idx.push_back(w);
+        if ((qmask[(size_t)q * c->mask_words + (w >> 5)] >> (w & 31)) & 1u) qm_idx.push_back(w * 128);
+      while (qm_idx.size() % 4) qm_idx.push_back(d->n_worlds * 128);
       qm_ptr[q + 1] = (int32_t)qm_idx.size();
     }
-    if (qm_idx.empty()) qm_idx.push_back(0);
+    if (qm_idx.empty()) qm_idx.assign(4, d->n_worlds * 128);
     up(&c->d_qm_ptr, qm_ptr); up(&c->d_qm_idx, qm_idx);
+    c->qm_len = (int32_t)qm_idx.size();
   }
   if (!qmask_c.empty()) up(&c->d_qmask_c, qmask_c);
   if (e == cudaSuccess) c->gen = gen_program_create(d, &e);
@@ -390,7 +395,7 @@ extern "C" int vael_circuit_queries_all(const vael_circuit_t* c, const float* fa
   if (!queries_all) return fail(VAEL_E_INVALID, "null output");
   if (pick_kernel(c, flags, nullptr) == 2 && c->n_queries <= 64) {
     Ad2QParams P{};
-    P.facts = facts; P.B = B; P.n_queries = c->n_queries; P.qm_ptr = c->d_qm_ptr; P.qm_idx = c->d_qm_idx;
+    P.facts = facts; P.B = B; P.n_queries = c->n_queries; P.qm_ptr = c->d_qm_ptr; P.qm_idx = c->d_qm_idx; P.qm_len = c->qm_len;
     P.queries_all = queries_all;
     CK(ad2_queries_all(c->ad_na, c->ad_nb, P, flags & VAEL_FLAG_NORMALIZE, c->num_sms, static_cast<cudaStream_t>(stream)));
     g_last_kernel = "ad2-queries";

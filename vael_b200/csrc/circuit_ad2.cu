@@ -422,52 +422,99 @@ __global__ void __launch_bounds__(256) ad2_backward_kernel(const Ad2Params P) {
 // all query nodes at once: queries_all[b, q] = sum over the member worlds of q, in world order
 // (the worlds[B,W] @ w_q[W,Q] mask contraction of utils/mnist_utils/metrics.py:71-75 and
 // compute_query, models/vael.py:200-206, fused after the product level: the worlds never leave the SM).
-// One warp per 32-row tile, lane <-> row; the W products of a row live in a shared-memory row
-// (written 128-bit, read back per member), the [32,Q] result tile is contiguous in global memory.
+// One warp per 32-row tile, lane <-> row.  The W products of the tile live in shared memory WORLD-major
+// (ws[w][lane]: every access is 32 consecutive words, conflict-free), plus one all-zero row the padded
+// member lists point at.  The member lists (byte offsets of world rows, padded to multiples of four) are
+// fetched 128 bits at a time and four queries are folded side by side: four independent FADD chains per
+// lane, each sequential in world order, so the result is bit-exact against the CSR fold.  The [32,Q]
+// result tile is contiguous in global memory.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ float q_lds(uint32_t a) {
+  float x;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(a));
+  return x;
+}
+__device__ __forceinline__ void q_sts(uint32_t a, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); }
+
+template <int NA, int NB>
+constexpr int queries_per_warp_bytes(int Q) {
+  return Ad2Shape<NA, NB>::FACT_BYTES + (Ad2Shape<NA, NB>::W + 1) * kWarp * 4 + ((kWarp * Q * 4 + 127) / 128) * 128;
+}
+
 template <int NA, int NB, bool NORM>
 __global__ void __launch_bounds__(256) ad2_queries_kernel(const Ad2QParams P) {
   using Sh = Ad2Shape<NA, NB>;
-  constexpr int F = Sh::F, W = Sh::W, FV = Sh::FV, WV = Sh::WV;
+  constexpr int F = Sh::F, W = Sh::W, FV = Sh::FV;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int Q = P.n_queries;
-  const int per_warp = Sh::FACT_BYTES + Sh::OUT_BYTES + ((kWarp * Q * 4 + 127) / 128) * 128;
-  float* fs = reinterpret_cast<float*>(smem + (size_t)warp * per_warp);
-  float* ws = reinterpret_cast<float*>(smem + (size_t)warp * per_warp + Sh::FACT_BYTES);
-  float* qs = reinterpret_cast<float*>(smem + (size_t)warp * per_warp + Sh::FACT_BYTES + Sh::OUT_BYTES);
+  const int per_warp = queries_per_warp_bytes<NA, NB>(Q);
+  float* fs = reinterpret_cast<float*>(smem + (size_t)warp * per_warp);                               // [32][F]
+  float* ws = reinterpret_cast<float*>(smem + (size_t)warp * per_warp + Sh::FACT_BYTES);               // [W + 1][32]
+  float* qs = reinterpret_cast<float*>(smem + (size_t)warp * per_warp + Sh::FACT_BYTES + (W + 1) * kWarp * 4);  // [32][Q]
+  const uint32_t wl = smem_u32(ws) + lane * 4;
+  q_sts(wl + W * 128, 0.0f);   // the zero row (written once)
+  // the member lists live in shared memory too (a few hundred bytes): the streaming fact loads would keep
+  // evicting them from L1 and every list fetch would pay an L2 round trip
+  int32_t* tab_ptr = reinterpret_cast<int32_t*>(smem + (size_t)nwarps * per_warp);   // [Q + 1], 16-byte aligned
+  int32_t* tab_idx = tab_ptr + ((Q + 1 + 3) & ~3);                                   // [qm_len]
+  for (int i = threadIdx.x; i <= Q; i += blockDim.x) tab_ptr[i] = __ldg(P.qm_ptr + i);
+  for (int i = threadIdx.x; i < P.qm_len; i += blockDim.x) tab_idx[i] = __ldg(P.qm_idx + i);
+  __syncthreads();
 
   const long long n_sub = (P.B + kWarp - 1) / kWarp;
   const long long gw = (long long)blockIdx.x * nwarps + warp;
   const long long GW = (long long)gridDim.x * nwarps;
+  // the next tile's facts are requested one iteration ahead (coalesced, F registers per lane) so that the HBM
+  // latency of the load hides behind the current tile's folds
+  float nx[F];
+  auto fetch = [&](long long sub) {
+    const long long r0 = sub * kWarp;
+    const int n = (sub < n_sub) ? (int)min((long long)kWarp, P.B - r0) * F : 0;
+    const float* src = P.facts + r0 * F;
+#pragma unroll
+    for (int k = 0; k < F; ++k) nx[k] = (k * kWarp + lane < n) ? __ldg(src + k * kWarp + lane) : 0.5f;
+  };
+  fetch(gw);
   for (long long sub = gw; sub < n_sub; sub += GW) {
     const long long row0 = sub * kWarp;
     const int rows = (int)min((long long)kWarp, P.B - row0);
     __syncwarp();
-    {
-      const float* src = P.facts + row0 * F;
-      for (int i = lane; i < kWarp * F; i += kWarp) fs[i] = (i < rows * F) ? __ldg(src + i) : 0.5f;
-    }
+#pragma unroll
+    for (int k = 0; k < F; ++k) fs[k * kWarp + lane] = nx[k];
     __syncwarp();
+    fetch(sub + GW);
     float p[F];
 #pragma unroll
     for (int c = 0; c < F / FV; ++c) lds_vec<FV>(p + c * FV, fs + lane * F + c * FV);
     float z = 1.0f;
     if constexpr (NORM) z = ad2_normaliser<NA, NB>(p);
-    float* wrow = ws + lane * W;
 #pragma unroll
-    for (int c = 0; c < W / WV; ++c) {
-      float o[WV];
+    for (int w = 0; w < W; ++w) q_sts(wl + w * 128, __fmul_rn(p[w / NB], p[NA + (w % NB)]));
+    for (int q = 0; q < Q; q += 4) {
+      int b[4], n[4];
+      int nmax = 0;
 #pragma unroll
-      for (int u = 0; u < WV; ++u) o[u] = __fmul_rn(p[(c * WV + u) / NB], p[NA + ((c * WV + u) % NB)]);
-      sts_vec<WV>(wrow + c * WV, o);
-    }
-    for (int q = 0; q < Q; ++q) {
-      const int b = __ldg(P.qm_ptr + q), e = __ldg(P.qm_ptr + q + 1);
-      float acc = 0.0f;
-      for (int i = b; i < e; ++i) acc = __fadd_rn(acc, wrow[__ldg(P.qm_idx + i)]);
-      if constexpr (NORM) acc = acc / z;
-      qs[lane * Q + q] = acc;
+      for (int u = 0; u < 4; ++u) {
+        const int qq = min(q + u, Q - 1);
+        b[u] = tab_ptr[qq];
+        n[u] = tab_ptr[qq + 1] - b[u];
+        nmax = max(nmax, n[u]);
+      }
+      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      for (int e = 0; e < nmax; e += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (e < n[u]) {
+            const int4 o = *reinterpret_cast<const int4*>(tab_idx + b[u] + e);
+            const float v0 = q_lds(wl + o.x), v1 = q_lds(wl + o.y), v2 = q_lds(wl + o.z), v3 = q_lds(wl + o.w);
+            acc[u] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc[u], v0), v1), v2), v3);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (q + u < Q) qs[lane * Q + q + u] = NORM ? acc[u] / z : acc[u];
     }
     __syncwarp();
     float* dst = P.queries_all + row0 * Q;
@@ -548,16 +595,16 @@ static cudaError_t launch_fwd_shape(const Ad2Params& P, bool norm, bool evid, in
 
 template <int NA, int NB>
 static cudaError_t launch_queries(const Ad2QParams& P, bool norm, int num_sms, cudaStream_t st) {
-  using Sh = Ad2Shape<NA, NB>;
-  const int per_warp = Sh::FACT_BYTES + Sh::OUT_BYTES + ((kWarp * P.n_queries * 4 + 127) / 128) * 128;
+  const int per_warp = queries_per_warp_bytes<NA, NB>(P.n_queries);
   int nw = 8;
-  while (nw > 1 && nw * per_warp > 100 * 1024) --nw;  // two CTAs per SM
+  while (nw > 1 && nw * per_warp > 110 * 1024) --nw;  // two CTAs per SM
   auto kern = norm ? ad2_queries_kernel<NA, NB, true> : ad2_queries_kernel<NA, NB, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, nw * per_warp);
+  const int smem_bytes = nw * per_warp + (((P.n_queries + 1 + 3) & ~3) + P.qm_len) * 4;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return e;
   const long long n_sub = (P.B + kWarp - 1) / kWarp;
   const long long grid = min((n_sub + nw - 1) / nw, (long long)num_sms * 2);
-  kern<<<(unsigned)grid, nw * 32, nw * per_warp, st>>>(P);
+  kern<<<(unsigned)grid, nw * 32, smem_bytes, st>>>(P);
   return cudaGetLastError();
 }
 

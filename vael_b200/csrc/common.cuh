@@ -120,6 +120,7 @@ struct vael_circuit {
   bool norm_fast_ok;         // the normaliser node has the per-AD shape the fast paths recompute
   int32_t* d_qm_ptr;         // [n_queries+1] member worlds of every query node (CSR, world order) — set with d_qmask
   int32_t* d_qm_idx;
+  int32_t qm_len;
   uint32_t* d_qmask_c;       // fast_kind 3: [n_queries][np][ceil(na*nb/32)] chunked membership masks
   // host-buffer pipeline (allocated lazily by the *_host entry points)
   vael_host_slot slot[kHostSlots];

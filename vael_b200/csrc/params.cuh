@@ -25,8 +25,9 @@ struct Ad2QParams {           // all query nodes at once
   const float* facts;         // [B,F]
   long long B;
   int32_t n_queries;
-  const int32_t* qm_ptr;      // [Q+1] CSR of the member worlds of every query node, in world order
-  const int32_t* qm_idx;
+  const int32_t* qm_ptr;      // [Q+1] CSR of the member worlds of every query node, in world order; lists padded to x4
+  const int32_t* qm_idx;      // byte offsets (world * 128) into the kernel's world-major tile; padding -> the zero row
+  int32_t qm_len;             // length of qm_idx
   float* queries_all;         // [B,Q]
 };
 cudaError_t ad2_queries_all(int na, int nb, const Ad2QParams& P, bool norm, int num_sms, cudaStream_t st);
