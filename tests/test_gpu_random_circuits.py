@@ -76,3 +76,18 @@ def test_random_circuit_forward_and_adjoint(cuda_device, seed, log_semiring):
             ((w64 * torch.from_numpy(gw).double()).sum() + (q64 * torch.from_numpy(gq).double()).sum()).backward()
             g_ref = f64.grad.numpy()
             assert rel_err(f.grad.cpu().numpy(), g_ref, floor=1e-3 * np.abs(g_ref).max() + 1e-12) < 1e-4
+
+
+@pytest.mark.parametrize("env", [{"VAEL_GEN_R": "1"}, {"VAEL_GEN_R": "4"}, {"VAEL_GEN_R": "4", "VAEL_GEN_CTAS": "3"},
+                                 {"VAEL_GEN_R": "2", "VAEL_GEN_CTAS": "6", "VAEL_GEN_WARPS_PER_SM": "12"}],
+                         ids=lambda e: "-".join(f"{k[9:]}{v}" for k, v in e.items()))
+def test_generic_kernel_tile_shapes(cuda_device, env):
+    """The generic kernels pick rows-per-lane (R) and the staged chunk width once per process: every forced
+    shape (1 / 2 / 4 rows per lane, whole-tile and chunked row-by-row staging) must give the same bits."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "tests.variant_check"], cwd=root, env={**os.environ, **env},
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "variant_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
