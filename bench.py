@@ -475,6 +475,15 @@ def secondary_probe(args, dev, rank, world, barrier, max_over_ranks, lib):
         "rows_per_gpu": B, "kernel_family": _lib.last_kernel(), "evals_per_sec": world * B * 1001 / ((f_ms + b_ms) * 1e-3),
         "fwd": {"ms": f_ms, "bytes_per_row": 4128, "GBs": B * 4128 / f_ms / 1e6, "frac": B * 4128 / f_ms / 1e6 / peak},
         "bwd": {"ms": b_ms, "bytes_per_row": 4248, "GBs": B * 4248 / b_ms / 1e6, "frac": B * 4248 / b_ms / 1e6 / peak}}
+    Bg = B // 4   # the same circuit through the generic CSR kernels (1163 nodes: R = 1 tiles, chunked staging)
+    f_ms, b_ms = _time_pair(
+        lambda: _lib.check(lib.vael_circuit_forward(dc3.handle, _p(facts), _p(qidx), -1, Bg, _p(worlds), _p(query), 4, sp)),
+        lambda: _lib.check(lib.vael_circuit_backward(dc3.handle, _p(facts), _p(qidx), -1, Bg, _p(gw), _p(gq), _p(gf), 4, sp)),
+        5, barrier, max_over_ranks)
+    out["generic_csr_3digit"] = {
+        "workload": "3-digit circuit through the generic level-ordered CSR kernels", "rows_per_gpu": Bg,
+        "fwd": {"ms": f_ms, "GBs": Bg * 4128 / f_ms / 1e6, "frac": Bg * 4128 / f_ms / 1e6 / peak},
+        "bwd": {"ms": b_ms, "GBs": Bg * 4248 / b_ms / 1e6, "frac": Bg * 4248 / b_ms / 1e6 / peak}}
     del worlds, gw, facts, p
     torch.cuda.empty_cache()
 
@@ -493,6 +502,50 @@ def secondary_probe(args, dev, rank, world, barrier, max_over_ranks, lib):
         "workload": "2-digit circuit through the generic level-ordered CSR kernels", "rows_per_gpu": B2,
         "fwd": {"ms": f_ms, "GBs": B2 * FWD_BYTES / f_ms / 1e6, "frac": B2 * FWD_BYTES / f_ms / 1e6 / peak},
         "bwd": {"ms": b_ms, "GBs": B2 * BWD_BYTES / b_ms / 1e6, "frac": B2 * BWD_BYTES / b_ms / 1e6 / peak}}
+    del w2, gw2, facts2
+    torch.cuda.empty_cache()
+
+    # -- Mario circuits (configs[2]): worlds / move query over 2 x 9 position facts (prob semiring, ad2<9,9>) and
+    # the 24 admissible worlds' log-probabilities (log semiring: products of 18 positive / negative literals,
+    # the generic CSR kernel's production user)
+    try:
+        from vael_b200.mario_task import admissible_circuit, compile_mario_family, mario_tables
+        Bm = 1 << 21
+        fam = compile_mario_family((3, 3))
+        dcm = DeviceCircuit(fam.circuit, dev)
+        dca = DeviceCircuit(admissible_circuit(mario_tables(fam)[2]), dev)
+        gm = torch.Generator(device=dev).manual_seed(parallel.rank_seed(555, rank))
+        pm = torch.softmax(torch.randn(Bm, 2, 9, device=dev, generator=gm), -1).clamp(1e-5, 0.9999).reshape(Bm, 18).contiguous()
+        qm = torch.randint(0, 4, (Bm,), device=dev, dtype=torch.int32, generator=gm)
+        wm = torch.empty(Bm, 81, device=dev); qom = torch.empty(Bm, device=dev); gfm = torch.empty(Bm, 18, device=dev)
+        gwm = torch.randn(Bm, 81, device=dev, generator=gm); gqm = torch.randn(Bm, device=dev, generator=gm)
+        f_ms, b_ms = _time_pair(
+            lambda: _lib.check(lib.vael_circuit_forward(dcm.handle, _p(pm), _p(qm), -1, Bm, _p(wm), _p(qom), 0, sp)),
+            lambda: _lib.check(lib.vael_circuit_backward(dcm.handle, _p(pm), _p(qm), -1, Bm, _p(gwm), _p(gqm), _p(gfm), 0, sp)),
+            10, barrier, max_over_ranks)
+        fam_m = _lib.last_kernel()
+        fb, bb = 72 + 4 + 324 + 4, 324 + 4 + 72 + 4 + 72
+        la = torch.empty(Bm, 24, device=dev); gla = torch.randn(Bm, 24, device=dev, generator=gm)
+        fa_ms, ba_ms = _time_pair(
+            lambda: _lib.check(lib.vael_circuit_forward(dca.handle, _p(pm), None, -1, Bm, _p(la), None, 0, sp)),
+            lambda: _lib.check(lib.vael_circuit_backward(dca.handle, _p(pm), None, -1, Bm, _p(gla), None, _p(gfm), 0, sp)),
+            10, barrier, max_over_ranks)
+        fab, bab = 72 + 96, 96 + 72 + 72
+        out["mario_circuits"] = {
+            "workload": "Mario 3x3: worlds[81] + move query (prob semiring) and admissible-world log-probabilities[24] "
+                        "(log semiring), fwd+bwd, fp32", "rows_per_gpu": Bm,
+            "worlds_query": {"kernel_family": fam_m,
+                             "fwd": {"ms": f_ms, "bytes_per_row": fb, "GBs": Bm * fb / f_ms / 1e6, "frac": Bm * fb / f_ms / 1e6 / peak},
+                             "bwd": {"ms": b_ms, "bytes_per_row": bb, "GBs": Bm * bb / b_ms / 1e6, "frac": Bm * bb / b_ms / 1e6 / peak}},
+            "admissible_logprob": {"kernel_family": _lib.last_kernel(),
+                                   "fwd": {"ms": fa_ms, "bytes_per_row": fab, "GBs": Bm * fab / fa_ms / 1e6, "frac": Bm * fab / fa_ms / 1e6 / peak},
+                                   "bwd": {"ms": ba_ms, "bytes_per_row": bab, "GBs": Bm * bab / ba_ms / 1e6, "frac": Bm * bab / ba_ms / 1e6 / peak}}}
+        del wm, gwm, la, gla, pm
+        torch.cuda.empty_cache()
+    except Exception as exc:  # noqa: BLE001 - a secondary probe must not take the headline down
+        out["mario_circuits"] = {"error": repr(exc)[:300]}
+
+    facts2, g2 = synthetic_facts(B2, dev, parallel.rank_seed(99, rank))
     qa = torch.empty(B2, 19, device=dev)
     a_ms, _ = _time_pair(lambda: _lib.check(lib.vael_circuit_queries_all(dc2.handle, _p(facts2), B2, _p(qa), 0, sp)),
                          lambda: None, 10, barrier, max_over_ranks)

@@ -13,4 +13,11 @@ if [ "$1" == "ncu" ]; then
   echo ncu_list_rc=$?
   $CMD > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:ad2_ -s 6 -c 2 -o gpurun_out/prof_ad2 -f $CMD > gpurun_out/ncu_full.log 2>&1
   echo ncu_full_rc=$?
+  # the generic CSR kernels (2-digit circuit, VAEL_FLAG_FORCE_GENERIC) and the all-queries kernel
+  GCMD="python scripts/quick_bench.py 2097152 generic"
+  $GCMD > gpurun_out/gen_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:generic_ -s 12 -c 2 -o gpurun_out/prof_gen -f $GCMD > gpurun_out/ncu_gen.log 2>&1
+  echo ncu_gen_rc=$?
+  QCMD="python bench.py --steps 2 --warmup 3 --no-train --no-cpu --no-e2e"
+  ncu --set full --clock-control none --import-source on -k regex:ad2_queries -s 3 -c 1 -o gpurun_out/prof_q -f $QCMD > gpurun_out/ncu_q.log 2>&1
+  echo ncu_q_rc=$?
 fi
