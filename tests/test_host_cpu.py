@@ -319,3 +319,61 @@ def test_program_text_is_what_the_reference_generator_writes():
         for add in (0, 9, 18):
             assert ref.define_ProbLog_model(facts, rules, label=add, digit_query="digits(X,Y)", mode=mode) == \
                 mnist_task.define_ProbLog_model(facts, rules, label=add, digit_query="digits(X,Y)", mode=mode)
+
+
+def _small_models():
+    import torch
+    from vael_b200 import networks as N
+    from vael_b200.mario_task import compile_mario_family, mario_tables
+    from vael_b200.vael import MarioVAELModel, MNISTPairsVAELModel
+    dev = torch.device("cpu")
+    mnist = MNISTPairsVAELModel(N.MNISTPairsEncoder(hidden_channels=4, latent_dim=23),
+                                N.MNISTPairsDecoder(label_dim=20, hidden_channels=4, latent_dim=8),
+                                N.MNISTPairsMLP(in_features=15, n_facts=20), (15, 8), None, torch.zeros(100, 20), dropout=0.5,
+                                is_train=True, device=dev)
+    W_all, WQ_all, W_adm, WQ_adm = (torch.from_numpy(t.astype("float32")) for t in mario_tables(compile_mario_family((3, 3))))
+    mario = MarioVAELModel(N.MarioEncoder(img_channels=3, hidden_channels=2, latent_dim=48),
+                           N.MarioDecoder(img_channels=3, hidden_channels=2, latent_dim_sub=30, label_dim=9),
+                           N.MarioMLP(in_features=18, n_facts=18, hidden_channels=32), (18, 30), None, WQ_all, W_all, WQ_adm,
+                           W_adm, (3, 3), dropout=0.5, is_train=True, device=dev)
+    return {"MNISTPairsVAELModel": (mnist, "ref_checkpoint_mnist.pt"), "MarioVAELModel": (mario, "ref_checkpoint_mario.pt")}
+
+
+def test_reference_checkpoints_load_and_round_trip(tmp_path):
+    """{'model', 'optimizer'} checkpoints written by the reference's own classes (utils/early_stopping.py:53-65;
+    tests/golden/make_checkpoint_golden.py) load strictly into this repo's models with their Adam state, and a
+    checkpoint written here has exactly the reference's keys and shapes."""
+    import json
+    import torch
+    from vael_b200.checkpoint import load_checkpoint, save_checkpoint
+    lay = json.load(open(os.path.join(G, "checkpoint_layouts.json")))
+    for name, (model, fname) in _small_models().items():
+        assert {k: list(v.shape) for k, v in model.state_dict().items()} == lay[name], name
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        ckpt = load_checkpoint(os.path.join(G, fname), model, opt, map_location="cpu")
+        assert set(ckpt) == {"model", "optimizer"}
+        for k, v in model.state_dict().items():
+            assert torch.equal(v, ckpt["model"][k]), k
+        st = opt.state_dict()["state"]
+        assert len(st) == len(list(model.parameters())) and all(int(s["step"]) == 1 for s in st.values())
+        out = save_checkpoint(model, opt, str(tmp_path / name / "checkpoint.pt"))
+        again = torch.load(out, weights_only=True)
+        assert list(again) == ["model", "optimizer"]
+        assert {k: list(v.shape) for k, v in again["model"].items()} == lay[name]
+        assert again["optimizer"]["param_groups"][0]["lr"] == ckpt["optimizer"]["param_groups"][0]["lr"]
+    with pytest.raises(ValueError):
+        torch.save({"weights": {}}, str(tmp_path / "bad.pt"))
+        load_checkpoint(str(tmp_path / "bad.pt"), model)
+
+
+def test_learning_curve_files_round_trip(tmp_path):
+    """train_info.npy / validation_info.npy: dict of per-epoch means under the reference's keys
+    (utils/mnist_utils/train.py:74-93,160-164,239-240), read back the way its analysis code reads them."""
+    from vael_b200.checkpoint import CURVE_KEYS, append_epoch, load_curves, save_curves
+    tr, va = {}, {}
+    for e in range(3):
+        append_epoch(tr, {k: 10.0 - e + i for i, k in enumerate(CURVE_KEYS)})
+        append_epoch(va, {k: 11.0 - e + i for i, k in enumerate(CURVE_KEYS)})
+    save_curves(str(tmp_path), tr, va)
+    tr2, va2 = load_curves(str(tmp_path))
+    assert list(tr2) == list(CURVE_KEYS) and tr2 == tr and va2 == va and len(tr2["elbo"]) == 3
