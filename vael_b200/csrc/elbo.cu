@@ -100,23 +100,38 @@ __global__ void __launch_bounds__(256) elbo_terms_kernel(const ElboParams P) {
     is_last = (done == gridDim.x - 1);
   }
   __syncthreads();
-  if (is_last && tid == 0) {
+  if (is_last) {
+    // every partial is final; the 256 threads of the last CTA add them in a FIXED pattern (thread t takes
+    // partials t, t + 256, ...; then a shuffle tree; then the eight warp sums in order), so the result does
+    // not depend on which CTA happened to finish last
     __threadfence();
     double r = 0.0, k = 0.0, q = 0.0;
     const volatile double* part = P.partials;
-    for (unsigned int b = 0; b < gridDim.x; ++b) {
+    for (unsigned int b = tid; b < gridDim.x; b += blockDim.x) {
       r += part[b * 3 + 0];
       k += part[b * 3 + 1];
       q += part[b * 3 + 2];
     }
-    // recon = mean_b ( D log 2 + sum_pix |x - recon| )
-    const float recon = (float)((double)P.D * 0.69314718055994531 + r / (double)P.B);
-    const float kl = (float)(-0.5 * k / (double)P.B), qb = (float)(q / (double)P.B);
-    P.terms[1] = recon;
-    P.terms[2] = kl;
-    P.terms[3] = qb;
-    P.terms[0] = P.recon_w * recon + P.kl_w * kl + P.query_w * qb;
-    *P.counter = 0u;  // self-cleaning for the next call
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      r += __shfl_xor_sync(0xffffffffu, r, o);
+      k += __shfl_xor_sync(0xffffffffu, k, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) { red[0][warp] = r; red[1][warp] = k; red[2][warp] = q; }
+    __syncthreads();
+    if (tid == 0) {
+      r = k = q = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { r += red[0][w]; k += red[1][w]; q += red[2][w]; }
+      // recon = mean_b ( D log 2 + sum_pix |x - recon| )
+      const float recon = (float)((double)P.D * 0.69314718055994531 + r / (double)P.B);
+      const float kl = (float)(-0.5 * k / (double)P.B), qb = (float)(q / (double)P.B);
+      P.terms[1] = recon;
+      P.terms[2] = kl;
+      P.terms[3] = qb;
+      P.terms[0] = P.recon_w * recon + P.kl_w * kl + P.query_w * qb;
+      *P.counter = 0u;  // self-cleaning for the next call
+    }
   }
 }
 

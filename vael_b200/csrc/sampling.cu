@@ -39,8 +39,24 @@ __global__ void __launch_bounds__(256) gumbel_forward_kernel(const GumbelParams 
   const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
   const float inv_tau = 1.0f / P.tau;
+  // the next row's scores (and injected noise) are requested one iteration ahead: a warp works on one row at
+  // a time, so without this every row would pay a full HBM round trip before its first instruction
+  float s_nx[ITEMS], n_nx[ITEMS];
+  auto fetch = [&](long long row) {
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const int e = lane + j * kWarp;
+      const bool on = row < P.B && e < P.W;
+      s_nx[j] = on ? __ldg(P.scores + row * P.W + e) : 1.0f;
+      n_nx[j] = (on && P.noise != nullptr) ? __ldg(P.noise + row * P.W + e) : 0.0f;
+    }
+  };
+  fetch(gwarp);
   for (long long row = gwarp; row < P.B; row += nwarp) {
-    float z[ITEMS];
+    float z[ITEMS], sc[ITEMS], nz[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) { sc[j] = s_nx[j]; nz[j] = n_nx[j]; }
+    fetch(row + nwarp);
     float mx = -INFINITY;
     int arg = 0x7fffffff;
     uint32_t rnd[4] = {0u, 0u, 0u, 0u};
@@ -56,9 +72,8 @@ __global__ void __launch_bounds__(256) gumbel_forward_kernel(const GumbelParams 
         rnd[0] = r.x; rnd[1] = r.y; rnd[2] = r.z; rnd[3] = r.w;
       }
       if (e < P.W) {
-        const float s = __ldg(P.scores + row * P.W + e);
-        const float logit = P.is_log ? s : logf(s);
-        const float g = (P.noise != nullptr) ? __ldg(P.noise + row * P.W + e) : gumbel_from_bits(rnd[j & 3]);
+        const float logit = P.is_log ? sc[j] : logf(sc[j]);
+        const float g = (P.noise != nullptr) ? nz[j] : gumbel_from_bits(rnd[j & 3]);
         z[j] = (logit + g) * inv_tau;
         if (z[j] > mx) { mx = z[j]; arg = e; }
       }
