@@ -539,7 +539,10 @@ template <int NA, int NB, bool NORM, bool EVID, int S, int SO, bool STG = false>
 static cudaError_t launch_fwd_cfg(const Ad2Params& P, int num_sms, cudaStream_t st) {
   using Sh = Ad2Shape<NA, NB>;
   constexpr int PER_WARP = S * Sh::FACT_BYTES + SO * Sh::OUT_BYTES + 128;
-  int nw = max(1, min(8, env_int("VAEL_AD2_FWD_WARPS", 5)));
+  // warps per SM measured on B200 (scripts/ad2_warp_sweep.sh): the write-dominated forward wants FEW store streams
+  // in flight for the 12.8 KB tiles of the 10 x 10 shape (5: 0.92 of the copy peak; 6-8: 0.87) and one more for
+  // the 10.4 KB tiles of Mario's 9 x 9 (6: 0.89; 5: 0.83)
+  int nw = max(1, min(8, env_int("VAEL_AD2_FWD_WARPS", Sh::W >= 100 ? 5 : 6)));
   while (nw > 1 && nw * PER_WARP > 227 * 1024) --nw;
   const int cps = max(1, min(8, env_int("VAEL_AD2_FWD_CTAS_PER_SM", (227 * 1024) / (nw * PER_WARP + 1024))));
   cudaError_t e = cudaFuncSetAttribute(ad2_forward_kernel<NA, NB, NORM, EVID, S, SO, STG>,
@@ -572,7 +575,8 @@ static cudaError_t launch_bwd_t(const Ad2Params& P, int num_sms, cudaStream_t st
   constexpr int S = 2, SO = 2;
   using Sh = Ad2Shape<NA, NB>;
   constexpr int PER_WARP = S * (Sh::FACT_BYTES + Sh::OUT_BYTES) + SO * Sh::FACT_BYTES + 128;
-  int nw = max(1, min(8, env_int("VAEL_AD2_BWD_WARPS", 6)));
+  // read-dominated: more loads in flight help (10 x 10: 6 warps 0.96; 9 x 9: 7 warps 0.88, 6 warps 0.79)
+  int nw = max(1, min(8, env_int("VAEL_AD2_BWD_WARPS", Sh::W >= 100 ? 6 : 7)));
   while (nw > 1 && nw * PER_WARP > 227 * 1024) --nw;
   const int cps = max(1, min(8, env_int("VAEL_AD2_BWD_CTAS_PER_SM", (227 * 1024) / (nw * PER_WARP + 1024))));
   cudaError_t e = cudaFuncSetAttribute(ad2_backward_kernel<NA, NB, NORM, S, SO>,

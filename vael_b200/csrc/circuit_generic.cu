@@ -58,6 +58,7 @@ struct GenProgram {
   int4* ops;               // {dst, a, b, kind | nc << 8}; leaves: a = fact column; n-ary ops: a = first edge (multiple of 4), b = padded length
   int32_t* edges;          // child offsets of the n-ary ops
   int4* segs;              // runs of equal op kind inside a level: {kind, first op, end, 0}
+  int32_t n_ops, n_edges, n_segs, sched_in_smem;  // forward schedule sizes; staged in shared memory when small
   int32_t seg_level_ptr[2][kMaxLevels + 1];  // [0]: every node; [1]: without the cone only the normaliser needs
   int32_t* world_off;      // [W] (padded to a multiple of 4)
   int32_t* query_off;      // [Q]
@@ -66,6 +67,7 @@ struct GenProgram {
   int4* bops;
   int32_t* bedges;
   int4* bsegs;
+  int32_t n_bops, n_bedges, n_bsegs, n_crec, n_csegs, n_prec, bsched_in_smem;  // backward schedule sizes
   int32_t bseg_level_ptr[kMaxLevels + 1];
   int32_t norm_slot_off;   // byte offset of Z in the slot space, or -1
   int4* crec;              // live children, level by level: {adj off, first record, n records, flags}
@@ -169,6 +171,50 @@ __device__ __forceinline__ VecT<R> vfma(const VecT<R>& a, const VecT<R>& b, cons
   return o;
 }
 
+// A read-only schedule table: global memory through the non-coherent path (__ldg), or — when the schedule is small
+// enough to be staged once per CTA — shared memory through ld.shared WITHOUT a memory clobber, so that the
+// compiler may move the fetch across the value stores of the preceding op (the table never changes after staging).
+template <bool SS, typename T>
+struct Tab {
+  const T* g;
+  uint32_t s;
+  // Construct AFTER the barrier that follows the staging copy: the shared address is passed through a volatile
+  // asm there, so no (side-effect-free) table fetch can be scheduled above that point.
+  __device__ __forceinline__ Tab(const T* gp, const void* sp) : g(gp), s(0u) {
+    if constexpr (SS) {
+      const uint32_t a = smem_u32(sp);
+      asm volatile("mov.u32 %0, %1;" : "=r"(s) : "r"(a) : "memory");
+    }
+  }
+  __device__ __forceinline__ int4 ld16(int i) const {   // 16 bytes starting at element i
+    if constexpr (SS) {
+      int4 v;
+      asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(s + i * (int)sizeof(T)));
+      return v;
+    } else {
+      return __ldg(reinterpret_cast<const int4*>(g + i));
+    }
+  }
+  __device__ __forceinline__ int2 ld8(int i) const {
+    if constexpr (SS) {
+      int2 v;
+      asm("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(s + i * (int)sizeof(T)));
+      return v;
+    } else {
+      return __ldg(reinterpret_cast<const int2*>(g + i));
+    }
+  }
+  __device__ __forceinline__ int32_t ld4(int i) const {
+    if constexpr (SS) {
+      int32_t v;
+      asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(s + i * (int)sizeof(T)));
+      return v;
+    } else {
+      return __ldg(reinterpret_cast<const int32_t*>(g + i));
+    }
+  }
+};
+
 // ---- staged I/O: [rows, cc] chunk (columns c0 .. c0+cc) of a row-major [B, K] tensor <-> stage[r * cc + c] ----
 // mode 0: plain coalesced copy by all threads; 1: the chunk is the whole contiguous tile, one bulk copy;
 // 2: one bulk copy per row.  The mode is CTA-uniform.
@@ -239,8 +285,8 @@ __device__ __forceinline__ VecT<R> leaf_value(uint32_t fl, int F, int col, bool 
 }
 
 // any op kind (the slow path: kinds without a tight loop in run_level)
-template <int R, bool LOG>
-__device__ __noinline__ VecT<R> exec_op(const int4 d, uint32_t fl, int F, uint32_t vl, const int32_t* edges) {
+template <int R, bool LOG, bool SS>
+__device__ __noinline__ VecT<R> exec_op(const int4 d, uint32_t fl, int F, uint32_t vl, const Tab<SS, int32_t> edges) {
   const int kind = d.w & 0xff, nc = d.w >> 8;
   switch (kind) {
     case OP_LEAF_POS: return leaf_value<R, LOG>(fl, F, d.y, false);
@@ -255,9 +301,9 @@ __device__ __noinline__ VecT<R> exec_op(const int4 d, uint32_t fl, int F, uint32
     case OP_IDENT_ONE: return vfill<R>(LOG ? 0.0f : 1.0f);
     case OP_IDENT_ZERO: return vfill<R>(LOG ? -INFINITY : 0.0f);
     case OP_PRODN: {
-      VecT<R> acc = ldv<R>(vl, __ldg(edges + d.y));
+      VecT<R> acc = ldv<R>(vl, edges.ld4(d.y));
       for (int e = 1; e < nc; ++e) {
-        const VecT<R> v = ldv<R>(vl, __ldg(edges + d.y + e));
+        const VecT<R> v = ldv<R>(vl, edges.ld4(d.y + e));
         acc = LOG ? vadd_rn<R>(acc, v) : vmul_rn<R>(acc, v);
       }
       return acc;
@@ -270,21 +316,21 @@ __device__ __noinline__ VecT<R> exec_op(const int4 d, uint32_t fl, int F, uint32
     if (kind == OP_ADD2 || kind == OP_COMPL2) {
       acc = vadd_rn<R>(ldv<R>(vl, d.y), ldv<R>(vl, d.z));
     } else {
-      acc = ldv<R>(vl, __ldg(edges + d.y));
-      for (int e = 1; e < nc; ++e) acc = vadd_rn<R>(acc, ldv<R>(vl, __ldg(edges + d.y + e)));
+      acc = ldv<R>(vl, edges.ld4(d.y));
+      for (int e = 1; e < nc; ++e) acc = vadd_rn<R>(acc, ldv<R>(vl, edges.ld4(d.y + e)));
     }
     return (kind == OP_COMPL2 || kind == OP_COMPLN) ? vcompl_rn<R>(acc) : acc;
   } else {  // logsumexp (COMPL is rejected for the log semiring at circuit creation)
     VecT<R> mx = vfill<R>(-INFINITY);
     for (int e = 0; e < nc; ++e) {
-      const int c = (kind == OP_ADD2) ? (e == 0 ? d.y : d.z) : __ldg(edges + d.y + e);
+      const int c = (kind == OP_ADD2) ? (e == 0 ? d.y : d.z) : edges.ld4(d.y + e);
       const VecT<R> v = ldv<R>(vl, c);
 #pragma unroll
       for (int j = 0; j < R; ++j) mx.v[j] = fmaxf(mx.v[j], v.v[j]);
     }
     VecT<R> s = vfill<R>(0.0f);
     for (int e = 0; e < nc; ++e) {
-      const int c = (kind == OP_ADD2) ? (e == 0 ? d.y : d.z) : __ldg(edges + d.y + e);
+      const int c = (kind == OP_ADD2) ? (e == 0 ? d.y : d.z) : edges.ld4(d.y + e);
       const VecT<R> v = ldv<R>(vl, c);
 #pragma unroll
       for (int j = 0; j < R; ++j) s.v[j] += expf(v.v[j] - mx.v[j]);
@@ -303,13 +349,12 @@ __device__ __noinline__ VecT<R> exec_op(const int4 d, uint32_t fl, int F, uint32
 // of branching (recomputing a node is harmless).  Binary ops: 2 G independent shared-memory loads, G R FP ops,
 // G stores.  N-ary folds: child lists padded to a multiple of four with pointers to the constant-0 / constant-1
 // rows and fetched 128 bits at a time, every fold sequential in CSR order (bit-exact).
-template <int R, int G, bool ADD>
-__device__ __forceinline__ void seg_binary(const int4* __restrict__ ops, int beg, int end, uint32_t vl, int warp,
-                                           int nwarps) {
+template <int R, int G, bool ADD, bool SS>
+__device__ __forceinline__ void seg_binary(const Tab<SS, int4> ops, int beg, int end, uint32_t vl, int warp, int nwarps) {
   for (int i = beg + G * warp; i < end; i += G * nwarps) {
     int4 d[G];
 #pragma unroll
-    for (int u = 0; u < G; ++u) d[u] = __ldg(ops + min(i + u, end - 1));
+    for (int u = 0; u < G; ++u) d[u] = ops.ld16(min(i + u, end - 1));
     VecT<R> x[G], y[G];
 #pragma unroll
     for (int u = 0; u < G; ++u) { x[u] = ldv<R>(vl, d[u].y); y[u] = ldv<R>(vl, d[u].z); }
@@ -317,15 +362,15 @@ __device__ __forceinline__ void seg_binary(const int4* __restrict__ ops, int beg
     for (int u = 0; u < G; ++u) stv<R>(vl, d[u].x, ADD ? vadd_rn<R>(x[u], y[u]) : vmul_rn<R>(x[u], y[u]));
   }
 }
-template <int R, int G, bool ADD>
-__device__ __forceinline__ void seg_fold(const int4* __restrict__ ops, const int32_t* __restrict__ edges, int beg,
-                                         int end, uint32_t vl, int warp, int nwarps) {
+template <int R, int G, bool ADD, bool SS>
+__device__ __forceinline__ void seg_fold(const Tab<SS, int4> ops, const Tab<SS, int32_t> edges, int beg, int end,
+                                         uint32_t vl, int warp, int nwarps) {
   for (int i = beg + G * warp; i < end; i += G * nwarps) {
     int4 d[G];
     int len = 0;
 #pragma unroll
     for (int u = 0; u < G; ++u) {
-      d[u] = __ldg(ops + min(i + u, end - 1));
+      d[u] = ops.ld16(min(i + u, end - 1));
       len = max(len, d[u].z);    // padded length (multiple of four); shorter lists stop early
     }
     VecT<R> acc[G];
@@ -335,7 +380,7 @@ __device__ __forceinline__ void seg_fold(const int4* __restrict__ ops, const int
 #pragma unroll
       for (int u = 0; u < G; ++u) {
         if (G > 1 && e >= d[u].z) continue;
-        const int4 c = __ldg(reinterpret_cast<const int4*>(edges + d[u].y + e));
+        const int4 c = edges.ld16(d[u].y + e);
         const VecT<R> v0 = ldv<R>(vl, c.x), v1 = ldv<R>(vl, c.y), v2 = ldv<R>(vl, c.z), v3 = ldv<R>(vl, c.w);
         if (ADD) {
           acc[u] = vadd_rn<R>(vadd_rn<R>(vadd_rn<R>(vadd_rn<R>(acc[u], v0), v1), v2), v3);
@@ -349,39 +394,39 @@ __device__ __forceinline__ void seg_fold(const int4* __restrict__ ops, const int
   }
 }
 
-template <int R, bool LOG>
-__device__ __forceinline__ void run_level(const int4* __restrict__ segs, int sbeg, int send,
-                                          const int4* __restrict__ ops, const int32_t* __restrict__ edges, uint32_t fl,
-                                          int F, uint32_t vl, int warp, int nwarps) {
+template <int R, bool LOG, bool SS>
+__device__ __forceinline__ void run_level(const Tab<SS, int4> segs, int sbeg, int send, const Tab<SS, int4> ops,
+                                          const Tab<SS, int32_t> edges, uint32_t fl, int F, uint32_t vl, int warp,
+                                          int nwarps) {
   constexpr int G = 4 / R;
   for (int s = sbeg; s < send; ++s) {
-    const int4 sg = __ldg(segs + s);
+    const int4 sg = segs.ld16(s);
     const int beg = sg.y, end = sg.z;
     switch (sg.x) {
       case OP_LEAF_POS:
       case OP_LEAF_NEG:
         for (int i = beg + warp; i < end; i += nwarps) {
-          const int4 d = __ldg(ops + i);
+          const int4 d = ops.ld16(i);
           stv<R>(vl, d.x, leaf_value<R, LOG>(fl, F, d.y, sg.x == OP_LEAF_NEG));
         }
         break;
       case OP_MUL2:
-        if (LOG) seg_binary<R, G, true>(ops, beg, end, vl, warp, nwarps);
-        else seg_binary<R, G, false>(ops, beg, end, vl, warp, nwarps);
+        if (LOG) seg_binary<R, G, true, SS>(ops, beg, end, vl, warp, nwarps);
+        else seg_binary<R, G, false, SS>(ops, beg, end, vl, warp, nwarps);
         break;
       case OP_PRODN:
-        if (LOG) seg_fold<R, G, true>(ops, edges, beg, end, vl, warp, nwarps);
-        else seg_fold<R, G, false>(ops, edges, beg, end, vl, warp, nwarps);
+        if (LOG) seg_fold<R, G, true, SS>(ops, edges, beg, end, vl, warp, nwarps);
+        else seg_fold<R, G, false, SS>(ops, edges, beg, end, vl, warp, nwarps);
         break;
       default:
         if (!LOG && sg.x == OP_ADD2) {
-          seg_binary<R, G, true>(ops, beg, end, vl, warp, nwarps);
+          seg_binary<R, G, true, SS>(ops, beg, end, vl, warp, nwarps);
         } else if (!LOG && sg.x == OP_SUMN) {
-          seg_fold<R, G, true>(ops, edges, beg, end, vl, warp, nwarps);
+          seg_fold<R, G, true, SS>(ops, edges, beg, end, vl, warp, nwarps);
         } else {
           for (int i = beg + warp; i < end; i += nwarps) {
-            const int4 d = __ldg(ops + i);
-            stv<R>(vl, d.x, exec_op<R, LOG>(d, fl, F, vl, edges));
+            const int4 d = ops.ld16(i);
+            stv<R>(vl, d.x, exec_op<R, LOG, SS>(d, fl, F, vl, edges));
           }
         }
         break;
@@ -400,7 +445,7 @@ __device__ __forceinline__ void init_const_rows(float* val, int n_rows, int T) {
 // ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
-template <int R, bool LOG>
+template <int R, bool LOG, bool SS>
 __global__ void __launch_bounds__(512) generic_forward_kernel(const GenArgs A) {
   constexpr int T = 32 * R;
   const GenProgram& P = A.G;
@@ -423,7 +468,21 @@ __global__ void __launch_bounds__(512) generic_forward_kernel(const GenArgs A) {
     fence_mbar_init();
   }
   init_const_rows(val, P.n_nodes, T);
+  // a small schedule is copied into shared memory once per CTA: every op / child-list / segment fetch is then a
+  // shared-memory broadcast instead of an L1 round trip in the middle of a dependent chain
+  int4* s_ops = reinterpret_cast<int4*>(out + T * P.cq);
+  int4* s_segs = s_ops + P.n_ops;
+  int32_t* s_edges = reinterpret_cast<int32_t*>(s_segs + P.n_segs);
+  int32_t* s_woff = s_edges + P.n_edges;
+  if (SS) {
+    for (int i = threadIdx.x; i < P.n_ops; i += blockDim.x) s_ops[i] = __ldg(P.ops + i);
+    for (int i = threadIdx.x; i < P.n_segs; i += blockDim.x) s_segs[i] = __ldg(P.segs + i);
+    for (int i = threadIdx.x; i < P.n_edges; i += blockDim.x) s_edges[i] = __ldg(P.edges + i);
+    for (int i = threadIdx.x; i < ((W + 3) & ~3); i += blockDim.x) s_woff[i] = __ldg(P.world_off + i);
+  }
   __syncthreads();
+  const Tab<SS, int4> ops(P.ops, s_ops), segs(P.segs, s_segs);
+  const Tab<SS, int32_t> edges(P.edges, s_edges), world_off(P.world_off, s_woff);
 
   // forward schedule: every node when Z is asked for, else without the cone only the normaliser needs
   const int sch = norm ? 0 : 1;
@@ -449,7 +508,7 @@ __global__ void __launch_bounds__(512) generic_forward_kernel(const GenArgs A) {
     }
     if (f_async) { mbar_wait(bar, ph); ph ^= 1; } else __syncthreads();
     for (int L = 0; L < n_lev; ++L) {
-      run_level<R, LOG>(P.segs, lptr[L], lptr[L + 1], P.ops, P.edges, fl, F, vl, warp, nwarps);
+      run_level<R, LOG, SS>(segs, lptr[L], lptr[L + 1], ops, edges, fl, F, vl, warp, nwarps);
       if (L == n_lev - 1) bulk_wait_read<0>();   // the previous tile's stores have finished reading the staging tile
       __syncthreads();
       if (L == leaf_lev - 1) {  // the facts tile is consumed: fetch the next one behind the remaining levels
@@ -489,7 +548,7 @@ __global__ void __launch_bounds__(512) generic_forward_kernel(const GenArgs A) {
         if ((cc & 3) == 0) {
           for (int g = warp; g < (cc >> 2); g += nwarps) {
             const int w = c0 + 4 * g;
-            const int4 off = __ldg(reinterpret_cast<const int4*>(P.world_off + w));
+            const int4 off = world_off.ld16(w);
             const VecT<R> a0 = ldv<R>(vl, off.x), a1 = ldv<R>(vl, off.y), a2 = ldv<R>(vl, off.z), a3 = ldv<R>(vl, off.w);
 #pragma unroll
             for (int j = 0; j < R; ++j) {
@@ -510,7 +569,7 @@ __global__ void __launch_bounds__(512) generic_forward_kernel(const GenArgs A) {
         } else {
           for (int c = warp; c < cc; c += nwarps) {
             const int w = c0 + c;
-            const VecT<R> a = ldv<R>(vl, __ldg(P.world_off + w));
+            const VecT<R> a = ldv<R>(vl, world_off.ld4(w));
 #pragma unroll
             for (int j = 0; j < R; ++j) {
               float o = a.v[j];
@@ -560,10 +619,10 @@ __global__ void __launch_bounds__(512) generic_forward_kernel(const GenArgs A) {
 // ---------------------------------------------------------------------------
 // backward: forward values of the nodes the adjoint needs, then the reverse sweep
 // ---------------------------------------------------------------------------
-template <int R, bool LOG>
-__device__ __forceinline__ VecT<R> apply_rec(VecT<R> a, const int2* __restrict__ prec, int i, uint32_t vl,
-                                             uint32_t al, const int32_t* __restrict__ bedges) {
-  const int2 rec = __ldg(prec + i);
+template <int R, bool LOG, bool SS>
+__device__ __forceinline__ VecT<R> apply_rec(VecT<R> a, const Tab<SS, int2> prec, int i, uint32_t vl, uint32_t al,
+                                             const Tab<SS, int32_t> bedges) {
+  const int2 rec = prec.ld8(i);
   const int kind = rec.x & 7;
   const VecT<R> ap = ldv<R>(al, rec.x >> 1 & ~3);
   switch (kind) {
@@ -579,19 +638,19 @@ __device__ __forceinline__ VecT<R> apply_rec(VecT<R> a, const int2* __restrict__
     }
     case PR_MUL_SIB: return vfma<R>(ap, ldv<R>(vl, rec.y), a);
     case PR_MUL_SIBS: {  // product of the other children of an n-ary product
-      const int2 ext = __ldg(prec + i + 1);
+      const int2 ext = prec.ld8(i + 1);
       const int nc = ext.y & 0xffff, pos = ext.y >> 16;
       VecT<R> sib = vfill<R>(1.0f);
       for (int e = 0; e < nc; ++e)
         if (e != pos) {
-          const VecT<R> v = ldv<R>(vl, __ldg(bedges + ext.x + e));
+          const VecT<R> v = ldv<R>(vl, bedges.ld4(ext.x + e));
 #pragma unroll
           for (int j = 0; j < R; ++j) sib.v[j] *= v.v[j];
         }
       return vfma<R>(ap, sib, a);
     }
     default: {  // PR_LSE: softmax weight of the child inside a logsumexp parent
-      const int2 ext = __ldg(prec + i + 1);
+      const int2 ext = prec.ld8(i + 1);
       const VecT<R> vc = ldv<R>(vl, rec.y), vp = ldv<R>(vl, ext.x);
 #pragma unroll
       for (int j = 0; j < R; ++j) a.v[j] = fmaf(ap.v[j], (vp.v[j] == -INFINITY) ? 0.0f : expf(vc.v[j] - vp.v[j]), a.v[j]);
@@ -600,7 +659,7 @@ __device__ __forceinline__ VecT<R> apply_rec(VecT<R> a, const int2* __restrict__
   }
 }
 
-template <int R, bool LOG>
+template <int R, bool LOG, bool SS>
 __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) {
   constexpr int T = 32 * R;
   const GenProgram& P = A.G;
@@ -627,7 +686,27 @@ __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) 
     fence_mbar_init();
   }
   init_const_rows(val, P.n_bvals, T);
+  // a small schedule is staged in shared memory once per CTA (see the forward kernel)
+  int4* s_bops = reinterpret_cast<int4*>(gws + T * min(P.cb, max(W, 1)));
+  int4* s_bsegs = s_bops + P.n_bops;
+  int4* s_crec = s_bsegs + P.n_bsegs;
+  int4* s_csegs = s_crec + P.n_crec;
+  int32_t* s_bedges = reinterpret_cast<int32_t*>(s_csegs + P.n_csegs);   // 16-byte aligned: read 128 bits at a time
+  int32_t* s_wseed = s_bedges + P.n_bedges;                               // n_bedges is a multiple of four
+  int2* s_prec = reinterpret_cast<int2*>(s_wseed + ((W + 3) & ~3));
+  if (SS) {
+    for (int i = threadIdx.x; i < P.n_bops; i += blockDim.x) s_bops[i] = __ldg(P.bops + i);
+    for (int i = threadIdx.x; i < P.n_bsegs; i += blockDim.x) s_bsegs[i] = __ldg(P.bsegs + i);
+    for (int i = threadIdx.x; i < P.n_crec; i += blockDim.x) s_crec[i] = __ldg(P.crec + i);
+    for (int i = threadIdx.x; i < P.n_csegs; i += blockDim.x) s_csegs[i] = __ldg(P.csegs + i);
+    for (int i = threadIdx.x; i < P.n_prec; i += blockDim.x) s_prec[i] = __ldg(P.prec + i);
+    for (int i = threadIdx.x; i < P.n_bedges; i += blockDim.x) s_bedges[i] = __ldg(P.bedges + i);
+    for (int i = threadIdx.x; i < ((W + 3) & ~3); i += blockDim.x) s_wseed[i] = __ldg(P.wseed_off + i);
+  }
   __syncthreads();
+  const Tab<SS, int4> bops(P.bops, s_bops), bsegs(P.bsegs, s_bsegs), crec(P.crec, s_crec), csegs(P.csegs, s_csegs);
+  const Tab<SS, int2> prec(P.prec, s_prec);
+  const Tab<SS, int32_t> bedges(P.bedges, s_bedges), wseed_off(P.wseed_off, s_wseed);
 
   long long tile = blockIdx.x;
   bool f_async = false, g_async = false;
@@ -657,7 +736,7 @@ __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) 
 
     for (int L = 0; L < P.n_levels; ++L) {
       if (P.bseg_level_ptr[L + 1] > P.bseg_level_ptr[L]) {
-        run_level<R, LOG>(P.bsegs, P.bseg_level_ptr[L], P.bseg_level_ptr[L + 1], P.bops, P.bedges, fl, F, vl, warp, nwarps);
+        run_level<R, LOG, SS>(bsegs, P.bseg_level_ptr[L], P.bseg_level_ptr[L + 1], bops, bedges, fl, F, vl, warp, nwarps);
         __syncthreads();
       }
       if (!LOG && L == P.leaf_levels_b - 1 && nt < n_tiles)
@@ -686,7 +765,7 @@ __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) 
     }
     // ---- world adjoints from the upstream gradient: row-major staging -> node-major (assignment) ----
     if (!have_gw) {
-      for (int w = warp; w < W; w += nwarps) stv<R>(al, __ldg(P.wseed_off + w), vfill<R>(0.0f));
+      for (int w = warp; w < W; w += nwarps) stv<R>(al, wseed_off.ld4(w), vfill<R>(0.0f));
       __syncthreads();
     } else {
       for (int c0 = 0; c0 < W; c0 += P.cb) {
@@ -695,7 +774,7 @@ __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) 
         if ((cc & 3) == 0) {
           for (int g = warp; g < (cc >> 2); g += nwarps) {
             const int w = c0 + 4 * g;
-            const int4 off = __ldg(reinterpret_cast<const int4*>(P.wseed_off + w));
+            const int4 off = wseed_off.ld16(w);
             VecT<R> a0, a1, a2, a3;
 #pragma unroll
             for (int j = 0; j < R; ++j) {
@@ -713,7 +792,7 @@ __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) 
               const float gv = gws[(lane + 32 * j) * cc + c];
               a.v[j] = norm ? gv / zv.v[j] : gv;
             }
-            stv<R>(al, __ldg(P.wseed_off + c0 + c), a);
+            stv<R>(al, wseed_off.ld4(c0 + c), a);
           }
         }
         __syncthreads();   // chunk consumed: the staging tile is free, the seeds are visible
@@ -745,7 +824,7 @@ __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) 
     constexpr int G = 4 / R;
     for (int L = P.n_levels - 2; L >= 0; --L) {
       for (int sgi = P.cseg_level_ptr[L]; sgi < P.cseg_level_ptr[L + 1]; ++sgi) {
-        const int4 sg = __ldg(P.csegs + sgi);
+        const int4 sg = csegs.ld16(sgi);
         const int beg = sg.y, end = sg.z, n = sg.w, uk = sg.x >> CR_UNIFORM_SHIFT;
         const bool seeded = sg.x & CR_SEEDED;
         if (!(sg.x & CR_WIDE) && (uk == 1 + PR_MUL_SIB || uk == 1 + PR_ADD)) {
@@ -754,14 +833,14 @@ __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) 
             VecT<R> a[G];
 #pragma unroll
             for (int u = 0; u < G; ++u) {
-              cr[u] = __ldg(P.crec + min(i + u, end - 1));
+              cr[u] = crec.ld16(min(i + u, end - 1));
               a[u] = seeded ? ldv<R>(al, cr[u].x) : vfill<R>(0.0f);
             }
             if (uk == 1 + PR_MUL_SIB) {
               for (int r = 0; r < n; ++r) {
                 int2 rec[G];
 #pragma unroll
-                for (int u = 0; u < G; ++u) rec[u] = __ldg(P.prec + cr[u].y + r);
+                for (int u = 0; u < G; ++u) rec[u] = prec.ld8(cr[u].y + r);
 #pragma unroll
                 for (int u = 0; u < G; ++u) a[u] = vfma<R>(ldv<R>(al, rec[u].x >> 1 & ~3), ldv<R>(vl, rec[u].y), a[u]);
               }
@@ -769,7 +848,7 @@ __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) 
               for (int r = 0; r < n; ++r) {
 #pragma unroll
                 for (int u = 0; u < G; ++u) {
-                  const VecT<R> ap = ldv<R>(al, __ldg(&P.prec[cr[u].y + r].x) >> 1 & ~3);
+                  const VecT<R> ap = ldv<R>(al, prec.ld8(cr[u].y + r).x >> 1 & ~3);
 #pragma unroll
                   for (int j = 0; j < R; ++j) a[u].v[j] += ap.v[j];
                 }
@@ -780,11 +859,11 @@ __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) 
           }
         } else {
           for (int i = beg + warp; i < end; i += nwarps) {
-            const int4 cr = __ldg(P.crec + i);
+            const int4 cr = crec.ld16(i);
             VecT<R> a = seeded ? ldv<R>(al, cr.x) : vfill<R>(0.0f);
             for (int r = 0, k = cr.y; r < cr.z; ++r) {
-              const int kind = __ldg(&P.prec[k].x) & 7;
-              a = apply_rec<R, LOG>(a, P.prec, k, vl, al, P.bedges);
+              const int kind = prec.ld8(k).x & 7;
+              a = apply_rec<R, LOG, SS>(a, prec, k, vl, al, bedges);
               k += (kind == PR_MUL_SIBS || kind == PR_LSE) ? 2 : 1;
             }
             stv<R>(al, cr.x, a);
@@ -987,6 +1066,17 @@ GenProgram* gen_program_create(const vael_circuit_desc_t* d, cudaError_t* err) {
     }
     g->seg_level_ptr[sch][d->n_levels] = (int)segs.size();
   }
+  g->n_ops = (int)ops.size(); g->n_edges = (int)((edges.size() + 3) / 4 * 4); g->n_segs = (int)segs.size();
+  edges.resize(g->n_edges, 0);
+  {
+    const size_t sched = (size_t)16 * (g->n_ops + g->n_segs) + (size_t)4 * (g->n_edges + (d->n_worlds + 3) / 4 * 4);
+    static const int sched_limit = [] { const char* v = getenv("VAEL_GEN_SCHED_SMEM"); return (v && *v) ? atoi(v) : 12288; }();
+    // staged behind the output staging tile (which is cq columns wide)
+    if (sched <= (size_t)sched_limit && g->fwd_smem + sched <= kSmemLimit && g->cf == std::max(d->n_worlds, 1)) {
+      g->sched_in_smem = 1;
+      g->fwd_smem += sched;
+    }
+  }
   std::vector<int32_t> world_off((d->n_worlds + 3) / 4 * 4, 0), query_off(d->n_queries);
   for (int w = 0; w < d->n_worlds; ++w) world_off[w] = d->world_node[w] * PBF;
   for (int q = 0; q < d->n_queries; ++q) query_off[q] = d->query_node[q] * PBF;
@@ -1127,6 +1217,20 @@ GenProgram* gen_program_create(const vael_circuit_desc_t* d, cudaError_t* err) {
   }
 
 
+  g->n_bops = (int)bops.size(); g->n_bsegs = (int)bsegs.size(); g->n_crec = (int)crec.size(); g->n_csegs = (int)csegs.size();
+  g->n_prec = (int)prec.size();
+  bedges.resize((bedges.size() + 3) / 4 * 4, 0);
+  g->n_bedges = (int)bedges.size();
+  {
+    const size_t sched = (size_t)16 * (g->n_bops + g->n_bsegs + g->n_crec + g->n_csegs) + (size_t)8 * g->n_prec +
+                         (size_t)4 * (g->n_bedges + (d->n_worlds + 3) / 4 * 4);
+    static const int sched_limit = [] { const char* v = getenv("VAEL_GEN_SCHED_SMEM"); return (v && *v) ? atoi(v) : 12288; }();
+    if (sched <= (size_t)sched_limit && g->bwd_smem + sched <= kSmemLimit && g->cb == std::max(d->n_worlds, 1)) {
+      g->bsched_in_smem = 1;
+      g->bwd_smem += sched;
+    }
+  }
+
   cudaError_t e = cudaSuccess;
   e = up(&g->ops, ops, e); e = up(&g->edges, edges, e); e = up(&g->segs, segs, e); e = up(&g->bsegs, bsegs, e);
   e = up(&g->csegs, csegs, e); e = up(&g->world_off, world_off, e);
@@ -1170,27 +1274,31 @@ static cudaError_t launch_generic(K kern, const GenProgram* g, const GenCall& C,
   return cudaGetLastError();
 }
 
-template <bool LOG>
+template <bool LOG, bool SS>
 static cudaError_t gen_forward_r(const GenProgram* g, const GenCall& C, int num_sms, cudaStream_t st) {
   switch (g->rf) {
-    case 4: return launch_generic(generic_forward_kernel<4, LOG>, g, C, g->fwd_smem, 4, num_sms, st);
-    case 2: return launch_generic(generic_forward_kernel<2, LOG>, g, C, g->fwd_smem, 2, num_sms, st);
-    default: return launch_generic(generic_forward_kernel<1, LOG>, g, C, g->fwd_smem, 1, num_sms, st);
+    case 4: return launch_generic(generic_forward_kernel<4, LOG, SS>, g, C, g->fwd_smem, 4, num_sms, st);
+    case 2: return launch_generic(generic_forward_kernel<2, LOG, SS>, g, C, g->fwd_smem, 2, num_sms, st);
+    default: return launch_generic(generic_forward_kernel<1, LOG, SS>, g, C, g->fwd_smem, 1, num_sms, st);
   }
 }
-template <bool LOG>
+template <bool LOG, bool SS>
 static cudaError_t gen_backward_r(const GenProgram* g, const GenCall& C, int num_sms, cudaStream_t st) {
   switch (g->rb) {
-    case 4: return launch_generic(generic_backward_kernel<4, LOG>, g, C, g->bwd_smem, 4, num_sms, st);
-    case 2: return launch_generic(generic_backward_kernel<2, LOG>, g, C, g->bwd_smem, 2, num_sms, st);
-    default: return launch_generic(generic_backward_kernel<1, LOG>, g, C, g->bwd_smem, 1, num_sms, st);
+    case 4: return launch_generic(generic_backward_kernel<4, LOG, SS>, g, C, g->bwd_smem, 4, num_sms, st);
+    case 2: return launch_generic(generic_backward_kernel<2, LOG, SS>, g, C, g->bwd_smem, 2, num_sms, st);
+    default: return launch_generic(generic_backward_kernel<1, LOG, SS>, g, C, g->bwd_smem, 1, num_sms, st);
   }
 }
 cudaError_t gen_forward(const GenProgram* g, const GenCall& C, int num_sms, cudaStream_t st) {
-  return g->semiring == VAEL_SEMIRING_LOG ? gen_forward_r<true>(g, C, num_sms, st) : gen_forward_r<false>(g, C, num_sms, st);
+  const bool lg = g->semiring == VAEL_SEMIRING_LOG;
+  if (g->sched_in_smem) return lg ? gen_forward_r<true, true>(g, C, num_sms, st) : gen_forward_r<false, true>(g, C, num_sms, st);
+  return lg ? gen_forward_r<true, false>(g, C, num_sms, st) : gen_forward_r<false, false>(g, C, num_sms, st);
 }
 cudaError_t gen_backward(const GenProgram* g, const GenCall& C, int num_sms, cudaStream_t st) {
-  return g->semiring == VAEL_SEMIRING_LOG ? gen_backward_r<true>(g, C, num_sms, st) : gen_backward_r<false>(g, C, num_sms, st);
+  const bool lg = g->semiring == VAEL_SEMIRING_LOG;
+  if (g->bsched_in_smem) return lg ? gen_backward_r<true, true>(g, C, num_sms, st) : gen_backward_r<false, true>(g, C, num_sms, st);
+  return lg ? gen_backward_r<true, false>(g, C, num_sms, st) : gen_backward_r<false, false>(g, C, num_sms, st);
 }
 
 }  // namespace vael
