@@ -72,9 +72,10 @@ def host_threads():
     return n
 
 
-def cpu_reference_rate(rows, steps, warmup):
-    """evals/s of the reference's dense logic path (forward + autograd backward) on the host
-    cores, torch CPU with all its threads, on `rows` rows per step."""
+def cpu_reference_rate(rows, steps, warmup, chunks=1):
+    """evals/s of the reference's dense logic path (forward + autograd backward) on the host cores, torch CPU
+    with all its threads.  One step = `chunks` batches of `rows` rows (the batch is what bounds host memory:
+    worlds + upstream gradient are 800 B per row), so a step can cover the GPU arm's rows per step."""
     from oracle import dense_path
     facts, g = synthetic_facts(rows, "cpu", 1234)
     facts = facts.reshape(rows, 2, 10)
@@ -84,9 +85,10 @@ def cpu_reference_rate(rows, steps, warmup):
     q = int(torch.randint(0, 19, (1,), generator=g))
 
     def step():
-        f = facts.clone().requires_grad_(True)
-        qp, worlds = dense_path.dense_inference(f, w_q, q)   # one query per batch: the reference's own mode
-        torch.autograd.backward([worlds, qp], [gw, gq])
+        for _ in range(chunks):
+            f = facts.clone().requires_grad_(True)
+            qp, worlds = dense_path.dense_inference(f, w_q, q)   # one query per batch: the reference's own mode
+            torch.autograd.backward([worlds, qp], [gw, gq])
         return f.grad
 
     for _ in range(warmup):
@@ -97,7 +99,7 @@ def cpu_reference_rate(rows, steps, warmup):
         step()
         times.append(time.perf_counter() - t0)
     dt = sum(times) / len(times)
-    return rows * EVALS_PER_ROW / dt, dt
+    return rows * chunks * EVALS_PER_ROW / dt, dt
 
 
 def cpu_extras():
@@ -166,15 +168,17 @@ def run_reference(args):
         return
     steps, warmup = max(1, args.steps), max(1, args.warmup)
     host_threads()
-    rate, dt = cpu_reference_rate(args.cpu_rows, steps, warmup)
+    chunks = max(1, args.rows // args.cpu_rows)   # one step covers the GPU arm's rows per step (8 Mi by default)
+    rate, dt = cpu_reference_rate(args.cpu_rows, steps, warmup, chunks)
     cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": "circuit_evals_per_sec", "value": rate, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rows_per_step": args.cpu_rows, "evals_per_row": EVALS_PER_ROW},
+        "config": {"workload": WORKLOAD, "rows_per_step": args.cpu_rows * chunks, "evals_per_row": EVALS_PER_ROW},
         "cpu_baseline": {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.cpu_rows} rows/step x {steps} steps, torch CPU fp32 port of "
+                         "sample": f"{chunks} batches x {args.cpu_rows} rows per step x {steps} steps "
+                                   f"({dt:.2f} s/step), torch CPU fp32 port of "
                                    f"models/vael.py:208-225 + autograd, os.cpu_count()={os.cpu_count()}"},
         "e2e": {"value": rate, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -384,9 +388,11 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         host_threads()
-        rate, dt = cpu_reference_rate(args.cpu_rows, 8, 2)
+        cpu_chunks = max(1, args.rows // args.cpu_rows)      # one CPU step = this arm's rows per step
+        rate, dt = cpu_reference_rate(args.cpu_rows, 6, 1, cpu_chunks)
         cpu = {"value": rate, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{args.cpu_rows} rows/step x 8 steps ({dt * 1e3:.0f} ms/step), torch CPU fp32 port of "
+               "sample": f"{cpu_chunks} batches x {args.cpu_rows} rows per step x 6 steps ({dt:.2f} s/step, "
+                         f"{7 * dt:.0f} s of CPU work), torch CPU fp32 port of "
                          f"models/vael.py:208-225 + autograd, os.cpu_count()={os.cpu_count()}"}
         try:
             cpu["also"] = cpu_extras()
@@ -456,6 +462,27 @@ def secondary_probe(args, dev, rank, world, barrier, max_over_ranks, lib):
     peak_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = float(json.load(open(peak_path))["hbm_gbs"]) if os.path.exists(peak_path) else 6650.0
     out = {}
+
+    # -- configs[3]: the 2-digit circuit at batch 1e5 .. 1e7 (the headline runs 8.4e6).  At 1e5 rows the whole
+    # working set (105 MB) sits in the 126 MB L2: that point is an L2-bandwidth number and is labelled so.
+    sweep = {}
+    dc2s = DeviceCircuit(compile_addition_family(2, 10).circuit, dev)
+    for Bs in (100_000, 1_000_000, 10_000_000):
+        fs, gs = synthetic_facts(Bs, dev, parallel.rank_seed(77, rank))
+        qs = torch.randint(0, 19, (Bs,), device=dev, dtype=torch.int32, generator=gs)
+        ws = torch.empty(Bs, 100, device=dev); qo = torch.empty(Bs, device=dev); gfs = torch.empty(Bs, 20, device=dev)
+        gws = torch.randn(Bs, 100, device=dev, generator=gs); gqs = torch.randn(Bs, device=dev, generator=gs)
+        f_ms, b_ms = _time_pair(
+            lambda: _lib.check(lib.vael_circuit_forward(dc2s.handle, _p(fs), _p(qs), -1, Bs, _p(ws), _p(qo), 0, sp)),
+            lambda: _lib.check(lib.vael_circuit_backward(dc2s.handle, _p(fs), _p(qs), -1, Bs, _p(gws), _p(gqs), _p(gfs), 0, sp)),
+            10, barrier, max_over_ranks)
+        sweep[f"B{Bs}"] = {"fwd_ms": f_ms, "bwd_ms": b_ms, "fwd_GBs": Bs * FWD_BYTES / f_ms / 1e6,
+                           "bwd_GBs": Bs * BWD_BYTES / b_ms / 1e6,
+                           "evals_per_sec": world * Bs * EVALS_PER_ROW / ((f_ms + b_ms) * 1e-3),
+                           "memory": "L2-resident working set" if Bs * (FWD_BYTES + BWD_BYTES) < 120e6 else "HBM"}
+        del fs, ws, gws
+        torch.cuda.empty_cache()
+    out["batch_sweep_2digit"] = sweep
 
     # -- 3-digit addition: F=30, W=1000, Q=28 -> fwd 4128 B/row, bwd 4248 B/row, 1001 evals/row
     B = args.wide_rows
