@@ -82,7 +82,7 @@ def test_reference_arm_prints_one_line_from_rank_zero_only():
     port = free_port()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
-           "--steps", "1", "--warmup", "1", "--cpu-rows", "2048"]
+           "--steps", "1", "--warmup", "1", "--cpu-rows", "2048", "--rows", "8192"]
     env = dict(os.environ, OMP_NUM_THREADS="2")
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
