@@ -12,10 +12,11 @@
 // conflict-free LDS/STS of 32 consecutive vectors whatever the circuit shape, and one decoded op does R
 // rows' worth of arithmetic per lane — the interpreter's decode cost is amortised over 32 R rows.  The
 // circuit is turned ONCE, at vael_circuit_create, into a schedule: one 16-byte op per node with the
-// children already converted to shared-memory byte offsets, ops sorted by kind inside each level.  Warps
-// take the ops of a level in groups of four; a group of four binary products / sums (the bulk of a
-// compiled program) runs as eight independent shared-memory loads, 4 R FP ops, four stores — no per-node
-// branching — and the warps meet at one barrier per level.
+// children already converted to shared-memory byte offsets, ops sorted by kind inside each level and every
+// run of one kind described as a segment.  The kind is decoded once per segment; the segment's ops are swept
+// by a tight loop specialised for that kind, G = 4 / R ops per warp at a time (binary products / sums: 2 G
+// independent shared-memory loads, G R FP ops, G stores), and the warps meet at one barrier per level.  A
+// small schedule is staged in shared memory once per CTA and read through side-effect-free ld.shared (Tab).
 //
 // Batch-major global tensors never meet the node-major layout in global memory: a [T, K] tile of a
 // row-major [B, K] tensor is one contiguous span, moved by ONE bulk copy (cp.async.bulk, SASS UBLKCP)
