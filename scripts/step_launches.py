@@ -1,4 +1,5 @@
-"""One eager VAEL train step at batch B (default 32) after warm-up: the launch list for ncu."""
+"""One eager VAEL train step at batch B (default 32) after warm-up: the launch list for ncu
+(`ncu --profile-from-start off --metrics gpu__time_duration.sum ... python scripts/step_launches.py 4096 cl`)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -24,8 +25,10 @@ labels = torch.cat([d, d.sum(1, keepdim=True), -torch.ones(B, 1, dtype=torch.lon
 for _ in range(4):
     train_step(model, opt, x, labels)
 torch.cuda.synchronize()
-torch.cuda.nvtx.range_push("step")
+# cudaProfilerStart/Stop bracket ONE step (run ncu with --profile-from-start off): unlike an NVTX range on the main
+# thread, this also catches the backward kernels, which the autograd engine launches from its own thread
+torch.cuda.profiler.start()
 train_step(model, opt, x, labels)
 torch.cuda.synchronize()
-torch.cuda.nvtx.range_pop()
+torch.cuda.profiler.stop()
 print("done")
