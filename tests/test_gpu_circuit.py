@@ -119,6 +119,30 @@ def test_queries_all(dc, addition_family, B, normalize):
         np.testing.assert_allclose(out.cpu().numpy(), w @ circ.worlds_queries_matrix().astype(np.float64), rtol=1e-5)
 
 
+@pytest.mark.parametrize("B", [1, 97, 4001])
+def test_queries_all_overlapping_members_mario(cuda_device, B):
+    """Mario's five queries (four moves + `constraint`, which is the union of the moves: worlds belong to TWO
+    queries, and the member lists have ragged lengths) through the all-queries kernel (ad2<9,9>) and the generic
+    kernel: both bit-exact against the CSR-order fp32 oracle, with and without the normaliser."""
+    from vael_b200 import _lib
+    from vael_b200.mario_task import compile_mario_family
+    from vael_b200.ops import DeviceCircuit, circuit_queries_all
+    circ = compile_mario_family((3, 3)).circuit
+    dcm = DeviceCircuit(circ, cuda_device)
+    rng = np.random.default_rng(B)
+    p = rng.dirichlet(np.ones(9), size=(B, 2)).astype(np.float32).clip(1e-5, 0.9999).reshape(B, 18)
+    f = torch.from_numpy(p).cuda()
+    for normalize in (False, True):
+        ref = fp_interp.queries_all(circ, p, normalize=normalize)
+        out = circuit_queries_all(dcm, f, normalize=normalize)
+        assert _lib.last_kernel() == "ad2-queries"
+        np.testing.assert_array_equal(out.cpu().numpy(), ref)
+        out_g = circuit_queries_all(dcm, f, normalize=normalize, force_generic=True)
+        assert _lib.last_kernel() == "generic-csr"
+        np.testing.assert_array_equal(out_g.cpu().numpy(), ref)
+    assert ref.shape == (B, 5)
+
+
 def test_empty_batch_and_errors(dc):
     from vael_b200._lib import VaelError
     from vael_b200.ops import circuit_forward
