@@ -141,6 +141,26 @@ def test_queries_all_overlapping_members_mario(cuda_device, B):
         assert _lib.last_kernel() == "generic-csr"
         np.testing.assert_array_equal(out_g.cpu().numpy(), ref)
     assert ref.shape == (B, 5)
+    # worlds [B,81] / per-row query / adjoint: W and F are not multiples of four (scalar staging paths of the generic
+    # kernel, 324-byte rows in the structured one); structured and generic kernels must agree bit for bit forward
+    from vael_b200.ops import circuit_forward
+    qi = torch.from_numpy(rng.integers(0, 5, size=B)).cuda()
+    gw = torch.from_numpy(rng.standard_normal((B, 81)).astype(np.float32)).cuda()
+    res = []
+    for generic in (False, True):
+        fg = f.clone().requires_grad_(True)
+        w, q = circuit_forward(dcm, fg, qi, force_generic=generic)
+        assert _lib.last_kernel() == ("generic-csr" if generic else "ad2-tma")
+        ((w * gw).sum() + 3.0 * q.sum()).backward()
+        res.append((w.detach().cpu().numpy(), q.detach().cpu().numpy(), fg.grad.cpu().numpy()))
+    w_ref, q_ref = fp_interp.forward(circ, p, query=qi.cpu().numpy())
+    np.testing.assert_array_equal(res[0][0], w_ref)
+    np.testing.assert_array_equal(res[1][0], w_ref)
+    np.testing.assert_array_equal(res[0][1][:, 0], q_ref)
+    np.testing.assert_array_equal(res[1][1][:, 0], q_ref)
+    g_ref = fp_interp.backward(circ, p, gw.cpu().numpy(), 3.0 * np.ones(B), qi.cpu().numpy())
+    for r in res:
+        assert rel_err(r[2], g_ref, floor=1e-3 * np.abs(g_ref).max()) < 1e-4
 
 
 def test_empty_batch_and_errors(dc):
