@@ -305,6 +305,17 @@ extern "C" int vael_circuit_create(const vael_circuit_desc_t* d, vael_circuit_t*
     if (qm_idx.empty()) qm_idx.assign(4, d->n_worlds * 128);
     up(&c->d_qm_ptr, qm_ptr); up(&c->d_qm_idx, qm_idx);
     c->qm_len = (int32_t)qm_idx.size();
+    // addition-shaped queries over a two-AD outer product: query s = { (j, k) : j + k = s }
+    c->queries_diagonal = false;
+    if (c->fast_kind == 2 && d->n_queries == c->ad_na + c->ad_nb - 1) {
+      bool diag = true;
+      for (int q = 0; q < d->n_queries && diag; ++q)
+        for (int w = 0; w < d->n_worlds && diag; ++w) {
+          const bool in = (qmask[(size_t)q * c->mask_words + (w >> 5)] >> (w & 31)) & 1u;
+          diag = in == ((w / c->ad_nb) + (w % c->ad_nb) == q);
+        }
+      c->queries_diagonal = diag;
+    }
   }
   if (!qmask_c.empty()) up(&c->d_qmask_c, qmask_c);
   if (e == cudaSuccess) c->gen = gen_program_create(d, &e);
@@ -396,6 +407,7 @@ extern "C" int vael_circuit_queries_all(const vael_circuit_t* c, const float* fa
   if (pick_kernel(c, flags, nullptr) == 2 && c->n_queries <= 64) {
     Ad2QParams P{};
     P.facts = facts; P.B = B; P.n_queries = c->n_queries; P.qm_ptr = c->d_qm_ptr; P.qm_idx = c->d_qm_idx; P.qm_len = c->qm_len;
+    P.diagonal = c->queries_diagonal ? 1 : 0;
     P.queries_all = queries_all;
     CK(ad2_queries_all(c->ad_na, c->ad_nb, P, flags & VAEL_FLAG_NORMALIZE, c->num_sms, static_cast<cudaStream_t>(stream)));
     g_last_kernel = "ad2-queries";

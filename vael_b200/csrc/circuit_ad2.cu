@@ -522,6 +522,61 @@ __global__ void __launch_bounds__(256) ad2_queries_kernel(const Ad2QParams P) {
   }
 }
 
+// Addition-shaped queries (the MNIST-addition task itself: query s holds exactly the worlds (j, k) with j + k = s,
+// recognised at vael_circuit_create): the member lists are the anti-diagonals of the NA x NB outer product, so the
+// whole contraction unrolls at compile time over register operands — 100 FMUL + 100 FADD per row, no shared-memory
+// world tile, no table fetches.  Each sum runs over j ascending = world order = CSR child order (bit-exact).  The
+// [32, Q] result tile goes through a shared-memory tile so that the global store is coalesced.
+template <int NA, int NB, bool NORM>
+__global__ void __launch_bounds__(256) ad2_queries_diag_kernel(const Ad2QParams P) {
+  using Sh = Ad2Shape<NA, NB>;
+  constexpr int F = Sh::F, FV = Sh::FV, Q = NA + NB - 1;
+  constexpr int PER_WARP = Sh::FACT_BYTES + ((kWarp * Q * 4 + 127) / 128) * 128;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* fs = reinterpret_cast<float*>(smem + (size_t)warp * PER_WARP);                      // [32][F]
+  float* qs = reinterpret_cast<float*>(smem + (size_t)warp * PER_WARP + Sh::FACT_BYTES);     // [32][Q]
+  const long long n_sub = (P.B + kWarp - 1) / kWarp;
+  const long long gw = (long long)blockIdx.x * nwarps + warp;
+  const long long GW = (long long)gridDim.x * nwarps;
+  float nx[F];
+  auto fetch = [&](long long sub) {
+    const long long r0 = sub * kWarp;
+    const int n = (sub < n_sub) ? (int)min((long long)kWarp, P.B - r0) * F : 0;
+    const float* src = P.facts + r0 * F;
+#pragma unroll
+    for (int k = 0; k < F; ++k) nx[k] = (k * kWarp + lane < n) ? __ldg(src + k * kWarp + lane) : 0.5f;
+  };
+  fetch(gw);
+  for (long long sub = gw; sub < n_sub; sub += GW) {
+    const long long row0 = sub * kWarp;
+    const int rows = (int)min((long long)kWarp, P.B - row0);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < F; ++k) fs[k * kWarp + lane] = nx[k];
+    __syncwarp();
+    fetch(sub + GW);
+    float p[F];
+#pragma unroll
+    for (int c = 0; c < F / FV; ++c) lds_vec<FV>(p + c * FV, fs + lane * F + c * FV);
+    float z = 1.0f;
+    if constexpr (NORM) z = ad2_normaliser<NA, NB>(p);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int j = 0; j < NA; ++j) {
+        const int k = q - j;
+        if (k >= 0 && k < NB) acc = __fadd_rn(acc, __fmul_rn(p[j], p[NA + (k >= 0 && k < NB ? k : 0)]));
+      }
+      qs[lane * Q + q] = NORM ? acc / z : acc;
+    }
+    __syncwarp();
+    float* dst = P.queries_all + row0 * Q;
+    for (int i = lane; i < rows * Q; i += kWarp) dst[i] = qs[i];
+  }
+}
+
 // ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
@@ -599,6 +654,18 @@ static cudaError_t launch_fwd_shape(const Ad2Params& P, bool norm, bool evid, in
 
 template <int NA, int NB>
 static cudaError_t launch_queries(const Ad2QParams& P, bool norm, int num_sms, cudaStream_t st) {
+  if (P.diagonal && P.n_queries == NA + NB - 1) {
+    using Sh = Ad2Shape<NA, NB>;
+    const int per_warp = Sh::FACT_BYTES + ((kWarp * (NA + NB - 1) * 4 + 127) / 128) * 128;
+    const int nw = 8;
+    auto kern = norm ? ad2_queries_diag_kernel<NA, NB, true> : ad2_queries_diag_kernel<NA, NB, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, nw * per_warp);
+    if (e != cudaSuccess) return e;
+    const long long n_sub = (P.B + kWarp - 1) / kWarp;
+    const long long grid = min((n_sub + nw - 1) / nw, (long long)num_sms * 4);
+    kern<<<(unsigned)grid, nw * 32, nw * per_warp, st>>>(P);
+    return cudaGetLastError();
+  }
   const int per_warp = queries_per_warp_bytes<NA, NB>(P.n_queries);
   int nw = 8;
   while (nw > 1 && nw * per_warp > 110 * 1024) --nw;  // two CTAs per SM

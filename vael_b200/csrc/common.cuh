@@ -121,6 +121,7 @@ struct vael_circuit {
   int32_t* d_qm_ptr;         // [n_queries+1] member worlds of every query node (CSR, world order) — set with d_qmask
   int32_t* d_qm_idx;
   int32_t qm_len;
+  bool queries_diagonal;     // fast_kind 2: query s = the worlds (j, k) with j + k = s (all-queries register kernel)
   uint32_t* d_qmask_c;       // fast_kind 3: [n_queries][np][ceil(na*nb/32)] chunked membership masks
   // host-buffer pipeline (allocated lazily by the *_host entry points)
   vael_host_slot slot[kHostSlots];

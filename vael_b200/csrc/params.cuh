@@ -28,6 +28,7 @@ struct Ad2QParams {           // all query nodes at once
   const int32_t* qm_ptr;      // [Q+1] CSR of the member worlds of every query node, in world order; lists padded to x4
   const int32_t* qm_idx;      // byte offsets (world * 128) into the kernel's world-major tile; padding -> the zero row
   int32_t qm_len;             // length of qm_idx
+  int32_t diagonal;           // query s holds exactly the worlds (j, k) with j + k = s (addition-shaped)
   float* queries_all;         // [B,Q]
 };
 cudaError_t ad2_queries_all(int na, int nb, const Ad2QParams& P, bool norm, int num_sms, cudaStream_t st);
