@@ -502,6 +502,14 @@ def secondary_probe(args, dev, rank, world, barrier, max_over_ranks, lib):
         "rows_per_gpu": B, "kernel_family": _lib.last_kernel(), "evals_per_sec": world * B * 1001 / ((f_ms + b_ms) * 1e-3),
         "fwd": {"ms": f_ms, "bytes_per_row": 4128, "GBs": B * 4128 / f_ms / 1e6, "frac": B * 4128 / f_ms / 1e6 / peak},
         "bwd": {"ms": b_ms, "bytes_per_row": 4248, "GBs": B * 4248 / b_ms / 1e6, "frac": B * 4248 / b_ms / 1e6 / peak}}
+    qa3 = torch.empty(B, 28, device=dev)
+    a3_ms, _ = _time_pair(lambda: _lib.check(lib.vael_circuit_queries_all(dc3.handle, _p(facts), B, _p(qa3), 0, sp)),
+                          lambda: None, 10, barrier, max_over_ranks)
+    out["all_queries_3digit"] = {"workload": "all 28 sums per row of the 3-digit circuit (worlds not materialised)",
+                                 "rows_per_gpu": B, "kernel_family": _lib.last_kernel(), "ms": a3_ms,
+                                 "bytes_per_row": 120 + 112, "GBs": B * 232 / a3_ms / 1e6,
+                                 "rows_per_sec": world * B / (a3_ms * 1e-3)}
+    del qa3
     Bg = B // 4   # the same circuit through the generic CSR kernels (1163 nodes: R = 1 tiles, chunked staging)
     f_ms, b_ms = _time_pair(
         lambda: _lib.check(lib.vael_circuit_forward(dc3.handle, _p(facts), _p(qidx), -1, Bg, _p(worlds), _p(query), 4, sp)),

@@ -144,3 +144,27 @@ def test_wide_full_size_properties(dc3, fam3):
                         (f3[:, 0].sum(1) * f3[:, 2].sum(1))[:, None].expand(B, 10),
                         (f3[:, 0].sum(1) * f3[:, 1].sum(1))[:, None].expand(B, 10)], 1)
     assert torch.allclose(gs, expect, rtol=1e-5)
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+@pytest.mark.parametrize("B", [1, 45, 1000])
+def test_wide_queries_all(dc3, fam3, B, normalize):
+    """All 28 sums of the 3-digit circuit per row (the `worlds @ w_q` loop of metrics.py:71-75 scaled to three
+    digits) from the register-resident kernel and from the generic CSR kernel: both bit-exact against the
+    CSR-order fp32 oracle; worlds are never materialised."""
+    from oracle import fp_interp
+    from tests.util import synthetic_facts
+    from vael_b200 import _lib
+    from vael_b200.ops import circuit_queries_all
+    circ = fam3.circuit
+    facts = synthetic_facts(B, groups=(10, 10, 10), seed=11 + B)
+    ref = fp_interp.queries_all(circ, facts, normalize=normalize)
+    f = torch.from_numpy(facts).cuda()
+    out = circuit_queries_all(dc3, f, normalize=normalize)
+    assert _lib.last_kernel() == "adw-queries"
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    out_g = circuit_queries_all(dc3, f, normalize=normalize, force_generic=True)
+    assert _lib.last_kernel() == "generic-csr"
+    np.testing.assert_array_equal(out_g.cpu().numpy(), ref)
+    if not normalize:
+        assert np.allclose(ref.sum(1), 1.0, atol=2e-5)   # every world belongs to exactly one sum

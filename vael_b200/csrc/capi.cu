@@ -307,6 +307,16 @@ extern "C" int vael_circuit_create(const vael_circuit_desc_t* d, vael_circuit_t*
     c->qm_len = (int32_t)qm_idx.size();
     // addition-shaped queries over a two-AD outer product: query s = { (j, k) : j + k = s }
     c->queries_diagonal = false;
+    if (c->fast_kind == 3 && d->n_queries == c->ad_np + c->ad_na + c->ad_nb - 2) {
+      bool diag = true;
+      for (int q = 0; q < d->n_queries && diag; ++q)
+        for (int w = 0; w < d->n_worlds && diag; ++w) {
+          const bool in = (qmask[(size_t)q * c->mask_words + (w >> 5)] >> (w & 31)) & 1u;
+          const int i = w / (c->ad_na * c->ad_nb), j = (w / c->ad_nb) % c->ad_na, k = w % c->ad_nb;
+          diag = in == (i + j + k == q);
+        }
+      c->queries_diagonal = diag;
+    }
     if (c->fast_kind == 2 && d->n_queries == c->ad_na + c->ad_nb - 1) {
       bool diag = true;
       for (int q = 0; q < d->n_queries && diag; ++q)
@@ -411,6 +421,13 @@ extern "C" int vael_circuit_queries_all(const vael_circuit_t* c, const float* fa
     P.queries_all = queries_all;
     CK(ad2_queries_all(c->ad_na, c->ad_nb, P, flags & VAEL_FLAG_NORMALIZE, c->num_sms, static_cast<cudaStream_t>(stream)));
     g_last_kernel = "ad2-queries";
+    g_launches++;
+    return VAEL_OK;
+  }
+  if (pick_kernel(c, flags, nullptr) == 3 && c->queries_diagonal) {
+    CK(adw_queries_diag(c->ad_np, c->ad_na, c->ad_nb, facts, B, queries_all, flags & VAEL_FLAG_NORMALIZE, c->num_sms,
+                        static_cast<cudaStream_t>(stream)));
+    g_last_kernel = "adw-queries";
     g_launches++;
     return VAEL_OK;
   }

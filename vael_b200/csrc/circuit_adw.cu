@@ -591,6 +591,86 @@ static cudaError_t launch_bwd(const AdwParams& P, int num_sms, cudaStream_t st) 
   return launch_bwd_cfg<NP, NA, NB, NORM, 3>(P, num_sms, st);
 }
 
+// ---------------------------------------------------------------------------
+// all query nodes at once for addition-shaped queries over three annotated disjunctions (3-digit addition:
+// query s holds exactly the worlds (i, j, k) with i + j + k = s; recognised at vael_circuit_create).  Same idea as
+// ad2_queries_diag_kernel: the whole contraction unrolls at compile time over register operands — world
+// (i, j, k) = (p1[i] * p2[j]) * p3[k], the left-deep product the CSR holds, each sum over (i, j) ascending = world
+// order = CSR child order (bit-exact); nothing but facts[B,30] in and queries[B,28] out touches memory.
+// ---------------------------------------------------------------------------
+template <int NP, int NA, int NB, bool NORM>
+__global__ void __launch_bounds__(256) adw_queries_diag_kernel(const float* __restrict__ facts, long long B,
+                                                               float* __restrict__ queries_all) {
+  constexpr int F = NP + NA + NB, Q = NP + NA + NB - 2;
+  constexpr int PER_WARP = ((kWarp * F * 4 + 127) / 128) * 128 + ((kWarp * Q * 4 + 127) / 128) * 128;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* fs = reinterpret_cast<float*>(smem + (size_t)warp * PER_WARP);                                        // [32][F]
+  float* qs = reinterpret_cast<float*>(smem + (size_t)warp * PER_WARP + ((kWarp * F * 4 + 127) / 128) * 128);   // [32][Q]
+  const long long n_sub = (B + kWarp - 1) / kWarp;
+  const long long gw = (long long)blockIdx.x * nwarps + warp;
+  const long long GW = (long long)gridDim.x * nwarps;
+  float nx[F];
+  auto fetch = [&](long long sub) {
+    const long long r0 = sub * kWarp;
+    const int n = (sub < n_sub) ? (int)min((long long)kWarp, B - r0) * F : 0;
+    const float* src = facts + r0 * F;
+#pragma unroll
+    for (int k = 0; k < F; ++k) nx[k] = (k * kWarp + lane < n) ? __ldg(src + k * kWarp + lane) : 0.5f;
+  };
+  fetch(gw);
+  for (long long sub = gw; sub < n_sub; sub += GW) {
+    const long long row0 = sub * kWarp;
+    const int rows = (int)min((long long)kWarp, B - row0);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < F; ++k) fs[k * kWarp + lane] = nx[k];
+    __syncwarp();
+    fetch(sub + GW);
+    float p[F];
+#pragma unroll
+    for (int c = 0; c < F; c += 2) {   // F * 4 bytes per row: 8-byte aligned rows
+      const float2 t = *reinterpret_cast<const float2*>(fs + lane * F + c);
+      p[c] = t.x; p[c + 1] = t.y;
+    }
+    float z = 1.0f;
+    if constexpr (NORM) z = adw_normaliser<NP, NA, NB>(p, p + NP, p + NP + NA);
+    float ab[NP * NA];   // the pair products the left-deep world products share
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+#pragma unroll
+      for (int j = 0; j < NA; ++j) ab[i * NA + j] = __fmul_rn(p[i], p[NP + j]);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int i = 0; i < NP; ++i)
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+          const int k = q - i - j;
+          if (k >= 0 && k < NB) acc = __fadd_rn(acc, __fmul_rn(ab[i * NA + j], p[NP + NA + (k >= 0 && k < NB ? k : 0)]));
+        }
+      qs[lane * Q + q] = NORM ? acc / z : acc;
+    }
+    __syncwarp();
+    float* dst = queries_all + row0 * Q;
+    for (int i = lane; i < rows * Q; i += kWarp) dst[i] = qs[i];
+  }
+}
+
+cudaError_t adw_queries_diag(int np, int na, int nb, const float* facts, long long B, float* queries_all, bool norm,
+                             int num_sms, cudaStream_t st) {
+  if (!(np == 10 && na == 10 && nb == 10)) return cudaErrorInvalidValue;
+  constexpr int F = 30, Q = 28;
+  constexpr int PER_WARP = ((kWarp * F * 4 + 127) / 128) * 128 + ((kWarp * Q * 4 + 127) / 128) * 128;
+  const int nw = 4;
+  auto kern = norm ? adw_queries_diag_kernel<10, 10, 10, true> : adw_queries_diag_kernel<10, 10, 10, false>;
+  const long long n_sub = (B + kWarp - 1) / kWarp;
+  const long long grid = min((n_sub + nw - 1) / nw, (long long)num_sms * 4);
+  kern<<<(unsigned)grid, nw * 32, nw * PER_WARP, st>>>(facts, B, queries_all);
+  return cudaGetLastError();
+}
+
 bool adw_supported(int np, int na, int nb) { return np == 10 && na == 10 && nb == 10; }
 
 // can this call go through the tensor-map path?  (16-byte aligned [B,W] base, driver entry point present)

@@ -57,6 +57,9 @@ bool adw_supported(int np, int na, int nb);
 bool adw_usable(const float* wide_tensor);
 cudaError_t adw_forward(int np, int na, int nb, const AdwParams& P, bool norm, bool evid, int num_sms, cudaStream_t st);
 cudaError_t adw_backward(int np, int na, int nb, const AdwParams& P, bool norm, int num_sms, cudaStream_t st);
+// all query nodes at once, addition-shaped queries (query s = worlds (i, j, k) with i + j + k = s)
+cudaError_t adw_queries_diag(int np, int na, int nb, const float* facts, long long B, float* queries_all, bool norm,
+                             int num_sms, cudaStream_t st);
 
 // ---- circuit_generic.cu ----------------------------------------------------
 constexpr int kMaxLevels = 24;
