@@ -108,7 +108,9 @@ VAEL_API const char* vael_last_kernel(void);
 VAEL_API int vael_circuit_create(const vael_circuit_desc_t* desc, vael_circuit_t** out);
 VAEL_API void vael_circuit_destroy(vael_circuit_t* c);
 /* 0 = generic CSR only; 2 / 3 = structured path for worlds that are the outer product of two / three
- * annotated disjunctions (1-D bulk-copy tiles / 2-D tensor-map tiles) */
+ * annotated disjunctions (1-D bulk-copy tiles / 2-D tensor-map tiles); 4 = literal table in the log
+ * semiring (every world one literal per fact column: MarioVAELModel.admissible_worlds_logprob,
+ * models/vael.py:368-375) */
 VAEL_API int vael_circuit_fast_kind(const vael_circuit_t* c);
 /* 64-bit FNV-1a hash of the uploaded arrays (bit-exact circuit identity) */
 VAEL_API uint64_t vael_circuit_hash(const vael_circuit_t* c);

@@ -241,3 +241,40 @@ def test_full_size_properties_and_host_path(dc, addition_family):
     hw2 = torch.empty(n, 100)          # pageable host memory works too
     _lib.check(dc.lib.vael_circuit_forward_host(dc.handle, _p(hf), None, 9, n, _p(hw2), None, 0))
     assert torch.equal(hw2, hw)
+
+
+@pytest.mark.parametrize("B", [1, 77, 3000])
+def test_admissible_worlds_literal_table_kernel(cuda_device, B):
+    """Mario's admissible-world log-probabilities (models/vael.py:368-375) through the literal-table kernel
+    (fast_kind 4): bit for bit the generic CSR kernel, within 1e-5 of the reference's two-matmul form, adjoint
+    against fp64 autograd of that form; a table the kernel does not cover stays on the generic kernel."""
+    from vael_b200 import _lib
+    from vael_b200.compiler import circuit_from_world_table
+    from vael_b200.mario_task import admissible_circuit, compile_mario_family, mario_tables
+    from vael_b200.ops import DeviceCircuit, circuit_forward
+    W_adm = mario_tables(compile_mario_family((3, 3)))[2]
+    dca = DeviceCircuit(admissible_circuit(W_adm), cuda_device)
+    assert dca.fast_kind == 4
+    rng = np.random.default_rng(B)
+    p = rng.dirichlet(np.ones(9), size=(B, 2)).astype(np.float32).clip(1e-5, 0.9999).reshape(B, 18)
+    ga = rng.standard_normal((B, 24)).astype(np.float32)
+    outs = []
+    for generic in (False, True):
+        f = torch.from_numpy(p).cuda().requires_grad_(True)
+        lw, _ = circuit_forward(dca, f, None, force_generic=generic)
+        assert _lib.last_kernel() == ("generic-csr" if generic else "lt-log")
+        (lw * torch.from_numpy(ga).cuda()).sum().backward()
+        assert _lib.last_kernel() == ("generic-csr" if generic else "lt-log")
+        outs.append((lw.detach().cpu().numpy(), f.grad.cpu().numpy()))
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    p64 = torch.from_numpy(p.astype(np.float64)).requires_grad_(True)
+    Wt = torch.from_numpy(W_adm.astype(np.float64))
+    ref = torch.log(p64) @ Wt.T + torch.log(1 - p64) @ (1 - Wt).T          # models/vael.py:371-374
+    (ref * torch.from_numpy(ga).double()).sum().backward()
+    assert rel_err(outs[0][0], ref.detach().numpy()) < 1e-5
+    g_ref = p64.grad.numpy()
+    for o in outs:
+        assert rel_err(o[1], g_ref, floor=1e-3 * np.abs(g_ref).max()) < 1e-4
+    # 19 fact columns: not a shape the kernel is built for
+    odd = DeviceCircuit(circuit_from_world_table(rng.integers(0, 2, size=(5, 19))), cuda_device)
+    assert odd.fast_kind == 0

@@ -288,6 +288,35 @@ extern "C" int vael_circuit_create(const vael_circuit_desc_t* d, vael_circuit_t*
     if (c->fast_kind) c->norm_fast_ok = c->norm_node >= 0 && norm_is_adk(d, c->norm_node, K, sizes, offs);
   }
 
+  // literal table in the log semiring (circuit_lt.cu): no queries, no normaliser, every world a product over all F
+  // fact columns — the positive literals in column order, then the negative ones (compiler.py:circuit_from_world_table)
+  if (c->fast_kind == 0 && d->semiring == VAEL_SEMIRING_LOG && d->n_queries == 0 && c->norm_node < 0 &&
+      lt_supported(d->n_facts, d->n_worlds)) {
+    bool ok = true;
+    const uint32_t all = d->n_facts >= 32 ? 0xffffffffu : ((1u << d->n_facts) - 1u);
+    for (int w = 0; w < d->n_worlds && ok; ++w) {
+      const int n = d->world_node[w];
+      ok = d->node_kind[n] == VAEL_NODE_PROD && d->child_ptr[n + 1] - d->child_ptr[n] == d->n_facts;
+      uint32_t pos = 0, neg = 0;
+      int prev_pos = -1, prev_neg = -1;
+      for (int e = d->child_ptr[n]; e < d->child_ptr[n + 1] && ok; ++e) {
+        const int ch = d->child_idx[e], f = d->node_arg[ch];
+        if (d->node_kind[ch] == VAEL_NODE_LEAF_POS) {
+          ok = neg == 0 && f > prev_pos;
+          prev_pos = f; pos |= 1u << f;
+        } else if (d->node_kind[ch] == VAEL_NODE_LEAF_NEG) {
+          ok = f > prev_neg;
+          prev_neg = f; neg |= 1u << f;
+        } else {
+          ok = false;
+        }
+      }
+      ok = ok && (pos & neg) == 0 && (pos | neg) == all;
+      c->lt_mask[w] = pos;
+    }
+    if (ok) c->fast_kind = 4;
+  }
+
   cudaError_t e = cudaSuccess;
   auto up = [&](auto** dp, const auto& v) { if (e == cudaSuccess) e = upload(dp, v); };
   if (masks_ok) {
@@ -373,6 +402,7 @@ static int check_common(const vael_circuit_t* c, const float* facts, const int32
 // of the call, whose base address the tensor map needs 16-byte aligned
 static int pick_kernel(const vael_circuit_t* c, uint32_t flags, const float* wide) {
   if (c->fast_kind == 0 || (flags & VAEL_FLAG_FORCE_GENERIC)) return 0;
+  if (c->fast_kind == 4) return (flags & VAEL_FLAG_EVIDENCE) ? 0 : 4;   // no normaliser node: NORMALIZE is a no-op
   if ((flags & VAEL_FLAG_NORMALIZE) && !c->norm_fast_ok) return 0;
   if (c->fast_kind == 3 && !adw_usable(wide)) return 0;
   return c->fast_kind;
@@ -397,6 +427,9 @@ extern "C" int vael_circuit_forward(const vael_circuit_t* c, const float* facts,
     P.qmask_c = c->d_qmask_c; P.B = B; P.worlds = worlds; P.query = query;
     CK(adw_forward(c->ad_np, c->ad_na, c->ad_nb, P, flags & VAEL_FLAG_NORMALIZE, flags & VAEL_FLAG_EVIDENCE, c->num_sms, st));
     g_last_kernel = "adw-tma2d";
+  } else if (kern == 4 && worlds != nullptr && query == nullptr) {
+    CK(lt_forward(c->n_facts, c->n_worlds, c->lt_mask, facts, B, worlds, c->num_sms, st));
+    g_last_kernel = "lt-log";
   } else {
     GenCall G = make_call(c, facts, qidx, needq ? qs : -1, B, flags);
     G.worlds = worlds; G.query = query;
@@ -462,6 +495,9 @@ extern "C" int vael_circuit_backward(const vael_circuit_t* c, const float* facts
     P.qmask_c = c->d_qmask_c; P.B = B; P.grad_worlds = grad_worlds; P.grad_query = grad_query; P.grad_facts = grad_facts;
     CK(adw_backward(c->ad_np, c->ad_na, c->ad_nb, P, flags & VAEL_FLAG_NORMALIZE, c->num_sms, st));
     g_last_kernel = "adw-tma2d";
+  } else if (kern == 4) {   // no query nodes: grad_query has nothing to seed
+    CK(lt_backward(c->n_facts, c->n_worlds, c->lt_mask, facts, grad_worlds, B, grad_facts, c->num_sms, st));
+    g_last_kernel = "lt-log";
   } else {
     GenCall G = make_call(c, facts, qidx, needq ? qs : -1, B, flags);
     G.grad_worlds = grad_worlds; G.grad_query = grad_query; G.grad_facts = grad_facts;

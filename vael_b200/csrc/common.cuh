@@ -115,12 +115,14 @@ struct vael_circuit {
   uint32_t* d_qmask;         // [n_queries][mask_words] world membership of each query (SUM over world nodes), or null
   int32_t mask_words;
   // structured fast path
-  int fast_kind;             // 0 none, 2 / 3 = worlds are the outer product of two / three annotated disjunctions
+  int fast_kind;             // 0 none, 2 / 3 = worlds are the outer product of two / three annotated disjunctions,
+                             // 4 = literal table in the log semiring (every world: one literal per fact column)
   int32_t ad_np, ad_na, ad_nb;  // AD sizes (np = leading AD, only for fast_kind 3); fact columns in that order
   bool norm_fast_ok;         // the normaliser node has the per-AD shape the fast paths recompute
   int32_t* d_qm_ptr;         // [n_queries+1] member worlds of every query node (CSR, world order) — set with d_qmask
   int32_t* d_qm_idx;
   int32_t qm_len;
+  uint32_t lt_mask[64];      // fast_kind 4: per world, the fact columns that enter as positive literals
   bool queries_diagonal;     // fast_kind 2: query s = the worlds (j, k) with j + k = s (all-queries register kernel)
   uint32_t* d_qmask_c;       // fast_kind 3: [n_queries][np][ceil(na*nb/32)] chunked membership masks
   // host-buffer pipeline (allocated lazily by the *_host entry points)

@@ -61,6 +61,13 @@ cudaError_t adw_backward(int np, int na, int nb, const AdwParams& P, bool norm, 
 cudaError_t adw_queries_diag(int np, int na, int nb, const float* facts, long long B, float* queries_all, bool norm,
                              int num_sms, cudaStream_t st);
 
+// ---- circuit_lt.cu (literal-table circuits in the log semiring: Mario's admissible worlds) ----
+bool lt_supported(int F, int W);
+cudaError_t lt_forward(int F, int W, const uint32_t* masks, const float* facts, long long B, float* worlds, int num_sms,
+                       cudaStream_t st);
+cudaError_t lt_backward(int F, int W, const uint32_t* masks, const float* facts, const float* grad_worlds, long long B,
+                        float* grad_facts, int num_sms, cudaStream_t st);
+
 // ---- circuit_generic.cu ----------------------------------------------------
 constexpr int kMaxLevels = 24;
 struct GenProgram;  // device-resident schedule of a circuit (ops per level, parent records), built once
