@@ -542,7 +542,7 @@ def secondary_probe(args, dev, rank, world, barrier, max_over_ranks, lib):
 
     # -- Mario circuits (configs[2]): worlds / move query over 2 x 9 position facts (prob semiring, ad2<9,9>) and
     # the 24 admissible worlds' log-probabilities (log semiring: products of 18 positive / negative literals,
-    # the generic CSR kernel's production user)
+    # the literal-table kernel)
     try:
         from vael_b200.mario_task import admissible_circuit, compile_mario_family, mario_tables
         Bm = 1 << 21
