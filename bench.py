@@ -679,8 +679,22 @@ def mario_probe(dev, B=32, n=30):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    return {"value": B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "elbo": float(elbo.item()), "mode": "eager",
-            "config": "Mario VAEL, synthetic 2x(100x100x3) frames, random-init weights, Adam"}
+    eager = {"value": B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "elbo": float(elbo.item()), "mode": "eager"}
+    # the same step captured once in a CUDA graph (B = 32 is launch-bound)
+    from vael_b200.train import GraphedTrainStep
+    opt_g = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)
+    stepper = GraphedTrainStep(model, opt_g, tuple(x.shape), tuple(moves.shape), device=dev, step_fn=mario_train_step)
+    for _ in range(3):
+        stepper(x, moves)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        elbo = stepper(x, moves)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return {"value": B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "elbo": float(elbo.item()), "mode": "cuda-graph",
+            "eager": eager, "config": "Mario VAEL, synthetic 2x(100x100x3) frames, random-init weights, Adam"}
 
 
 if __name__ == "__main__":

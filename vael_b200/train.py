@@ -111,11 +111,14 @@ class GraphedTrainStep:
     instead of a host-drawn seed, which a graph would freeze).
 
     Usage: step = GraphedTrainStep(model, optimizer, batch_shape); terms = step(data, labels)
-    The optimizer must be capturable (torch.optim.Adam(..., capturable=True)).
+    The optimizer must be capturable (torch.optim.Adam(..., capturable=True)).  `step_fn` is the eager step
+    to capture: `train_step` (MNIST, returns the [4] term vector) or `mario_train_step` (Mario: `labels` are the
+    one-hot moves [B,4]; returns the elbo).
     """
 
     def __init__(self, model, optimizer, data_shape, labels_shape=None, device=None, warmup=3,
-                 memory_format=torch.contiguous_format, **loss_kw):
+                 memory_format=torch.contiguous_format, step_fn=None, **loss_kw):
+        step_fn = step_fn or train_step
         device = torch.device(device) if device is not None else next(model.parameters()).device
         if device.type != "cuda":
             raise RuntimeError("vael_b200: CUDA graphs need a CUDA device")
@@ -124,16 +127,30 @@ class GraphedTrainStep:
         self.data = torch.zeros(data_shape, device=device).contiguous(memory_format=memory_format)
         self.labels = torch.zeros(labels_shape or (B, 4), dtype=torch.long, device=device)
         model.graph_safe_rng = True
+        # The model keeps its last forward's tensors as attributes (facts_probs, worlds_prob, query_prob, ... — the
+        # reference's side-effect attributes).  After eager steps they keep that autograd graph, and with it the
+        # parameters' AccumulateGrad nodes created on the default stream, alive — and a backward captured on another
+        # stream would then touch the legacy stream (cudaErrorStreamCaptureImplicit).  Detach them first.
+        def _detached(v):
+            if torch.is_tensor(v):
+                return v.detach() if v.grad_fn is not None else v
+            if isinstance(v, (tuple, list)):
+                return type(v)(_detached(u) for u in v)
+            return v
+
+        for name, value in list(vars(model).items()):
+            if torch.is_tensor(value) or isinstance(value, (tuple, list)):
+                object.__setattr__(model, name, _detached(value))
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
             for _ in range(warmup):   # allocator warm-up, lazy circuit upload, cuDNN plan selection
-                train_step(model, optimizer, self.data, self.labels, **loss_kw)
+                step_fn(model, optimizer, self.data, self.labels, **loss_kw)
         torch.cuda.current_stream(device).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         optimizer.zero_grad(set_to_none=True)
         with torch.cuda.graph(self.graph):
-            self.terms = train_step(model, optimizer, self.data, self.labels, **loss_kw)
+            self.terms = step_fn(model, optimizer, self.data, self.labels, **loss_kw)
 
     def __call__(self, data, labels):
         """Copies the batch into the static buffers and replays the step; returns the [4] term vector
