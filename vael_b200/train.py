@@ -149,7 +149,7 @@ class GraphedTrainStep:
         torch.cuda.current_stream(device).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         optimizer.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):   # the stream the warm-up ran on: AccumulateGrad nodes match
             self.terms = step_fn(model, optimizer, self.data, self.labels, **loss_kw)
 
     def __call__(self, data, labels):
