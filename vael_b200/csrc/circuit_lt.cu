@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(256) lt_forward_kernel(const float* __restrict
       lp[f] = logf(p[f]);
       ln[f] = logf(__fsub_rn(1.0f, p[f]));
     }
+#pragma unroll 2   // two worlds = two independent FADD chains in flight per lane
     for (int w = 0; w < W; ++w) {
       const uint32_t m = M.m[w];
       float acc = 0.0f;   // 0 + x is exact: the fold starts at its first literal
