@@ -597,7 +597,7 @@ def train_probe(args, dev, rank, world, distributed, barrier, max_over_ranks):
     on the vael_b200 kernels, Adam; the whole step is one CUDA graph at N = 1, DDP/NCCL eager at N > 1."""
     from vael_b200.mnist_task import build_model_dict, build_worlds_queries_matrix
     from vael_b200.networks import MNISTPairsDecoder, MNISTPairsEncoder, MNISTPairsMLP
-    from vael_b200.train import GraphedTrainStep, train_step
+    from vael_b200.train import GraphedTrainStep, as_channels_last, train_step
     from vael_b200.vael import MNISTPairsVAELModel
     from vael_b200 import parallel
     model_dict = build_model_dict(2, 10, device=dev)
@@ -614,7 +614,7 @@ def train_probe(args, dev, rank, world, distributed, barrier, max_over_ranks):
         model = model.to(memory_format=torch.channels_last)
         opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=graphed, fused=True)
         g = torch.Generator(device=dev).manual_seed(parallel.rank_seed(1234, rank))
-        x = torch.randn(Bt, 1, 28, 56, device=dev, generator=g).contiguous(memory_format=torch.channels_last)
+        x = as_channels_last(torch.randn(Bt, 1, 28, 56, device=dev, generator=g))   # explicit NHWC strides for C = 1
         d = torch.randint(0, 10, (Bt, 2), device=dev, generator=g)
         labels = torch.cat([d, d.sum(1, keepdim=True), -torch.ones(Bt, 1, dtype=torch.long, device=dev)], 1)
         if graphed:

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from vael_b200.mnist_task import build_model_dict, build_worlds_queries_matrix
 from vael_b200.networks import MNISTPairsDecoder, MNISTPairsEncoder, MNISTPairsMLP
-from vael_b200.train import train_step
+from vael_b200.train import as_channels_last, train_step
 from vael_b200.vael import MNISTPairsVAELModel
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 CL = len(sys.argv) > 2 and sys.argv[2] == "cl"
@@ -19,7 +19,7 @@ if CL:
 opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=CL)
 x = torch.randn(B, 1, 28, 56, device=dev)
 if CL:
-    x = x.contiguous(memory_format=torch.channels_last)
+    x = as_channels_last(x)
 d = torch.randint(0, 10, (B, 2), device=dev)
 labels = torch.cat([d, d.sum(1, keepdim=True), -torch.ones(B, 1, dtype=torch.long, device=dev)], 1)
 for _ in range(4):

@@ -5,7 +5,7 @@ import torch
 from torch.profiler import profile, ProfilerActivity
 from vael_b200.mnist_task import build_model_dict, build_worlds_queries_matrix
 from vael_b200.networks import MNISTPairsDecoder, MNISTPairsEncoder, MNISTPairsMLP
-from vael_b200.train import train_step
+from vael_b200.train import as_channels_last, train_step
 from vael_b200.vael import MNISTPairsVAELModel
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 dev = torch.device("cuda", 0)
@@ -15,7 +15,7 @@ model = MNISTPairsVAELModel(MNISTPairsEncoder(hidden_channels=64, latent_dim=23)
                             build_worlds_queries_matrix(2, 10).to(dev), dropout=0.5, is_train=True, device=dev, query_per_row=True).to(dev)
 model = model.to(memory_format=torch.channels_last)
 opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
-x = torch.randn(B, 1, 28, 56, device=dev).contiguous(memory_format=torch.channels_last)
+x = as_channels_last(torch.randn(B, 1, 28, 56, device=dev))
 d = torch.randint(0, 10, (B, 2), device=dev)
 labels = torch.cat([d, d.sum(1, keepdim=True), -torch.ones(B, 1, dtype=torch.long, device=dev)], 1)
 for _ in range(4):
