@@ -251,17 +251,35 @@ __global__ void __launch_bounds__(256) facts_tile_kernel(const float* __restrict
   float* xs = tile_s + (size_t)warp * (BWD ? 2 : 1) * kWarp * PITCH;
   float* gs = xs + kWarp * PITCH;
   const long long n_sub = (B + kWarp - 1) / kWarp;
-  for (long long sub = (long long)blockIdx.x * nwarps + warp; sub < n_sub; sub += (long long)gridDim.x * nwarps) {
+  const long long gw = (long long)blockIdx.x * nwarps + warp, GW = (long long)gridDim.x * nwarps;
+  // the next tile (a contiguous span: coalesced) is requested one iteration ahead into registers, so that a warp
+  // does not sit out a full HBM round trip before every tile
+  float nx[F], ng[BWD ? F : 1];
+  auto fetch = [&](long long sub) {
+    const long long r0 = sub * kWarp;
+    const int n = (sub < n_sub) ? (int)min((long long)kWarp, B - r0) * F : 0;
+#pragma unroll
+    for (int k = 0; k < F; ++k) {
+      const int i = k * kWarp + lane;
+      nx[k] = (i < n) ? __ldg(logits + r0 * F + i) : 0.0f;
+      if (BWD) ng[k] = (i < n) ? __ldg(grad_facts + r0 * F + i) : 0.0f;
+    }
+  };
+  fetch(gw);
+  for (long long sub = gw; sub < n_sub; sub += GW) {
     const long long row0 = sub * kWarp;
     const int rows = (int)min((long long)kWarp, B - row0);
     const int n = rows * F;
     __syncwarp();
-    for (int i = lane; i < kWarp * F; i += kWarp) {   // coalesced: the tile is one contiguous span
+#pragma unroll
+    for (int k = 0; k < F; ++k) {
+      const int i = k * kWarp + lane;
       const int r = i / F, c = i - r * F;               // F is a compile-time constant: mul-shift, no division
-      xs[r * PITCH + c] = (i < n) ? __ldg(logits + row0 * F + i) : 0.0f;
-      if (BWD) gs[r * PITCH + c] = (i < n) ? __ldg(grad_facts + row0 * F + i) : 0.0f;
+      xs[r * PITCH + c] = nx[k];
+      if (BWD) gs[r * PITCH + c] = ng[k];
     }
     __syncwarp();
+    fetch(sub + GW);
     float x[F], y[F], zs[NG];
 #pragma unroll
     for (int c = 0; c < F; ++c) x[c] = xs[lane * PITCH + c];
