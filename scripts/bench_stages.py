@@ -25,4 +25,9 @@ for B in (1 << 20,):
     hb = torch.cat([torch.eye(10).repeat_interleave(10, 0), torch.eye(10).repeat(10, 1)], 1).cuda()
     ms = timeit(lambda: gumbel_world(p, hb, seed=1))
     out[f"gumbel_B{B}"] = dict(ms=ms, GBs=B * (400 + 400 + 4 + 80) / ms / 1e6)
+    pg = p.clone().requires_grad_(True)
+    wh, idx, ys = gumbel_world(pg, hb, seed=1)
+    gwh = torch.randn_like(wh)
+    ms = timeit(lambda: torch.autograd.grad(wh, pg, gwh, retain_graph=True))
+    out[f"gumbel_bwd_B{B}"] = dict(ms=ms, GBs=B * (400 + 80 + 400 + 400) / ms / 1e6)
 print(json.dumps(out))

@@ -135,15 +135,21 @@ __global__ void __launch_bounds__(256) gumbel_backward_kernel(const GumbelParams
     for (int j = 0; j < ITEMS; ++j) {
       const int e = lane + j * kWarp;
       G[j] = 0.0f;
-      ys[j] = 0.0f;
-      if (e < P.W) {
-        float acc = 0.0f;
-        for (int h = 0; h < P.H; ++h) acc = fmaf(__ldg(P.grad_world_h + row * P.H + h), hb[e * P.H + h], acc);
-        G[j] = acc;
-        ys[j] = __ldg(P.y_soft + row * P.W + e);
-        dot = fmaf(ys[j], acc, dot);
+      ys[j] = (e < P.W) ? __ldg(P.y_soft + row * P.W + e) : 0.0f;
+    }
+    // h outer: every upstream gradient component is fetched once per row (a warp-wide broadcast) and feeds the
+    // ITEMS accumulation chains of the lane; each chain still adds in h order
+    for (int h = 0; h < P.H; ++h) {
+      const float gh = __ldg(P.grad_world_h + row * P.H + h);
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) {
+        const int e = min(lane + j * kWarp, P.W - 1);
+        G[j] = fmaf(gh, hb[e * P.H + h], G[j]);
       }
     }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+      if (lane + j * kWarp < P.W) dot = fmaf(ys[j], G[j], dot);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
 #pragma unroll
