@@ -116,10 +116,15 @@ __global__ void __launch_bounds__(256) gumbel_forward_kernel(const GumbelParams 
 
 template <int ITEMS>
 __global__ void __launch_bounds__(256) gumbel_backward_kernel(const GumbelParams P) {
-  extern __shared__ float hb_s[];  // [W][H] Herbrand table (when it fits; else read through L1/L2)
+  extern __shared__ float hb_s[];  // [W][H | 1] Herbrand table (when it fits; else read through L1/L2)
   const float* hb = P.herbrand;
+  int hp = P.H;                    // row pitch of `hb`
   if (P.hb_in_smem) {
-    for (int i = threadIdx.x; i < P.W * P.H; i += blockDim.x) hb_s[i] = __ldg(P.herbrand + i);
+    hp = P.H | 1;                  // odd pitch: lanes (= consecutive worlds) read column h without bank conflicts
+    for (int i = threadIdx.x; i < P.W * P.H; i += blockDim.x) {
+      const int w = i / P.H, h = i - w * P.H;
+      hb_s[w * hp + h] = __ldg(P.herbrand + i);
+    }
     __syncthreads();
     hb = hb_s;
   }
@@ -144,7 +149,7 @@ __global__ void __launch_bounds__(256) gumbel_backward_kernel(const GumbelParams
 #pragma unroll
       for (int j = 0; j < ITEMS; ++j) {
         const int e = min(lane + j * kWarp, P.W - 1);
-        G[j] = fmaf(gh, hb[e * P.H + h], G[j]);
+        G[j] = fmaf(gh, hb[e * hp + h], G[j]);
       }
     }
 #pragma unroll
@@ -195,7 +200,7 @@ cudaError_t gumbel_forward(const GumbelParams& P, int num_sms, cudaStream_t st) 
 
 template <int ITEMS>
 static cudaError_t launch_gumbel_bwd(GumbelParams P, int grid, cudaStream_t st) {
-  size_t smem = (size_t)P.W * P.H * sizeof(float);
+  size_t smem = (size_t)P.W * (P.H | 1) * sizeof(float);
   P.hb_in_smem = smem <= (size_t)200 * 1024;
   if (!P.hb_in_smem) smem = 0;
   if (smem > 48 * 1024) {
