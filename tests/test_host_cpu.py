@@ -377,3 +377,18 @@ def test_learning_curve_files_round_trip(tmp_path):
     save_curves(str(tmp_path), tr, va)
     tr2, va2 = load_curves(str(tmp_path))
     assert list(tr2) == list(CURVE_KEYS) and tr2 == tr and va2 == va and len(tr2["elbo"]) == 3
+
+
+def test_as_channels_last_gives_one_channel_images_explicit_nhwc_strides():
+    """For C = 1 torch keeps NCHW strides under .contiguous(channels_last) and the convolution heuristics then see
+    an NCHW tensor; train.as_channels_last hands out the same bytes with strides (H*W, 1, W, 1)."""
+    from vael_b200.train import as_channels_last
+    x = torch.arange(2 * 1 * 3 * 5, dtype=torch.float32).reshape(2, 1, 3, 5)
+    plain = x.contiguous(memory_format=torch.channels_last)
+    assert plain.stride() == (15, 15, 5, 1)                       # ambiguous: what torch leaves us with
+    y = as_channels_last(x)
+    assert y.stride() == (15, 1, 5, 1) and torch.equal(y, x) and y.data_ptr() == x.data_ptr()
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    assert y.suggest_memory_format() == torch.channels_last if hasattr(y, "suggest_memory_format") else True
+    z = as_channels_last(torch.randn(2, 3, 4, 4))                 # C > 1: the ordinary conversion
+    assert z.stride() == (48, 1, 12, 3)
