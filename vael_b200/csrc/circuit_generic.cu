@@ -456,7 +456,10 @@ __global__ void __launch_bounds__(512) generic_forward_kernel(const GenArgs A) {
   float* val = reinterpret_cast<float*>(gsm_raw + 16);          // [n_nodes + 2][T]
   float* fs = val + (P.n_nodes + 2) * T;                        // [T][F] row-major staging
   float* out = fs + T * P.n_facts;                              // [T][<= cf] row-major staging
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // opaque to the compiler from here on: otherwise it re-derives the three values from S2R / LDC at every use
+  // (about a hundred instructions per warp and tile)
+  asm volatile("" : "+r"(warp), "+r"(lane), "+r"(nwarps));
   const uint32_t vl = smem_u32(val) + lane * (4 * R);
   const uint32_t fl = smem_u32(fs) + lane * (4 * P.n_facts);
   const long long n_tiles = (C.B + T - 1) / T;
@@ -673,7 +676,10 @@ __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) 
   float* fs = adj + (P.n_nodes + 1) * T;                        // [T][F] facts staging
   float* gfs = fs + T * P.n_facts;                              // [T][F] grad_facts staging
   float* gws = gfs + T * P.n_facts;                             // [T][<= cb] grad_worlds staging
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // opaque to the compiler from here on: otherwise it re-derives the three values from S2R / LDC at every use
+  // (about a hundred instructions per warp and tile)
+  asm volatile("" : "+r"(warp), "+r"(lane), "+r"(nwarps));
   const uint32_t vl = smem_u32(val) + lane * (4 * R);
   const uint32_t al = smem_u32(adj) + lane * (4 * R);
   const uint32_t fl = smem_u32(fs) + lane * (4 * P.n_facts);
