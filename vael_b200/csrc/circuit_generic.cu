@@ -52,7 +52,7 @@ struct GenProgram {
   int32_t rf, rb;          // rows per lane of the forward / backward kernel
   int32_t cf, cb;          // staged columns per chunk: worlds (forward) / grad_worlds (backward)
   int32_t cq;              // column capacity of the forward staging tile (>= cf; queries_all chunks)
-  int32_t leaf_levels_f[2], leaf_levels_b;  // levels [0, leaf_levels) hold every leaf op of the schedule
+  int32_t leaf_levels_f[2], leaf_levels_b[2];  // levels [0, leaf_levels) hold every leaf op of the schedule
   int32_t n_levels_f[2];   // levels of the forward schedule up to its last non-empty one
   // forward.  The value tile has n_nodes + 2 rows: the last two hold the constants 0 and 1 the padded
   // child lists point at.
@@ -69,7 +69,7 @@ struct GenProgram {
   int32_t* bedges;
   int4* bsegs;
   int32_t n_bops, n_bedges, n_bsegs, n_crec, n_csegs, n_prec, bsched_in_smem;  // backward schedule sizes
-  int32_t bseg_level_ptr[kMaxLevels + 1];
+  int32_t bseg_level_ptr[2][kMaxLevels + 1];  // [0]: with the normaliser's cone (NORMALIZE calls); [1]: without
   int32_t norm_slot_off;   // byte offset of Z in the slot space, or -1
   int4* crec;              // live children, level by level: {adj off, first record, n records, flags}
   int4* csegs;             // runs of children of the same shape inside a level: {flags, first child, end, n records}
@@ -715,6 +715,10 @@ __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) 
   const Tab<SS, int2> prec(P.prec, s_prec);
   const Tab<SS, int32_t> bedges(P.bedges, s_bedges), wseed_off(P.wseed_off, s_wseed);
 
+  // recomputed values: with the normaliser's cone only when Z is asked for
+  const int32_t* blptr = P.bseg_level_ptr[norm ? 0 : 1];
+  const int leaf_lev_b = P.leaf_levels_b[norm ? 0 : 1];
+
   long long tile = blockIdx.x;
   bool f_async = false, g_async = false;
   uint32_t ph_f = 0, ph_g = 0;
@@ -742,14 +746,14 @@ __global__ void __launch_bounds__(512) generic_backward_kernel(const GenArgs A) 
     if (f_async) { mbar_wait(bar_f, ph_f); ph_f ^= 1; } else __syncthreads();
 
     for (int L = 0; L < P.n_levels; ++L) {
-      if (P.bseg_level_ptr[L + 1] > P.bseg_level_ptr[L]) {
-        run_level<R, LOG, SS>(bsegs, P.bseg_level_ptr[L], P.bseg_level_ptr[L + 1], bops, bedges, fl, F, vl, warp, nwarps);
+      if (blptr[L + 1] > blptr[L]) {
+        run_level<R, LOG, SS>(bsegs, blptr[L], blptr[L + 1], bops, bedges, fl, F, vl, warp, nwarps);
         __syncthreads();
       }
-      if (!LOG && L == P.leaf_levels_b - 1 && nt < n_tiles)
+      if (!LOG && L == leaf_lev_b - 1 && nt < n_tiles)
         f_async = stage_load(fs, C.facts, nt * T, nrows, T, F, 0, F, bar_f, 0.5f);
     }
-    if (!LOG && P.leaf_levels_b == 0 && nt < n_tiles) {
+    if (!LOG && leaf_lev_b == 0 && nt < n_tiles) {
       __syncthreads();   // every thread is past its wait on the facts barrier
       f_async = stage_load(fs, C.facts, nt * T, nrows, T, F, 0, F, bar_f, 0.5f);
     }
@@ -1102,10 +1106,17 @@ GenProgram* gen_program_create(const vael_circuit_desc_t* d, cudaError_t* err) {
       for (int e = d->child_ptr[p]; e < d->child_ptr[p + 1]; ++e) need[d->child_idx[e]] = 1;
     }
   }
+  // two sets: what a call without VAEL_FLAG_NORMALIZE needs, and that plus the normaliser's cone.  Both use the
+  // slot numbering of the larger set (the parent records refer to it).
+  auto close = [&](std::vector<char>& set) {
+    for (int n = N - 1; n >= 0; --n)  // closure: a kept node needs its children
+      if (set[n])
+        for (int e = d->child_ptr[n]; e < d->child_ptr[n + 1]; ++e) set[d->child_idx[e]] = 1;
+  };
+  std::vector<char> need_plain = need;
+  close(need_plain);
   if (g->norm_node >= 0) need[g->norm_node] = 1;
-  for (int n = N - 1; n >= 0; --n)  // closure: a kept node needs its children
-    if (need[n])
-      for (int e = d->child_ptr[n]; e < d->child_ptr[n + 1]; ++e) need[d->child_idx[e]] = 1;
+  close(need);
   std::vector<int32_t> bslot(N, -1);
   for (int n = 0; n < N; ++n)
     if (need[n]) bslot[n] = g->n_bvals++;
@@ -1115,17 +1126,20 @@ GenProgram* gen_program_create(const vael_circuit_desc_t* d, cudaError_t* err) {
   const int PBB = 128 * g->rb;
   std::vector<int4> bops, bsegs;
   std::vector<int32_t> bedges;
-  g->leaf_levels_b = 0;
-  for (int L = 0; L < d->n_levels; ++L) {
-    g->bseg_level_ptr[L] = (int)bsegs.size();
-    std::vector<HostOp> lvl;
-    for (int n = d->level_ptr[L]; n < d->level_ptr[L + 1]; ++n)
-      if (need[n]) lvl.push_back(make_op(d, n, [&](int x) { return bslot[x] * PBB; }));
-    for (const HostOp& h : lvl)
-      if ((h.op.w & 0xff) <= OP_LEAF_NEG) g->leaf_levels_b = L + 1;
-    emit_level(lvl, is_log, g->n_bvals * PBB, (g->n_bvals + 1) * PBB, bops, bedges, bsegs);
+  for (int sch = 0; sch < 2; ++sch) {
+    const std::vector<char>& set = sch == 0 ? need : need_plain;
+    g->leaf_levels_b[sch] = 0;
+    for (int L = 0; L < d->n_levels; ++L) {
+      g->bseg_level_ptr[sch][L] = (int)bsegs.size();
+      std::vector<HostOp> lvl;
+      for (int n = d->level_ptr[L]; n < d->level_ptr[L + 1]; ++n)
+        if (set[n]) lvl.push_back(make_op(d, n, [&](int x) { return bslot[x] * PBB; }));
+      for (const HostOp& h : lvl)
+        if ((h.op.w & 0xff) <= OP_LEAF_NEG) g->leaf_levels_b[sch] = L + 1;
+      emit_level(lvl, is_log, g->n_bvals * PBB, (g->n_bvals + 1) * PBB, bops, bedges, bsegs);
+    }
+    g->bseg_level_ptr[sch][d->n_levels] = (int)bsegs.size();
   }
-  g->bseg_level_ptr[d->n_levels] = (int)bsegs.size();
   g->norm_slot_off = g->norm_node >= 0 ? bslot[g->norm_node] * PBB : -1;
 
   // ---- liveness: a node carries an adjoint iff it is an output (world / query node) or feeds a live node ----
