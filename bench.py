@@ -2,7 +2,7 @@
 """Benchmark of the VAEL logic hot path (BASELINE.json metric: circuit evals/s).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path (baseline/_ref)
 
 One "step" = one forward + one adjoint backward of the compiled 2-digit-addition circuit
 over B batch rows per GPU (synthetic facts in the domain compute_facts_probability emits,
@@ -72,22 +72,76 @@ def host_threads():
     return n
 
 
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+STUB_DIR = os.path.join(ROOT, "baseline", "problog_stub")
+TRAIN_WORKLOAD = ("2digit-MNIST addition VAEL train step (encoder/decoder CNNs, logic path, ELBO, Adam), "
+                  "synthetic 28x56 images, random-init weights, fp32")
+
+
+def workload_config(rows_per_gpu, train_batch, l2, parallelism, train=None):
+    """`config` of the JSON line: the SAME keys from both arms (the driver compares them)."""
+    t = train or {}
+    return {"workload": WORKLOAD, "rows_per_gpu": rows_per_gpu, "evals_per_row": EVALS_PER_ROW, "l2": l2,
+            "parallelism": parallelism, "train_workload": TRAIN_WORKLOAD, "train_batch_per_gpu": train_batch,
+            "train_samples_per_sec": t.get("value"), "train_ms_per_step": t.get("ms_per_step"),
+            "train_mode": t.get("mode")}
+
+
+def reference_modules():
+    """The UNMODIFIED reference, copied to baseline/_ref by scripts/install_ref.py (it has no setup.py to pip
+    install).  Its only unsatisfiable imports, problog.logic / problog.evaluator, come from the inert stub under
+    baseline/problog_stub (no vael_b200 code).  -> (models.vael, models.vael_networks, utils.mnist_utils.train)
+    or None when baseline/_ref did not travel."""
+    if not os.path.exists(os.path.join(REF_DIR, "models", "vael.py")):
+        return None
+    for d in (STUB_DIR, REF_DIR):
+        if d not in sys.path:
+            sys.path.insert(0, d)
+    import importlib
+    return tuple(importlib.import_module(m) for m in ("models.vael", "models.vael_networks", "utils.mnist_utils.train"))
+
+
+def reference_w_q():
+    """build_worlds_queries_matrix (utils/mnist_utils/mnist_task_VAEL.py:222-234): that module imports matplotlib
+    and torchvision at the top, so the one function is exec'd from the reference's source file."""
+    import ast
+    from itertools import product
+    rel = "utils/mnist_utils/mnist_task_VAEL.py"
+    tree = ast.parse(open(os.path.join(REF_DIR, rel)).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "build_worlds_queries_matrix")
+    ns = {"torch": torch, "product": product}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), rel, "exec"), ns)
+    return ns["build_worlds_queries_matrix"](2, 10)
+
+
 def cpu_reference_rate(rows, steps, warmup, chunks=1):
     """evals/s of the reference's dense logic path (forward + autograd backward) on the host cores, torch CPU
-    with all its threads.  One step = `chunks` batches of `rows` rows (the batch is what bounds host memory:
-    worlds + upstream gradient are 800 B per row), so a step can cover the GPU arm's rows per step."""
-    from oracle import dense_path
+    with all its threads: MNISTPairsVAELModel.problog_inference (models/vael.py:208-225) of the reference itself
+    (baseline/_ref; `kind` "reference"), else the oracle's port of it (`kind` "port").  One step = `chunks`
+    batches of `rows` rows (the batch is what bounds host memory: worlds + upstream gradient are 800 B per row).
+    -> (rate, seconds per step, kind)"""
     facts, g = synthetic_facts(rows, "cpu", 1234)
     facts = facts.reshape(rows, 2, 10)
-    w_q = dense_path.worlds_queries_matrix()
     gw = torch.randn(rows, 100, generator=g)
     gq = torch.randn(rows, 1, generator=g)
     q = int(torch.randint(0, 19, (1,), generator=g))
+    ref = reference_modules()
+    if ref is not None:
+        vael, nets, _ = ref
+        model = vael.MNISTPairsVAELModel(encoder=None, decoder=None, mlp=nets.MNISTPairsMLP(in_features=15, n_facts=20),
+                                         latent_dims=(15, 8), model_dict=None, w_q=reference_w_q(), dropout=None,
+                                         is_train=True, device="cpu")
+        labels = torch.tensor([[0, 0, q, -1]]).expand(rows, 4)   # one query per batch: the reference's own mode (:212-213)
+        infer, kind = (lambda f: model.problog_inference(f, labels=labels)), "reference"
+    else:
+        from oracle import dense_path
+        w_q = dense_path.worlds_queries_matrix()
+        infer, kind = (lambda f: dense_path.dense_inference(f, w_q, q)), "port"
 
     def step():
         for _ in range(chunks):
             f = facts.clone().requires_grad_(True)
-            qp, worlds = dense_path.dense_inference(f, w_q, q)   # one query per batch: the reference's own mode
+            qp, worlds = infer(f)
             torch.autograd.backward([worlds, qp], [gw, gq])
         return f.grad
 
@@ -99,7 +153,42 @@ def cpu_reference_rate(rows, steps, warmup, chunks=1):
         step()
         times.append(time.perf_counter() - t0)
     dt = sum(times) / len(times)
-    return rows * chunks * EVALS_PER_ROW / dt, dt
+    return rows * chunks * EVALS_PER_ROW / dt, dt, kind
+
+
+def cpu_reference_train(batch, steps=3, warmup=1):
+    """The reference's own train step (utils/mnist_utils/train.py:105-150: forward, loss_function LAPLACE,
+    backward, Adam) on the host cores with the reference's classes from baseline/_ref; None without them."""
+    ref = reference_modules()
+    if ref is None:
+        return None
+    vael, nets, rtrain = ref
+    torch.manual_seed(0)
+    model = vael.MNISTPairsVAELModel(nets.MNISTPairsEncoder(hidden_channels=64, latent_dim=23, dropout=0.5),
+                                     nets.MNISTPairsDecoder(hidden_channels=64, latent_dim=8, label_dim=20, dropout=0.5),
+                                     nets.MNISTPairsMLP(in_features=15, n_facts=20), (15, 8), None, reference_w_q(),
+                                     dropout=0.5, is_train=True, device="cpu")
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(batch, 1, 28, 56, generator=g)
+    d = torch.randint(0, 10, (1, 2), generator=g).expand(batch, 2)      # the reference loader: one world per batch
+    labels = torch.cat([d, d.sum(1, keepdim=True), -torch.ones(batch, 1, dtype=torch.long)], 1)
+
+    def step():
+        opt.zero_grad()
+        recon, mu, logvar, add_prob = model(x, labels)
+        loss, *_ = rtrain.loss_function(recon, x, mu, logvar, add_prob, model=model, labels=labels, query=True,
+                                        recon_w=1e-1, kl_w=1e-5, query_w=1.0, sup_w=0.0, sup=False, rec_loss="LAPLACE")
+        loss.backward()
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": batch / dt, "unit": "samples/s", "ms_per_step": dt * 1e3, "mode": "reference eager, torch CPU"}
 
 
 def cpu_extras():
@@ -163,23 +252,34 @@ def cpu_extras():
 
 
 def run_reference(args):
+    """The reference arm: the reference's OWN dense logic path + autograd (baseline/_ref, stock torch CPU code
+    path, none of this repo's kernels) on the box's host cores with every thread torch can use.  Under torchrun
+    rank 0 alone runs; the other ranks exit 0."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(1, args.warmup)
     host_threads()
-    chunks = max(1, args.rows // args.cpu_rows)   # one step covers the GPU arm's rows per step (8 Mi by default)
-    rate, dt = cpu_reference_rate(args.cpu_rows, steps, warmup, chunks)
+    chunks = max(1, args.rows // args.cpu_rows)   # one step covers ONE GPU's rows per step (8 Mi by default)
+    rate, dt, kind = cpu_reference_rate(args.cpu_rows, steps, warmup, chunks)
     cores = torch.get_num_threads()
+    train = None
+    if not args.no_train:
+        try:
+            train = cpu_reference_train(args.train_batch)
+        except Exception as exc:  # noqa: BLE001 - the probe must not cost the line
+            train = {"mode": "error: " + repr(exc)[:120]}
+    what = ("the reference's own MNISTPairsVAELModel.problog_inference (baseline/_ref/models/vael.py:208-225) + autograd"
+            if kind == "reference" else "oracle port of models/vael.py:208-225 + autograd (baseline/_ref absent)")
     line = {
         "impl": "reference", "metric": "circuit_evals_per_sec", "value": rate, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rows_per_step": args.cpu_rows * chunks, "evals_per_row": EVALS_PER_ROW},
-        "cpu_baseline": {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
+        "config": workload_config(args.rows, args.train_batch, "n/a (host arm: inputs in host DRAM)",
+                                  "one host process, all torch CPU threads", train),
+        "cpu_baseline": {"value": rate, "unit": "evals/s", "cores": cores, "kind": kind,
                          "sample": f"{chunks} batches x {args.cpu_rows} rows per step x {steps} steps "
-                                   f"({dt:.2f} s/step), torch CPU fp32 port of "
-                                   f"models/vael.py:208-225 + autograd, os.cpu_count()={os.cpu_count()}"},
+                                   f"({dt:.2f} s/step), torch CPU fp32, {what}, os.cpu_count()={os.cpu_count()}"},
         "e2e": {"value": rate, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -269,7 +369,12 @@ def run_ours(args):
     distributed = world > 1
     numa = parallel.bind_to_gpu_numa_node(local) if distributed and not os.environ.get("VAEL_NO_NUMA_BIND") else None
     if distributed:
-        os.environ["NCCL_DEBUG"] = os.environ.get("VAEL_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # NCCL_DEBUG belongs to the caller (the driver reads the communicator lines) and is honoured as set.  Unset:
+        # the communicator-init lines (ranks, NVLS / P2P transport) are logged to STDERR, stdout stays one JSON line.
+        if not os.environ.get("NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -359,6 +464,22 @@ def run_ours(args):
         torch.cuda.synchronize()
         link_gbs = Be * 400 / ((time.perf_counter() - tp0) / 3) / 1e9
         del d_up, d_dn
+        # the byte diet: what the reference's training loop consumes (query in the BCE term, its gradient back to the
+        # facts) without any [B,W] tensor over PCIe — vael_circuit_query_grad_host, 88 B up + 84 B down per row
+        hgf2, hqo2 = torch.empty(Be, 20).pin_memory(), torch.empty(Be).pin_memory()
+
+        def diet_step():
+            _lib.check(lib.vael_circuit_query_grad_host(dc.handle, _p(hf), _p(hq), -1, Be, _p(hgq), _p(hqo2), _p(hgf2), 0))
+
+        for _ in range(2):
+            diet_step()
+        barrier()
+        td0 = time.perf_counter()
+        for _ in range(ke):
+            diet_step()
+        torch.cuda.synchronize()
+        diet_s = max_over_ranks((time.perf_counter() - td0) / ke)
+        assert torch.equal(hqo2[:4096], query[:4096].cpu()), "query_grad host path and device path disagree"
         e2e = {"value": world * Be * EVALS_PER_ROW / e2e_s, "unit": "evals/s",
                "h2d_bytes_per_step": Be * (80 + 4 + 400 + 4), "d2h_bytes_per_step": Be * (400 + 4 + 80),
                "rows_per_gpu": Be, "ms_per_step": e2e_s * 1e3, "cpu_affinity": numa,
@@ -366,7 +487,12 @@ def run_ours(args):
                         "frac": (Be * 488 / e2e_s / 1e9) / link_gbs,
                         "what": "PCIe-bound: bytes each way / step time against plain pinned cudaMemcpyAsync "
                                 "running H2D and D2H concurrently on this box"},
-               "api": "vael_circuit_fwdbwd_host (C-ABI, pinned host buffers, 128Ki-row chunks over 4 streams)"}
+               "api": "vael_circuit_fwdbwd_host (C-ABI, pinned host buffers, 128Ki-row chunks over 4 streams)",
+               "query_grad_rows_per_sec": world * Be / diet_s, "query_grad_ms_per_step": diet_s * 1e3,
+               "query_grad_h2d_bytes_per_step": Be * (80 + 4 + 4), "query_grad_d2h_bytes_per_step": Be * (4 + 80),
+               "query_grad_vs_full_rows_per_sec": e2e_s / diet_s,
+               "query_grad_api": "vael_circuit_query_grad_host: facts + query index + grad_query in, query + grad_facts "
+                                 "out (what utils/mnist_utils/train.py:123-147 consumes); no [B,W] tensor crosses PCIe"}
 
     # ---- secondary probe: VAEL train step (configs[1]), DDP when N > 1 --------------------------------
     train = None
@@ -389,11 +515,13 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         host_threads()
         cpu_chunks = max(1, args.rows // args.cpu_rows)      # one CPU step = this arm's rows per step
-        rate, dt = cpu_reference_rate(args.cpu_rows, 6, 1, cpu_chunks)
-        cpu = {"value": rate, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port",
+        rate, dt, kind = cpu_reference_rate(args.cpu_rows, 6, 1, cpu_chunks)
+        cpu = {"value": rate, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": kind,
                "sample": f"{cpu_chunks} batches x {args.cpu_rows} rows per step x 6 steps ({dt:.2f} s/step, "
-                         f"{7 * dt:.0f} s of CPU work), torch CPU fp32 port of "
-                         f"models/vael.py:208-225 + autograd, os.cpu_count()={os.cpu_count()}"}
+                         f"{7 * dt:.0f} s of CPU work), torch CPU fp32, "
+                         + ("the reference's own models/vael.py:208-225 (baseline/_ref) + autograd" if kind == "reference"
+                            else "oracle port of models/vael.py:208-225 + autograd")
+                         + f", os.cpu_count()={os.cpu_count()}"}
         try:
             cpu["also"] = cpu_extras()
         except Exception as exc:
@@ -421,19 +549,25 @@ def run_ours(args):
             "metric": "circuit_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rows_per_gpu": B, "evals_per_row": EVALS_PER_ROW,
-                       "kernel_family": kernel_family, "l2": "inputs larger than L2 (per-GPU step traffic "
-                       f"{B * (FWD_BYTES + BWD_BYTES) / 1e9:.2f} GB vs 126 MB L2)", "parallelism": f"rows sharded x{world}, "
-                       "circuit replicated, no collective on the data path"},
-            "roofline": {"bound": "hbm", "kernel": dom["name"], "achieved": dom["GBs"], "peak": peak, "unit": "GB/s",
+            "config": workload_config(B, args.train_batch, "inputs larger than L2 (per-GPU step traffic "
+                                      f"{B * (FWD_BYTES + BWD_BYTES) / 1e9:.2f} GB vs 126 MB L2)",
+                                      f"rows sharded x{world}, circuit replicated, no collective on the data path; "
+                                      "train step: DDP-style data parallel, one NCCL all-reduce of the flat gradient",
+                                      train if isinstance(train, dict) and "value" in train else None),
+            "kernel_family": kernel_family,
+            "roofline": {"bound": "hbm", "kernel": dom["name"], "kernel_family": kernel_family, "achieved": dom["GBs"], "peak": peak, "unit": "GB/s",
                          "frac": dom["GBs"] / peak, "traffic": traffic, "peak_source": peak_src, "kernels": kern,
                          "algorithmic_bytes_per_launch": B * dom["bytes_per_row"]},
             "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu, "train": train,
             "secondary": secondary,
         }
+    if distributed:
+        dist.barrier()        # nothing else writes to stdout while rank 0 prints the line
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if distributed:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -580,6 +714,13 @@ def secondary_probe(args, dev, rank, world, barrier, max_over_ranks, lib):
     except Exception as exc:  # noqa: BLE001 - a secondary probe must not take the headline down
         out["mario_circuits"] = {"error": repr(exc)[:300]}
 
+    # -- the training-mode logic path (models/vael.py:55-65): ONE fused kernel per direction against the three-stage
+    # chain it replaces (facts head -> circuit -> Gumbel sampling), both with in-kernel Philox noise
+    try:
+        out["logic_train_path"] = logic_path_probe(dev, rank, barrier, max_over_ranks, lib, peak)
+    except Exception as exc:  # noqa: BLE001
+        out["logic_train_path"] = {"error": repr(exc)[:300]}
+
     facts2, g2 = synthetic_facts(B2, dev, parallel.rank_seed(99, rank))
     qa = torch.empty(B2, 19, device=dev)
     a_ms, _ = _time_pair(lambda: _lib.check(lib.vael_circuit_queries_all(dc2.handle, _p(facts2), B2, _p(qa), 0, sp)),
@@ -591,10 +732,61 @@ def secondary_probe(args, dev, rank, world, barrier, max_over_ranks, lib):
     return out
 
 
+def logic_path_probe(dev, rank, barrier, max_over_ranks, lib, peak, Bl=1 << 20):
+    from vael_b200 import _lib, parallel
+    from vael_b200.mnist_task import compile_addition_family
+    from vael_b200.ops import DeviceCircuit, _p
+    sp = torch.cuda.current_stream().cuda_stream
+    dc = DeviceCircuit(compile_addition_family(2, 10).circuit, dev)
+    g = torch.Generator(device=dev).manual_seed(parallel.rank_seed(31, rank))
+    logits = 3.0 * torch.randn(Bl, 20, device=dev, generator=g)
+    qidx = torch.randint(0, 19, (Bl,), device=dev, dtype=torch.int32, generator=g)
+    gh = torch.randn(Bl, 20, device=dev, generator=g); gq = torch.randn(Bl, device=dev, generator=g)
+    facts = torch.empty(Bl, 20, device=dev); query = torch.empty(Bl, device=dev); wh = torch.empty(Bl, 20, device=dev)
+    idx = torch.empty(Bl, device=dev, dtype=torch.int32); gl = torch.empty(Bl, 20, device=dev)
+    f_ms, b_ms = _time_pair(
+        lambda: _lib.check(lib.vael_logic_train_forward(dc.handle, _p(logits), _p(qidx), -1, Bl, 1e-5, 1.0, None, 1234, None,
+                                                        _p(facts), _p(query), _p(idx), _p(wh), None, sp)),
+        lambda: _lib.check(lib.vael_logic_train_backward(dc.handle, _p(logits), _p(qidx), -1, Bl, 1e-5, 1.0, None, 1234, None,
+                                                         _p(gh), _p(gq), None, _p(gl), sp)),
+        10, barrier, max_over_ranks)
+    fb, bb = 80 + 4 + 80 + 4 + 4 + 80, 80 + 4 + 80 + 4 + 80
+    # the stage kernels on the same rows
+    worlds = torch.empty(Bl, 100, device=dev); ys = torch.empty(Bl, 100, device=dev); gs = torch.empty(Bl, 100, device=dev)
+    gf = torch.empty(Bl, 20, device=dev)
+    hb = torch.cat([torch.eye(10).repeat_interleave(10, 0), torch.eye(10).repeat(10, 1)], 1).to(dev).contiguous()
+
+    def stage_fwd():
+        _lib.check(lib.vael_facts_forward(_p(logits), Bl, 2, 10, 1e-5, _p(facts), sp))
+        _lib.check(lib.vael_circuit_forward(dc.handle, _p(facts), _p(qidx), -1, Bl, _p(worlds), _p(query), 0, sp))
+        _lib.check(lib.vael_gumbel_world_forward(_p(worlds), None, 1234, Bl, 100, 0, 1.0, _p(hb), 20, _p(ys), _p(idx), _p(wh), sp))
+
+    def stage_bwd():
+        _lib.check(lib.vael_gumbel_world_backward(_p(worlds), _p(ys), _p(gh), Bl, 100, 0, 1.0, _p(hb), 20, _p(gs), sp))
+        _lib.check(lib.vael_circuit_backward(dc.handle, _p(facts), _p(qidx), -1, Bl, _p(gs), _p(gq), _p(gf), 0, sp))
+        _lib.check(lib.vael_facts_backward(_p(logits), _p(gf), Bl, 2, 10, 1e-5, _p(gl), sp))
+
+    sf_ms, sb_ms = _time_pair(stage_fwd, stage_bwd, 10, barrier, max_over_ranks)
+    sfb = (80 + 80) + (80 + 4 + 400 + 4) + (400 + 400 + 4 + 80)              # facts head, circuit, gumbel
+    sbb = (400 + 400 + 80 + 400) + (400 + 4 + 80 + 4 + 80) + (80 + 80 + 80)  # gumbel, circuit, facts head adjoints
+    return {"workload": "2digit VAEL logic path in training mode: logits[20] -> facts -> worlds -> query -> Gumbel arg-max "
+                        "-> Herbrand vector, and its adjoint; in-kernel Philox noise, per-row query", "rows_per_gpu": Bl,
+            "fused": {"fwd": {"ms": f_ms, "bytes_per_row": fb, "GBs": Bl * fb / f_ms / 1e6, "frac_hbm": Bl * fb / f_ms / 1e6 / peak,
+                              "rows_per_sec": Bl / (f_ms * 1e-3)},
+                      "bwd": {"ms": b_ms, "bytes_per_row": bb, "GBs": Bl * bb / b_ms / 1e6, "frac_hbm": Bl * bb / b_ms / 1e6 / peak,
+                              "rows_per_sec": Bl / (b_ms * 1e-3)},
+                      "bound": "FP32/SFU issue (about 5.5 k instructions per row: 25 Philox4x32-10 calls, 100 Gumbel "
+                               "transforms, 100 expf, 20 logf), not HBM"},
+            "three_stage_kernels": {"fwd": {"ms": sf_ms, "bytes_per_row": sfb, "GBs": Bl * sfb / sf_ms / 1e6},
+                                    "bwd": {"ms": sb_ms, "bytes_per_row": sbb, "GBs": Bl * sbb / sb_ms / 1e6}},
+            "speedup": {"fwd": sf_ms / f_ms, "bwd": sb_ms / b_ms}}
+
+
 def train_probe(args, dev, rank, world, distributed, barrier, max_over_ranks):
-    """VAEL train samples/s: BASELINE.json configs[1] (2digit-MNIST addition, batch 4096 per GPU, DDP when
-    N > 1) and configs[0] (the B = 32 reference configuration): encoder/decoder in PyTorch, the logic path
-    on the vael_b200 kernels, Adam; the whole step is one CUDA graph at N = 1, DDP/NCCL eager at N > 1."""
+    """VAEL train samples/s: BASELINE.json configs[1] (2digit-MNIST addition, batch 4096 per GPU, data parallel
+    when N > 1) and configs[0] (the B = 32 reference configuration): encoder/decoder in PyTorch, the logic path
+    on the fused vael_b200 kernel, Adam; the step is one CUDA graph at N = 1 and two graphs around one NCCL
+    all-reduce of the flat gradient at N > 1 (eager DistributedDataParallel timed beside it)."""
     from vael_b200.mnist_task import build_model_dict, build_worlds_queries_matrix
     from vael_b200.networks import MNISTPairsDecoder, MNISTPairsEncoder, MNISTPairsMLP
     from vael_b200.train import GraphedTrainStep, as_channels_last, train_step
@@ -618,6 +810,8 @@ def train_probe(args, dev, rank, world, distributed, barrier, max_over_ranks):
         d = torch.randint(0, 10, (Bt, 2), device=dev, generator=g)
         labels = torch.cat([d, d.sum(1, keepdim=True), -torch.ones(Bt, 1, dtype=torch.long, device=dev)], 1)
         if graphed:
+            # N = 1: one CUDA graph.  N > 1: forward+backward graph, ONE NCCL all-reduce of the flat 7.4 MB gradient
+            # (train.FlatGradBucket), Adam graph
             stepper = GraphedTrainStep(model, opt, tuple(x.shape), tuple(labels.shape), device=dev,
                                        memory_format=torch.channels_last)
             step = lambda: stepper(x, labels)
@@ -634,15 +828,23 @@ def train_probe(args, dev, rank, world, distributed, barrier, max_over_ranks):
         e1.record()
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1)) / n
+        mode = ("cuda-graph" if not distributed else "2 cuda graphs + 1 nccl all-reduce of the flat gradient") if graphed \
+            else ("ddp-nccl eager" if distributed else "eager")
         return {"value": world * Bt / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "global_batch": world * Bt,
-                "loss": float(terms[0].item()), "mode": "cuda-graph" if graphed else ("ddp-nccl eager" if distributed else "eager")}
+                "loss": float(terms[0].item()), "mode": mode}
 
     out = {"metric": "vael_train_samples_per_sec",
            "config": "2digit-MNIST addition VAEL, synthetic 28x56 images, random-init weights, Adam, fp32 "
                      "(cuDNN TF32 convolutions as in stock PyTorch), channels_last activations, fused Adam"}
-    main = run(args.train_batch, graphed=not distributed, n=20)
+    try:
+        main = run(args.train_batch, graphed=True, n=20)
+    except Exception as exc:   # noqa: BLE001 - fall back to the eager step rather than lose the number
+        if not distributed:
+            raise
+        main = run(args.train_batch, graphed=False, n=20)
+        main["graphed_error"] = repr(exc)[:200]
     out.update(main)
-    out["eager"] = run(args.train_batch, graphed=False, n=20) if not distributed else None
+    out["eager"] = run(args.train_batch, graphed=False, n=20)
     if not distributed:
         out["reference_config_B32"] = {"cuda_graph": run(32, True, 200), "eager": run(32, False, 50)}
         try:

@@ -15,7 +15,14 @@
  *    synchronisation, CUDA-graph capturable.
  *  - *_host entry points take HOST buffers, do the H2D / D2H copies
  *    themselves in row chunks on internal streams, and return after the
- *    results are in the host buffers.
+ *    results are in the host buffers (also on an error return: no copy is
+ *    still in flight when the caller gets its buffers back).
+ *  - threading: a circuit handle is immutable after creation as far as the
+ *    device entry points are concerned — any number of host threads may call
+ *    them on one handle, each on its own stream.  The *_host entry points
+ *    share the handle's staging buffers and streams (allocated on first use):
+ *    concurrent *_host callers of ONE handle are serialised by a mutex inside
+ *    the handle; use one handle per thread for parallel host pipelines.
  *  - return value: 0 = ok, otherwise a VAEL_E_* code; vael_last_error() gives
  *    the message for the calling thread.
  *  - there is no CPU fallback: without a CUDA device every compute entry
@@ -30,7 +37,7 @@
 extern "C" {
 #endif
 
-#define VAEL_B200_ABI_VERSION 1
+#define VAEL_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define VAEL_API __attribute__((visibility("default")))
@@ -61,6 +68,16 @@ extern "C" {
 #define VAEL_FLAG_NORMALIZE 1u /* divide every output by the normaliser node Z (GraphSemiring.normalize, :54-55) */
 #define VAEL_FLAG_EVIDENCE 2u  /* condition the worlds on the selected query node: P(w | q) (models/vael.py:119-135) */
 #define VAEL_FLAG_FORCE_GENERIC 4u /* run the generic level-by-level CSR kernel even if a structured fast path exists */
+#define VAEL_FLAG_CHECK_QUERY 8u   /* validate the per-row query indices first: any index outside [-1, Q) makes the
+                                      call return VAEL_E_INVALID before the circuit kernel is launched (-1 is the
+                                      "no query for this row" sentinel: its query value is 0).  The check
+                                      synchronises `stream`, so a call carrying this flag is NOT graph-capturable.
+                                      Without the flag an out-of-range index silently yields 0. */
+
+/* ---- reconstruction terms of vael_elbo_terms (rec_loss of loss_function, utils/mnist_utils/train.py:16-21) ---- */
+#define VAEL_REC_LAPLACE 0 /* -mean_b sum_pix log Laplace(x | recon, 1)   (config.py:17,45: the shipped setting) */
+#define VAEL_REC_MSE 1     /* torch.nn.MSELoss(reduction='mean') over the flattened images */
+#define VAEL_REC_BCE 2     /* torch.nn.BCELoss(reduction='mean') over the flattened images */
 
 /*
  * Host description of a compiled circuit.  Nodes are numbered level by level
@@ -154,6 +171,13 @@ VAEL_API int vael_circuit_fwdbwd_host(const vael_circuit_t* c, const float* fact
                              int32_t query_scalar, int64_t B, const float* grad_worlds_h,
                              const float* grad_query_h, float* worlds_h, float* query_h,
                              float* grad_facts_h, uint32_t flags);
+/* What the reference's training loop consumes from the logic path (utils/mnist_utils/train.py:123-147: the
+ * query probability enters the BCE term, its gradient flows back to the facts) without moving any [B,W] tensor
+ * over PCIe: facts [B,F] + query index (+ upstream grad_query [B]) in; query [B] + grad_facts [B,F] =
+ * grad_query * d query / d facts out.  172 B per row against 1000 B for vael_circuit_fwdbwd_host. */
+VAEL_API int vael_circuit_query_grad_host(const vael_circuit_t* c, const float* facts_h, const int32_t* query_idx_h,
+                                 int32_t query_scalar, int64_t B, const float* grad_query_h, float* query_h,
+                                 float* grad_facts_h, uint32_t flags);
 
 /* ---- facts from MLP logits --------------------------------------------------
  * MNISTPairsVAELModel.compute_facts_probability (models/vael.py:159-177):
@@ -164,6 +188,13 @@ VAEL_API int vael_facts_forward(const float* logits, int64_t B, int32_t n_groups
 /* logits are re-read (the softmax is recomputed); grad_facts [B,n_groups*group] -> grad_logits */
 VAEL_API int vael_facts_backward(const float* logits, const float* grad_facts, int64_t B, int32_t n_groups,
                         int32_t group, float eps, float* grad_logits, void* stream);
+
+/* MarioVAELModel's facts (models/vael.py:319-322): per group softmax, then clamp to [lo, hi]
+ * (torch.clip(min=1e-5, max=0.9999)); the gradient passes where lo <= softmax <= hi.          */
+VAEL_API int vael_facts_clip_forward(const float* logits, int64_t B, int32_t n_groups, int32_t group, float lo,
+                            float hi, float* facts, void* stream);
+VAEL_API int vael_facts_clip_backward(const float* logits, const float* grad_facts, int64_t B, int32_t n_groups,
+                             int32_t group, float lo, float hi, float* grad_logits, void* stream);
 
 /* ---- Gumbel-softmax world sampling + Herbrand projection --------------------
  * Replaces logits=log(worlds_prob); F.gumbel_softmax(logits, tau, hard=True);
@@ -183,21 +214,46 @@ VAEL_API int vael_gumbel_world_backward(const float* scores, const float* y_soft
                                int64_t B, int32_t W, int32_t is_log, float tau, const float* herbrand,
                                int32_t H, float* grad_scores, void* stream);
 
+/* ---- the training-mode logic path in one kernel per direction -----------------------
+ * VAELModel.forward between the MLP and the decoder (models/vael.py:55-65) for the two-digit program family:
+ * compute_facts_probability (:159-177) -> problog_inference (:200-225) -> log + F.gumbel_softmax(hard) (:61-62)
+ * -> herbrand with define_herbrand_base (:82-84, :179-187).  No [B,W] tensor touches memory; the adjoint redraws
+ * the Gumbel noise from the same counters (Philox4x32-10 keyed by `seed`, or by the device word `seed_dev` when
+ * given — a CUDA graph can refresh it per replay) instead of saving it.  Covers circuits of fast_kind 2 whose two
+ * annotated disjunctions have 9 or 10 values each (vael_logic_fused_supported); the Herbrand base is the
+ * reference's: row i*N+k = [onehot(i), onehot(k)].
+ *   logits   [B,2N]  MLP outputs                     noise  [B,W] injected Gumbel noise or NULL
+ *   facts    [B,2N]  out or NULL                     query  [B]   out or NULL (selected per row by query_idx / scalar)
+ *   world_idx[B]     out or NULL (arg-max world)     world_h[B,2N] out or NULL  ((1-y)+y at the two selected columns)
+ *   y_soft   [B,W]   out or NULL (tests)                                                                   */
+VAEL_API int vael_logic_fused_supported(const vael_circuit_t* c);
+VAEL_API int vael_logic_train_forward(const vael_circuit_t* c, const float* logits, const int32_t* query_idx,
+                             int32_t query_scalar, int64_t B, float eps, float tau, const float* noise,
+                             uint64_t seed, const uint64_t* seed_dev, float* facts, float* query,
+                             int32_t* world_idx, float* world_h, float* y_soft, void* stream);
+/* autograd through all of the above (utils/mnist_utils/train.py:147): grad_world_h [B,2N], grad_query [B],
+ * grad_facts [B,2N] (upstream gradient of the `facts` output) — each may be NULL (= 0) -> grad_logits [B,2N] */
+VAEL_API int vael_logic_train_backward(const vael_circuit_t* c, const float* logits, const int32_t* query_idx,
+                              int32_t query_scalar, int64_t B, float eps, float tau, const float* noise,
+                              uint64_t seed, const uint64_t* seed_dev, const float* grad_world_h,
+                              const float* grad_query, const float* grad_facts, float* grad_logits, void* stream);
+
 /* ---- ELBO terms ---------------------------------------------------------------
- * loss_function with rec_loss='LAPLACE' (utils/mnist_utils/train.py:13-55;
- * utils/mario_utils/train.py:11-69):
- *   recon = -mean_b sum_pix( -log 2 - |x - recon| ),  kl = mean_b -0.5*sum(1+logvar-mu^2-exp(logvar)),
+ * loss_function (utils/mnist_utils/train.py:13-55; utils/mario_utils/train.py:11-69):
+ *   recon = rec_loss LAPLACE: -mean_b sum_pix( -log 2 - |x - recon| );  MSE / BCE: torch's mean-reduced losses
+ *   kl = mean_b -0.5*sum(1+logvar-mu^2-exp(logvar)),
  *   qbce  = mean_b -max(log q, -100),  loss = recon_w*recon + kl_w*kl + query_w*qbce.
  *   terms[4] device out: {loss, recon, kl, qbce}.
  * The same pass writes the gradients of `loss` (any of the grad_* may be NULL).
  * `workspace`: device scratch of vael_elbo_workspace_bytes() bytes, zero-filled once by
  * the caller before its first use (the kernel leaves it clean); per-CTA partial sums
- * are added in a fixed order by the last CTA, so the terms are deterministic.   */
+ * are added in a fixed order by the last CTA, so the terms are deterministic.  A workspace
+ * belongs to ONE call in flight: calls that may overlap (different streams) need their own. */
 VAEL_API int64_t vael_elbo_workspace_bytes(void);
 VAEL_API int vael_elbo_terms(const float* recon, const float* x, int64_t B, int64_t D, const float* mu,
                     const float* logvar, int32_t L, const float* query_prob, float recon_w, float kl_w,
-                    float query_w, float* terms, float* grad_recon, float* grad_mu, float* grad_logvar,
-                    float* grad_query, void* workspace, void* stream);
+                    float query_w, int32_t rec_loss, float* terms, float* grad_recon, float* grad_mu,
+                    float* grad_logvar, float* grad_query, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -246,8 +246,9 @@ def test_full_size_properties_and_host_path(dc, addition_family):
 @pytest.mark.parametrize("B", [1, 77, 3000])
 def test_admissible_worlds_literal_table_kernel(cuda_device, B):
     """Mario's admissible-world log-probabilities (models/vael.py:368-375) through the literal-table kernel
-    (fast_kind 4): bit for bit the generic CSR kernel, within 1e-5 of the reference's two-matmul form, adjoint
-    against fp64 autograd of that form; a table the kernel does not cover stays on the generic kernel."""
+    (fast_kind 4): within 1e-5 of the reference's two-matmul form (fp64) — like the generic CSR kernel, which folds
+    the same terms in CSR order —, adjoint against fp64 autograd of that form; tables with mostly-positive rows take
+    the base+ form; a table the kernel does not cover stays on the generic kernel."""
     from vael_b200 import _lib
     from vael_b200.compiler import circuit_from_world_table
     from vael_b200.mario_task import admissible_circuit, compile_mario_family, mario_tables
@@ -266,15 +267,34 @@ def test_admissible_worlds_literal_table_kernel(cuda_device, B):
         (lw * torch.from_numpy(ga).cuda()).sum().backward()
         assert _lib.last_kernel() == ("generic-csr" if generic else "lt-log")
         outs.append((lw.detach().cpu().numpy(), f.grad.cpu().numpy()))
-    np.testing.assert_array_equal(outs[0][0], outs[1][0])
     p64 = torch.from_numpy(p.astype(np.float64)).requires_grad_(True)
     Wt = torch.from_numpy(W_adm.astype(np.float64))
     ref = torch.log(p64) @ Wt.T + torch.log(1 - p64) @ (1 - Wt).T          # models/vael.py:371-374
     (ref * torch.from_numpy(ga).double()).sum().backward()
-    assert rel_err(outs[0][0], ref.detach().numpy()) < 1e-5
     g_ref = p64.grad.numpy()
     for o in outs:
+        assert rel_err(o[0], ref.detach().numpy()) < 1e-5
         assert rel_err(o[1], g_ref, floor=1e-3 * np.abs(g_ref).max()) < 1e-4
-    # 19 fact columns: not a shape the kernel is built for
+    # a random table with sparse, dense and half-set rows: base- and base+ forms side by side
+    tab = np.zeros((12, 18), dtype=np.int8)
+    for w, k in enumerate((0, 1, 2, 3, 5, 8, 9, 10, 14, 16, 17, 18)):
+        tab[w, rng.permutation(18)[:k]] = 1
+    dct = DeviceCircuit(circuit_from_world_table(tab), cuda_device)
+    assert dct.fast_kind == 4
+    f = torch.from_numpy(p).cuda().requires_grad_(True)
+    gt = rng.standard_normal((B, 12)).astype(np.float32)
+    lw, _ = circuit_forward(dct, f, None)
+    assert _lib.last_kernel() == "lt-log"
+    (lw * torch.from_numpy(gt).cuda()).sum().backward()
+    p64 = torch.from_numpy(p.astype(np.float64)).requires_grad_(True)
+    Tt = torch.from_numpy(tab.astype(np.float64))
+    ref = torch.log(p64) @ Tt.T + torch.log(1 - p64) @ (1 - Tt).T
+    (ref * torch.from_numpy(gt).double()).sum().backward()
+    assert rel_err(lw.detach().cpu().numpy(), ref.detach().numpy()) < 1e-5
+    assert rel_err(f.grad.cpu().numpy(), p64.grad.numpy(), floor=1e-3 * np.abs(p64.grad.numpy()).max()) < 1e-4
+    # 19 fact columns: not a shape the kernel is built for; 40 worlds all setting column 0: the per-column list
+    # does not fit the kernel's tables
     odd = DeviceCircuit(circuit_from_world_table(rng.integers(0, 2, size=(5, 19))), cuda_device)
     assert odd.fast_kind == 0
+    long_col = rng.integers(0, 2, size=(40, 18)); long_col[:, 0] = 1
+    assert DeviceCircuit(circuit_from_world_table(long_col), cuda_device).fast_kind == 0

@@ -50,19 +50,28 @@ _PROTOTYPES = {
     "vael_circuit_queries_all": (C.c_int, [_P, _P, C.c_int64, _P, C.c_uint32, _P]),
     "vael_circuit_forward_host": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, _P, _P, C.c_uint32]),
     "vael_circuit_fwdbwd_host": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, _P, _P, _P, _P, _P, C.c_uint32]),
+    "vael_circuit_query_grad_host": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, _P, _P, _P, C.c_uint32]),
     "vael_facts_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_float, _P, _P]),
     "vael_facts_backward": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_float, _P, _P]),
+    "vael_facts_clip_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P]),
+    "vael_facts_clip_backward": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P]),
     "vael_gumbel_world_forward": (C.c_int, [_P, _P, C.c_uint64, C.c_int64, C.c_int32, C.c_int32, C.c_float, _P,
                                             C.c_int32, _P, _P, _P, _P]),
     "vael_gumbel_world_backward": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_float, _P, C.c_int32,
                                              _P, _P]),
+    "vael_logic_fused_supported": (C.c_int, [_P]),
+    "vael_logic_train_forward": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_float, C.c_float, _P, C.c_uint64, _P,
+                                           _P, _P, _P, _P, _P, _P]),
+    "vael_logic_train_backward": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_float, C.c_float, _P, C.c_uint64, _P,
+                                            _P, _P, _P, _P, _P]),
     "vael_elbo_workspace_bytes": (C.c_int64, []),
     "vael_elbo_terms": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, C.c_int32, _P, C.c_float, C.c_float,
-                                  C.c_float, _P, _P, _P, _P, _P, _P, _P]),
+                                  C.c_float, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
 
 _lib = None
+ABI_VERSION = 2
 
 
 def load() -> C.CDLL:
@@ -78,7 +87,7 @@ def load() -> C.CDLL:
     for name, (res, args) in _PROTOTYPES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.vael_abi_version() != 1:
+    if lib.vael_abi_version() != ABI_VERSION:
         raise ImportError("libvael_b200.so ABI version mismatch")
     _lib = lib
     return lib

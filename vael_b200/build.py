@@ -13,8 +13,8 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libvael_b200.so"
-SOURCES = ["capi.cu", "circuit_ad2.cu", "circuit_adw.cu", "circuit_generic.cu", "circuit_lt.cu", "sampling.cu", "elbo.cu"]
-HEADERS = [CSRC / "common.cuh", CSRC / "params.cuh", PKG.parent / "include" / "vael_b200.h"]
+SOURCES = ["capi.cu", "circuit_ad2.cu", "circuit_adw.cu", "circuit_generic.cu", "circuit_lt.cu", "sampling.cu", "logic_fused.cu", "elbo.cu"]
+HEADERS = [CSRC / "common.cuh", CSRC / "params.cuh", CSRC / "sampling.cuh", PKG.parent / "include" / "vael_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

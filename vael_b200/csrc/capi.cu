@@ -1,9 +1,11 @@
 // C-ABI of libvael_b200.so (include/vael_b200.h): circuit upload + validation,
 // kernel dispatch, host-buffer (e2e) variants.  No torch types anywhere.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -125,6 +127,8 @@ extern "C" void vael_circuit_destroy(vael_circuit_t* c) {
   cudaSetDevice(c->device);
   gen_program_destroy(c->gen);
   cudaFree(c->d_qmask); cudaFree(c->d_qm_ptr); cudaFree(c->d_qm_idx); cudaFree(c->d_qmask_c);
+  cudaFree(c->d_bad_query);
+  if (c->h_bad_query) cudaFreeHost(c->h_bad_query);
   for (auto& S : c->slot) {
     cudaFree(S.facts); cudaFree(S.worlds); cudaFree(S.query); cudaFree(S.gw); cudaFree(S.gq); cudaFree(S.gf);
     cudaFree(S.qidx);
@@ -194,8 +198,7 @@ extern "C" int vael_circuit_create(const vael_circuit_desc_t* d, vael_circuit_t*
   CK(cudaGetDevice(&dev));
   if (int rc = device_sms(&sms)) return rc;
 
-  vael_circuit_t* c = new vael_circuit_t();
-  memset(c, 0, sizeof(*c));
+  vael_circuit_t* c = new vael_circuit_t();   // value-initialised: every plain member is zero
   c->device = dev; c->num_sms = sms;
   c->n_facts = d->n_facts; c->n_nodes = d->n_nodes; c->n_levels = d->n_levels; c->n_edges = d->n_edges;
   c->n_worlds = d->n_worlds; c->n_queries = d->n_queries; c->semiring = d->semiring;
@@ -314,7 +317,7 @@ extern "C" int vael_circuit_create(const vael_circuit_desc_t* d, vael_circuit_t*
       ok = ok && (pos & neg) == 0 && (pos | neg) == all;
       c->lt_mask[w] = pos;
     }
-    if (ok) c->fast_kind = 4;
+    if (ok && lt_masks_fit(d->n_facts, d->n_worlds, c->lt_mask)) c->fast_kind = 4;
   }
 
   cudaError_t e = cudaSuccess;
@@ -357,6 +360,9 @@ extern "C" int vael_circuit_create(const vael_circuit_desc_t* d, vael_circuit_t*
     }
   }
   if (!qmask_c.empty()) up(&c->d_qmask_c, qmask_c);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->d_bad_query), sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMemset(c->d_bad_query, 0, sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&c->h_bad_query), sizeof(int32_t));
   if (e == cudaSuccess) c->gen = gen_program_create(d, &e);
   if (e != cudaSuccess) {
     vael_circuit_destroy(c);
@@ -372,6 +378,31 @@ extern "C" uint64_t vael_circuit_hash(const vael_circuit_t* c) { return c ? c->h
 // ---------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------
+// VAEL_FLAG_CHECK_QUERY: count per-row query indices outside [-1, Q) (-1 = "no query for this row", value 0)
+__global__ void check_query_idx_kernel(const int32_t* __restrict__ qidx, long long B, int32_t Q, int32_t* bad) {
+  int32_t mine = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (long long)gridDim.x * blockDim.x) {
+    const int32_t q = __ldg(qidx + i);
+    mine |= (q < -1 || q >= Q) ? 1 : 0;
+  }
+  if (__any_sync(0xffffffffu, mine) && (threadIdx.x & 31) == 0) atomicOr(bad, 1);
+}
+
+// Synchronises `st` (this is the one device entry-point option that is NOT CUDA-graph capturable).
+static int check_query_indices(const vael_circuit_t* c, const int32_t* qidx, int64_t B, cudaStream_t st) {
+  if (!qidx || B == 0) return VAEL_OK;
+  std::lock_guard<std::mutex> lock(c->check_mutex);   // one flag word per circuit
+  const int grid = (int)std::min<long long>((B + 255) / 256, (long long)c->num_sms * 8);
+  check_query_idx_kernel<<<grid, 256, 0, st>>>(qidx, B, c->n_queries, c->d_bad_query);
+  CK(cudaGetLastError());
+  g_launches++;
+  CK(cudaMemcpyAsync(c->h_bad_query, c->d_bad_query, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemsetAsync(c->d_bad_query, 0, sizeof(int32_t), st));
+  CK(cudaStreamSynchronize(st));
+  if (*c->h_bad_query) return fail(VAEL_E_INVALID, "per-row query index out of range (valid: -1 = none, 0..Q-1)");
+  return VAEL_OK;
+}
+
 static GenCall make_call(const vael_circuit_t* c, const float* facts, const int32_t* qidx, int32_t qs, int64_t B,
                          uint32_t flags) {
   GenCall G;
@@ -414,6 +445,8 @@ extern "C" int vael_circuit_forward(const vael_circuit_t* c, const float* facts,
   if (int rc = check_common(c, facts, qidx, qs, B, flags, needq)) return rc;
   if (B == 0) return VAEL_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((flags & VAEL_FLAG_CHECK_QUERY) && needq)
+    if (int rc = check_query_indices(c, qidx, B, st)) return rc;
   const int kern = pick_kernel(c, flags, worlds);
   if (kern == 2) {
     Ad2Params P{};
@@ -482,6 +515,8 @@ extern "C" int vael_circuit_backward(const vael_circuit_t* c, const float* facts
   if (B == 0) return VAEL_OK;
   if (!grad_facts) return fail(VAEL_E_INVALID, "null grad_facts");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((flags & VAEL_FLAG_CHECK_QUERY) && needq)
+    if (int rc = check_query_indices(c, qidx, B, st)) return rc;
   const int kern = pick_kernel(c, flags, grad_worlds);
   if (kern == 2) {
     Ad2Params P{};
@@ -514,37 +549,45 @@ extern "C" int vael_circuit_backward(const vael_circuit_t* c, const float* facts
 // buffers) so that the H2D copy of one chunk, the kernels of another and the D2H copy of a third overlap
 // and both PCIe directions stay busy
 // ---------------------------------------------------------------------------
-static int ensure_slots(vael_circuit_t* x) {
-  const vael_circuit_t* c = x;
-  if (x->chunk_rows) return VAEL_OK;
+// Caller holds host_mutex.  All-or-nothing: a failure frees what this call created.
+static int ensure_slots(const vael_circuit_t* c) {
+  if (c->chunk_rows) return VAEL_OK;
   const char* env = getenv("VAEL_HOST_CHUNK_ROWS");
   long long rows = env && *env ? atoll(env) : (1 << 17);
   if (rows < 32) rows = 32;
-  const size_t F = c->n_facts, W = c->n_worlds;
-  for (int s = 0; s < kHostSlots; ++s) {
-    auto& S = x->slot[s];
-    CK(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
-    CK(cudaMalloc(&S.facts, rows * F * 4)); CK(cudaMalloc(&S.gf, rows * F * 4));
-    CK(cudaMalloc(&S.worlds, rows * W * 4)); CK(cudaMalloc(&S.gw, rows * W * 4));
-    CK(cudaMalloc(&S.query, rows * 4)); CK(cudaMalloc(&S.gq, rows * 4)); CK(cudaMalloc(&S.qidx, rows * 4));
+  const size_t F = c->n_facts, W = c->n_worlds ? c->n_worlds : 1;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](auto** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(p), bytes); };
+  for (int s = 0; s < kHostSlots && e == cudaSuccess; ++s) {
+    auto& S = c->slot[s];
+    e = cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking);
+    alloc(&S.facts, rows * F * 4); alloc(&S.gf, rows * F * 4);
+    alloc(&S.worlds, rows * W * 4); alloc(&S.gw, rows * W * 4);
+    alloc(&S.query, rows * 4); alloc(&S.gq, rows * 4); alloc(&S.qidx, rows * 4);
   }
-  x->chunk_rows = rows;
+  if (e != cudaSuccess) {
+    for (auto& S : c->slot) {
+      cudaFree(S.facts); cudaFree(S.worlds); cudaFree(S.query); cudaFree(S.gw); cudaFree(S.gq); cudaFree(S.gf);
+      cudaFree(S.qidx);
+      if (S.stream) cudaStreamDestroy(S.stream);
+      S = vael_host_slot{};
+    }
+    return cuda_fail(e, "host pipeline allocation");
+  }
+  c->chunk_rows = rows;
   return VAEL_OK;
 }
 
-static int host_pipeline(const vael_circuit_t* c, const float* facts_h, const int32_t* qidx_h, int32_t qs, int64_t B,
-                         const float* gw_h, const float* gq_h, float* worlds_h, float* query_h, float* gf_h,
-                         uint32_t flags, bool backward) {
-  if (!c) return fail(VAEL_E_INVALID, "null circuit");
-  if (B < 0 || (B > 0 && !facts_h)) return fail(VAEL_E_INVALID, "bad host buffers");
-  if (backward && B > 0 && !gf_h) return fail(VAEL_E_INVALID, "null grad_facts host buffer");
-  vael_circuit_t* x = const_cast<vael_circuit_t*>(c);
-  if (int rc = ensure_slots(x)) return rc;
+// worlds_h / query_h / gf_h select what is computed and copied back; `backward` runs the adjoint with the
+// upstream gradients gw_h / gq_h (either may be null = 0; both null with `ones_gq` = d query / d facts).
+static int host_pipeline_locked(const vael_circuit_t* c, const float* facts_h, const int32_t* qidx_h, int32_t qs,
+                                int64_t B, const float* gw_h, const float* gq_h, float* worlds_h, float* query_h,
+                                float* gf_h, uint32_t flags, bool backward) {
   const size_t F = c->n_facts, W = c->n_worlds;
   int idx = 0;
-  for (int64_t r0 = 0; r0 < B; r0 += x->chunk_rows, ++idx) {
-    const int64_t n = (B - r0 < x->chunk_rows) ? (B - r0) : x->chunk_rows;
-    auto& S = x->slot[idx % kHostSlots];
+  for (int64_t r0 = 0; r0 < B; r0 += c->chunk_rows, ++idx) {
+    const int64_t n = (B - r0 < c->chunk_rows) ? (B - r0) : c->chunk_rows;
+    auto& S = c->slot[idx % kHostSlots];
     CK(cudaMemcpyAsync(S.facts, facts_h + r0 * F, n * F * 4, cudaMemcpyHostToDevice, S.stream));
     if (qidx_h) CK(cudaMemcpyAsync(S.qidx, qidx_h + r0, n * 4, cudaMemcpyHostToDevice, S.stream));
     if (worlds_h || query_h) {
@@ -558,12 +601,35 @@ static int host_pipeline(const vael_circuit_t* c, const float* facts_h, const in
       if (gw_h) CK(cudaMemcpyAsync(S.gw, gw_h + r0 * W, n * W * 4, cudaMemcpyHostToDevice, S.stream));
       if (gq_h) CK(cudaMemcpyAsync(S.gq, gq_h + r0, n * 4, cudaMemcpyHostToDevice, S.stream));
       if (int rc = vael_circuit_backward(c, S.facts, qidx_h ? S.qidx : nullptr, qs, n, gw_h ? S.gw : nullptr,
-                                         gq_h ? S.gq : nullptr, S.gf, flags, S.stream))
+                                         gq_h ? S.gq : nullptr, S.gf, flags & ~VAEL_FLAG_CHECK_QUERY, S.stream))
         return rc;
       CK(cudaMemcpyAsync(gf_h + r0 * F, S.gf, n * F * 4, cudaMemcpyDeviceToHost, S.stream));
     }
   }
-  for (int s = 0; s < kHostSlots; ++s) CK(cudaStreamSynchronize(x->slot[s].stream));
+  return VAEL_OK;
+}
+
+static int host_pipeline(const vael_circuit_t* c, const float* facts_h, const int32_t* qidx_h, int32_t qs, int64_t B,
+                         const float* gw_h, const float* gq_h, float* worlds_h, float* query_h, float* gf_h,
+                         uint32_t flags, bool backward) {
+  if (!c) return fail(VAEL_E_INVALID, "null circuit");
+  if (B < 0 || (B > 0 && !facts_h)) return fail(VAEL_E_INVALID, "bad host buffers");
+  if (backward && B > 0 && !gf_h) return fail(VAEL_E_INVALID, "null grad_facts host buffer");
+  int dev = -1;
+  CK(cudaGetDevice(&dev));
+  if (dev != c->device) return fail(VAEL_E_INVALID, "circuit was created on another CUDA device");
+  // the slot buffers and streams belong to the circuit handle: concurrent host callers of one handle take turns
+  std::lock_guard<std::mutex> lock(c->host_mutex);
+  if (int rc = ensure_slots(c)) return rc;
+  const int rc = host_pipeline_locked(c, facts_h, qidx_h, qs, B, gw_h, gq_h, worlds_h, query_h, gf_h, flags, backward);
+  // success or not, no copy may still be in flight when the caller gets its host buffers back
+  cudaError_t first = cudaSuccess;
+  for (int s = 0; s < kHostSlots; ++s) {
+    const cudaError_t e = cudaStreamSynchronize(c->slot[s].stream);
+    if (first == cudaSuccess) first = e;
+  }
+  if (rc) return rc;
+  if (first != cudaSuccess) return cuda_fail(first, "cudaStreamSynchronize");
   return VAEL_OK;
 }
 
@@ -576,6 +642,12 @@ extern "C" int vael_circuit_fwdbwd_host(const vael_circuit_t* c, const float* fa
                                         float* query_h, float* gf_h, uint32_t flags) {
   return host_pipeline(c, facts_h, qidx_h, qs, B, gw_h, gq_h, worlds_h, query_h, gf_h, flags, true);
 }
+extern "C" int vael_circuit_query_grad_host(const vael_circuit_t* c, const float* facts_h, const int32_t* qidx_h,
+                                            int32_t qs, int64_t B, const float* gq_h, float* query_h, float* gf_h,
+                                            uint32_t flags) {
+  if (B > 0 && (!gq_h || !query_h)) return fail(VAEL_E_INVALID, "null grad_query / query host buffer");
+  return host_pipeline(c, facts_h, qidx_h, qs, B, nullptr, gq_h, nullptr, query_h, gf_h, flags, true);
+}
 
 // ---------------------------------------------------------------------------
 // facts head, Gumbel sampling, ELBO terms
@@ -587,7 +659,7 @@ extern "C" int vael_facts_forward(const float* logits, int64_t B, int32_t n_grou
   if (!logits || !facts) return fail(VAEL_E_INVALID, "null pointer");
   int sms = 0;
   if (int rc = device_sms(&sms)) return rc;
-  CK(facts_forward(logits, B, n_groups, group, eps, facts, sms, static_cast<cudaStream_t>(stream)));
+  CK(facts_forward(logits, B, n_groups, group, eps, 0.0f, facts, sms, static_cast<cudaStream_t>(stream)));
   g_launches++;
   return VAEL_OK;
 }
@@ -598,7 +670,29 @@ extern "C" int vael_facts_backward(const float* logits, const float* grad_facts,
   if (!logits || !grad_facts || !grad_logits) return fail(VAEL_E_INVALID, "null pointer");
   int sms = 0;
   if (int rc = device_sms(&sms)) return rc;
-  CK(facts_backward(logits, grad_facts, B, n_groups, group, eps, grad_logits, sms, static_cast<cudaStream_t>(stream)));
+  CK(facts_backward(logits, grad_facts, B, n_groups, group, eps, 0.0f, grad_logits, sms, static_cast<cudaStream_t>(stream)));
+  g_launches++;
+  return VAEL_OK;
+}
+extern "C" int vael_facts_clip_forward(const float* logits, int64_t B, int32_t n_groups, int32_t group, float lo,
+                                       float hi, float* facts, void* stream) {
+  if (B < 0 || n_groups <= 0 || group <= 0 || !(hi > 0.0f) || !(lo <= hi)) return fail(VAEL_E_INVALID, "bad shape or clip range");
+  if (B == 0) return VAEL_OK;
+  if (!logits || !facts) return fail(VAEL_E_INVALID, "null pointer");
+  int sms = 0;
+  if (int rc = device_sms(&sms)) return rc;
+  CK(facts_forward(logits, B, n_groups, group, lo, hi, facts, sms, static_cast<cudaStream_t>(stream)));
+  g_launches++;
+  return VAEL_OK;
+}
+extern "C" int vael_facts_clip_backward(const float* logits, const float* grad_facts, int64_t B, int32_t n_groups,
+                                        int32_t group, float lo, float hi, float* grad_logits, void* stream) {
+  if (B < 0 || n_groups <= 0 || group <= 0 || !(hi > 0.0f) || !(lo <= hi)) return fail(VAEL_E_INVALID, "bad shape or clip range");
+  if (B == 0) return VAEL_OK;
+  if (!logits || !grad_facts || !grad_logits) return fail(VAEL_E_INVALID, "null pointer");
+  int sms = 0;
+  if (int rc = device_sms(&sms)) return rc;
+  CK(facts_backward(logits, grad_facts, B, n_groups, group, lo, hi, grad_logits, sms, static_cast<cudaStream_t>(stream)));
   g_launches++;
   return VAEL_OK;
 }
@@ -634,19 +728,75 @@ extern "C" int vael_gumbel_world_backward(const float* scores, const float* y_so
   return VAEL_OK;
 }
 
+// ---------------------------------------------------------------------------
+// fused training-mode logic path (logic_fused.cu)
+// ---------------------------------------------------------------------------
+static int fused_check(const vael_circuit_t* c, const float* logits, const int32_t* qidx, int32_t qs, int64_t B,
+                       float tau, bool need_query) {
+  if (!c) return fail(VAEL_E_INVALID, "null circuit");
+  if (B < 0) return fail(VAEL_E_INVALID, "negative batch size");
+  if (B > 0 && !logits) return fail(VAEL_E_INVALID, "null logits");
+  if (!(tau > 0.0f)) return fail(VAEL_E_INVALID, "tau must be positive");
+  int dev = -1;
+  CK(cudaGetDevice(&dev));
+  if (dev != c->device) return fail(VAEL_E_INVALID, "circuit was created on another CUDA device");
+  if (c->fast_kind != 2 || !fused_supported(c->ad_na, c->ad_nb) || !c->d_qmask)
+    return fail(VAEL_E_UNSUPPORTED, "the fused logic kernel covers two equal annotated disjunctions of 9 or 10 values");
+  if (need_query && !qidx && (qs < 0 || qs >= c->n_queries)) return fail(VAEL_E_INVALID, "query index out of range");
+  return VAEL_OK;
+}
+
+extern "C" int vael_logic_fused_supported(const vael_circuit_t* c) {
+  return c && c->fast_kind == 2 && fused_supported(c->ad_na, c->ad_nb) && c->d_qmask ? 1 : 0;
+}
+
+extern "C" int vael_logic_train_forward(const vael_circuit_t* c, const float* logits, const int32_t* qidx, int32_t qs,
+                                        int64_t B, float eps, float tau, const float* noise, uint64_t seed,
+                                        const uint64_t* seed_dev, float* facts, float* query, int32_t* world_idx,
+                                        float* world_h, float* y_soft, void* stream) {
+  if (int rc = fused_check(c, logits, qidx, qs, B, tau, query != nullptr)) return rc;
+  if (B == 0) return VAEL_OK;
+  FusedParams P{};
+  P.logits = logits; P.qidx = qidx; P.qscalar = query ? qs : -1; P.n_queries = c->n_queries; P.qmask = c->d_qmask;
+  P.B = B; P.eps = eps; P.tau = tau; P.noise = noise; P.seed = seed; P.seed_dev = seed_dev;
+  P.facts = facts; P.query = query; P.world_idx = world_idx; P.world_h = world_h; P.y_soft = y_soft;
+  CK(fused_forward(c->ad_na, P, c->num_sms, static_cast<cudaStream_t>(stream)));
+  g_last_kernel = "logic-fused";
+  g_launches++;
+  return VAEL_OK;
+}
+
+extern "C" int vael_logic_train_backward(const vael_circuit_t* c, const float* logits, const int32_t* qidx, int32_t qs,
+                                         int64_t B, float eps, float tau, const float* noise, uint64_t seed,
+                                         const uint64_t* seed_dev, const float* grad_world_h, const float* grad_query,
+                                         const float* grad_facts, float* grad_logits, void* stream) {
+  if (int rc = fused_check(c, logits, qidx, qs, B, tau, grad_query != nullptr)) return rc;
+  if (B == 0) return VAEL_OK;
+  if (!grad_logits) return fail(VAEL_E_INVALID, "null grad_logits");
+  FusedParams P{};
+  P.logits = logits; P.qidx = qidx; P.qscalar = grad_query ? qs : -1; P.n_queries = c->n_queries; P.qmask = c->d_qmask;
+  P.B = B; P.eps = eps; P.tau = tau; P.noise = noise; P.seed = seed; P.seed_dev = seed_dev;
+  P.grad_world_h = grad_world_h; P.grad_query = grad_query; P.grad_facts = grad_facts; P.grad_logits = grad_logits;
+  CK(fused_backward(c->ad_na, P, c->num_sms, static_cast<cudaStream_t>(stream)));
+  g_last_kernel = "logic-fused";
+  g_launches++;
+  return VAEL_OK;
+}
+
 extern "C" int64_t vael_elbo_workspace_bytes(void) { return (int64_t)elbo_workspace_bytes(); }
 
 extern "C" int vael_elbo_terms(const float* recon, const float* x, int64_t B, int64_t D, const float* mu,
                                const float* logvar, int32_t L, const float* query_prob, float recon_w, float kl_w,
-                               float query_w, float* terms, float* grad_recon, float* grad_mu, float* grad_logvar,
-                               float* grad_query, void* workspace, void* stream) {
+                               float query_w, int32_t rec_loss, float* terms, float* grad_recon, float* grad_mu,
+                               float* grad_logvar, float* grad_query, void* workspace, void* stream) {
   if (B <= 0 || D <= 0 || L < 0) return fail(VAEL_E_INVALID, "bad shape");
+  if (rec_loss < VAEL_REC_LAPLACE || rec_loss > VAEL_REC_BCE) return fail(VAEL_E_INVALID, "unknown rec_loss");
   if (!recon || !x || !terms || !workspace || (L > 0 && (!mu || !logvar))) return fail(VAEL_E_INVALID, "null pointer");
   int sms = 0;
   if (int rc = device_sms(&sms)) return rc;
   ElboParams P{};
   P.recon = recon; P.x = x; P.B = B; P.D = D; P.mu = mu; P.logvar = logvar; P.L = L; P.query_prob = query_prob;
-  P.recon_w = recon_w; P.kl_w = kl_w; P.query_w = query_w; P.terms = terms; P.grad_recon = grad_recon;
+  P.recon_w = recon_w; P.kl_w = kl_w; P.query_w = query_w; P.rec_loss = rec_loss; P.terms = terms; P.grad_recon = grad_recon;
   P.grad_mu = grad_mu; P.grad_logvar = grad_logvar; P.grad_query = grad_query;
   CK(elbo_terms(P, workspace, sms, static_cast<cudaStream_t>(stream)));
   g_launches++;

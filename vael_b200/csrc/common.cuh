@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "../../include/vael_b200.h"
 
 namespace vael {
@@ -125,7 +127,14 @@ struct vael_circuit {
   uint32_t lt_mask[64];      // fast_kind 4: per world, the fact columns that enter as positive literals
   bool queries_diagonal;     // fast_kind 2: query s = the worlds (j, k) with j + k = s (all-queries register kernel)
   uint32_t* d_qmask_c;       // fast_kind 3: [n_queries][np][ceil(na*nb/32)] chunked membership masks
-  // host-buffer pipeline (allocated lazily by the *_host entry points)
-  vael_host_slot slot[kHostSlots];
-  long long chunk_rows;
+  // VAEL_FLAG_CHECK_QUERY: device flag word + its pinned host mirror, one check at a time
+  int32_t* d_bad_query;
+  int32_t* h_bad_query;
+  mutable std::mutex check_mutex;
+  // host-buffer pipeline: the only mutable part of a circuit handle.  Allocated lazily by the *_host entry
+  // points under host_mutex, which also serialises concurrent host callers of one handle (they share the
+  // slot buffers and streams).
+  mutable std::mutex host_mutex;
+  mutable vael_host_slot slot[kHostSlots];
+  mutable long long chunk_rows;
 };

@@ -6,6 +6,9 @@
 //   kl    =  mean_b -0.5 sum_l (1 + logvar - mu^2 - exp(logvar))
 //   qbce  =  BCELoss(q, 1) = mean_b -max(log q, -100)
 //   loss  =  recon_w recon + kl_w kl + query_w qbce
+// rec_loss = 'MSE' / 'BCE' (train.py:16-21; the other two values of the reference's option): the reconstruction
+// term is the mean over ALL B*D elements of (recon - x)^2, resp. of -(x max(log r, -100) + (1-x) max(log(1-r), -100))
+// (torch BCELoss incl. its clamps; gradient (r - x) / max(r (1-r), 1e-12)).
 // HBM-bound: reads recon and x once (2*D floats per row) and writes grad_recon.
 // The reconstruction term is a sum over ALL pixels of the batch divided by B, so the kernel treats
 // recon / x / grad_recon as one flat stream: every CTA takes a contiguous span of it (128-bit loads, four in
@@ -18,19 +21,42 @@ namespace vael {
 
 __device__ __forceinline__ float sgn(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }
 
-__device__ __forceinline__ float abs_and_grad4(const float4 x, const float4 r, float gr, float4* g) {
-  const float d0 = r.x - x.x, d1 = r.y - x.y, d2 = r.z - x.z, d3 = r.w - x.w;
-  if (g) *g = make_float4(gr * sgn(d0), gr * sgn(d1), gr * sgn(d2), gr * sgn(d3));
-  return (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
+// one element of the reconstruction term: returns its contribution, writes d(term)/d(recon) * gr to *g
+template <int REC>
+__device__ __forceinline__ float rec_elem(float x, float r, float gr, float* g) {
+  if (REC == VAEL_REC_LAPLACE) {
+    const float d = r - x;
+    *g = gr * sgn(d);
+    return fabsf(d);
+  } else if (REC == VAEL_REC_MSE) {
+    const float d = r - x;
+    *g = gr * 2.0f * d;
+    return d * d;
+  } else {
+    *g = gr * (r - x) / fmaxf((1.0f - r) * r, 1e-12f);
+    return -(x * fmaxf(logf(r), -100.0f) + (1.0f - x) * fmaxf(logf(1.0f - r), -100.0f));
+  }
 }
 
+template <int REC>
+__device__ __forceinline__ float abs_and_grad4(const float4 x, const float4 r, float gr, float4* g) {
+  float4 o;
+  const float s = (rec_elem<REC>(x.x, r.x, gr, &o.x) + rec_elem<REC>(x.y, r.y, gr, &o.y)) +
+                  (rec_elem<REC>(x.z, r.z, gr, &o.z) + rec_elem<REC>(x.w, r.w, gr, &o.w));
+  if (g) *g = o;
+  return s;
+}
+
+template <int REC>
 __global__ void __launch_bounds__(256) elbo_terms_kernel(const ElboParams P) {
   __shared__ double red[3][8];
   __shared__ bool is_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float invB = 1.0f / (float)P.B;
-  const float gr = P.recon_w * invB, gk = P.kl_w * invB, gq = P.query_w * invB;
   const long long n = P.B * P.D;
+  // LAPLACE: sum over pixels, mean over the batch; MSE / BCE: mean over all elements
+  const float gr = REC == VAEL_REC_LAPLACE ? P.recon_w * invB : P.recon_w / (float)n;
+  const float gk = P.kl_w * invB, gq = P.query_w * invB;
   const bool vec = (n % 4 == 0) && aligned16(P.recon) && aligned16(P.x) &&
                    (P.grad_recon == nullptr || aligned16(P.grad_recon));
   const long long gtid = (long long)blockIdx.x * blockDim.x + tid, gsz = (long long)gridDim.x * blockDim.x;
@@ -50,14 +76,14 @@ __global__ void __launch_bounds__(256) elbo_terms_kernel(const ElboParams P) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) { a[u] = __ldg(x4 + i + u * 256); b[u] = __ldg(r4 + i + u * 256); }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) s_abs += abs_and_grad4(a[u], b[u], gr, g4 ? g4 + i + u * 256 : nullptr);
+      for (int u = 0; u < 4; ++u) s_abs += abs_and_grad4<REC>(a[u], b[u], gr, g4 ? g4 + i + u * 256 : nullptr);
     }
-    for (; i < end; i += 256) s_abs += abs_and_grad4(__ldg(x4 + i), __ldg(r4 + i), gr, g4 ? g4 + i : nullptr);
+    for (; i < end; i += 256) s_abs += abs_and_grad4<REC>(__ldg(x4 + i), __ldg(r4 + i), gr, g4 ? g4 + i : nullptr);
   } else {
     for (long long i = gtid; i < n; i += gsz) {
-      const float d = __ldg(P.recon + i) - __ldg(P.x + i);
-      s_abs += fabsf(d);
-      if (P.grad_recon) P.grad_recon[i] = gr * sgn(d);
+      float g;
+      s_abs += rec_elem<REC>(__ldg(P.x + i), __ldg(P.recon + i), gr, &g);
+      if (P.grad_recon) P.grad_recon[i] = g;
     }
   }
   // ---- KL over [B,L] ----
@@ -123,8 +149,9 @@ __global__ void __launch_bounds__(256) elbo_terms_kernel(const ElboParams P) {
     if (tid == 0) {
       r = k = q = 0.0;
       for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { r += red[0][w]; k += red[1][w]; q += red[2][w]; }
-      // recon = mean_b ( D log 2 + sum_pix |x - recon| )
-      const float recon = (float)((double)P.D * 0.69314718055994531 + r / (double)P.B);
+      // LAPLACE: recon = mean_b ( D log 2 + sum_pix |x - recon| ); MSE / BCE: mean over all B*D elements
+      const float recon = REC == VAEL_REC_LAPLACE ? (float)((double)P.D * 0.69314718055994531 + r / (double)P.B)
+                                                  : (float)(r / ((double)P.B * (double)P.D));
       const float kl = (float)(-0.5 * k / (double)P.B), qb = (float)(q / (double)P.B);
       P.terms[1] = recon;
       P.terms[2] = kl;
@@ -144,7 +171,9 @@ cudaError_t elbo_terms(ElboParams P, void* workspace, int num_sms, cudaStream_t 
   // enough CTAs to fill the chip, never more than one per 1024 float4s of the pixel stream
   const long long work = max(1LL, (P.B * P.D) / 4096);
   const int grid = (int)max(1LL, min(work, (long long)min(kElboMaxGrid, num_sms * 8)));
-  elbo_terms_kernel<<<grid, 256, 0, st>>>(P);
+  if (P.rec_loss == VAEL_REC_MSE) elbo_terms_kernel<VAEL_REC_MSE><<<grid, 256, 0, st>>>(P);
+  else if (P.rec_loss == VAEL_REC_BCE) elbo_terms_kernel<VAEL_REC_BCE><<<grid, 256, 0, st>>>(P);
+  else elbo_terms_kernel<VAEL_REC_LAPLACE><<<grid, 256, 0, st>>>(P);
   return cudaGetLastError();
 }
 

@@ -63,6 +63,7 @@ cudaError_t adw_queries_diag(int np, int na, int nb, const float* facts, long lo
 
 // ---- circuit_lt.cu (literal-table circuits in the log semiring: Mario's admissible worlds) ----
 bool lt_supported(int F, int W);
+bool lt_masks_fit(int F, int W, const uint32_t* masks);  // the per-world / per-column lists fit the kernel's tables
 cudaError_t lt_forward(int F, int W, const uint32_t* masks, const float* facts, long long B, float* worlds, int num_sms,
                        cudaStream_t st);
 cudaError_t lt_backward(int F, int W, const uint32_t* masks, const float* facts, const float* grad_worlds, long long B,
@@ -110,10 +111,39 @@ struct GumbelParams {
 };
 cudaError_t gumbel_forward(const GumbelParams& P, int num_sms, cudaStream_t st);
 cudaError_t gumbel_backward(const GumbelParams& P, int num_sms, cudaStream_t st);
-cudaError_t facts_forward(const float* logits, long long B, int n_groups, int group, float eps, float* facts,
+cudaError_t facts_forward(const float* logits, long long B, int n_groups, int group, float eps, float hi, float* facts,
                           int num_sms, cudaStream_t st);
 cudaError_t facts_backward(const float* logits, const float* grad_facts, long long B, int n_groups, int group,
-                           float eps, float* grad_logits, int num_sms, cudaStream_t st);
+                           float eps, float hi, float* grad_logits, int num_sms, cudaStream_t st);
+
+// ---- logic_fused.cu (training-mode logic path in one kernel per direction) ----
+struct FusedParams {
+  const float* logits;       // [B,2N]
+  const int32_t* qidx;       // [B] or null
+  int32_t qscalar;
+  int32_t n_queries;
+  const uint32_t* qmask;     // [Q][MW] world membership of every query node
+  long long B;
+  float eps, tau;
+  const float* noise;        // [B,W] Gumbel noise to add, or null -> Philox4x32-10 keyed by the seed
+  uint64_t seed;
+  const uint64_t* seed_dev;  // device word holding the seed (overrides `seed`): lets a CUDA graph draw a fresh
+                             // seed per replay with a captured generator op
+  // forward outputs (each may be null)
+  float* facts;              // [B,2N]
+  float* query;              // [B]
+  int32_t* world_idx;        // [B]
+  float* world_h;            // [B,2N]
+  float* y_soft;             // [B,W]  (tests)
+  // backward
+  const float* grad_world_h; // [B,2N] or null
+  const float* grad_query;   // [B] or null
+  const float* grad_facts;   // [B,2N] or null: upstream gradient of the `facts` output
+  float* grad_logits;        // [B,2N]
+};
+bool fused_supported(int na, int nb);
+cudaError_t fused_forward(int n, const FusedParams& P, int num_sms, cudaStream_t st);
+cudaError_t fused_backward(int n, const FusedParams& P, int num_sms, cudaStream_t st);
 
 // ---- elbo.cu ---------------------------------------------------------------
 struct ElboParams {
@@ -125,6 +155,7 @@ struct ElboParams {
   int32_t L;
   const float* query_prob;  // [B] or null
   float recon_w, kl_w, query_w;
+  int32_t rec_loss;  // VAEL_REC_*
   float* terms;  // [4] {loss, recon, kl, qbce}
   float* grad_recon;
   float* grad_mu;

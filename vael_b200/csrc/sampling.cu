@@ -8,30 +8,9 @@
 // max / argmax / sum reductions are warp shuffles; nothing is staged in shared
 // memory except the small 0/1 Herbrand table.
 #include "params.cuh"
+#include "sampling.cuh"
 
 namespace vael {
-
-// ---- Philox4x32-10 (Salmon et al. 2011), counter = (row, world), key = seed -------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
-}
-// Gumbel(0,1) = -log(E), E ~ Exp(1) = -log(U), U in (0,1]  (torch: -empty.exponential_().log())
-__device__ __forceinline__ float gumbel_from_bits(uint32_t bits) {
-  // the noise only has to be Gumbel-distributed, not bit-reproducible against a CPU libm: fast logarithms
-  const float u = (static_cast<float>(bits >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0,1]
-  const float e = fmaxf(-__logf(u), 1.17549435e-38f);
-  return -__logf(e);
-}
-
 
 template <int ITEMS>
 __global__ void __launch_bounds__(256) gumbel_forward_kernel(const GumbelParams P) {
@@ -234,27 +213,13 @@ cudaError_t gumbel_backward(const GumbelParams& P, int num_sms, cudaStream_t st)
 // HBM-bound: 2 * NG*N*4 bytes per row forward, 3 * NG*N*4 backward (logits re-read, softmax recomputed).
 // Any other shape takes the generic one-thread-per-(row, group) kernels below.
 // ---------------------------------------------------------------------------
-template <int NG, int N>
-__device__ __forceinline__ void facts_row(const float* x, float eps, float* y, float* zs) {
-#pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    float mx = x[g * N];
-#pragma unroll
-    for (int i = 1; i < N; ++i) mx = fmaxf(mx, x[g * N + i]);
-    float e[N], s = 0.0f;
-#pragma unroll
-    for (int i = 0; i < N; ++i) { e[i] = expf(x[g * N + i] - mx); s += e[i]; }
-    float zsum = 0.0f;
-#pragma unroll
-    for (int i = 0; i < N; ++i) { y[g * N + i] = e[i] / s; zsum += y[g * N + i] + eps; }
-    zs[g] = zsum;
-  }
-}
-
-template <int NG, int N, bool BWD>
+// CLIP: out = clamp(softmax, eps, hi) instead of (softmax + eps) / sum — MarioVAELModel's facts
+// (models/vael.py:319-322: Softmax then torch.clip(min=1e-5, max=0.9999)); its gradient passes where
+// eps <= softmax <= hi (torch.clip's rule) and is zero elsewhere.
+template <int NG, int N, bool BWD, bool CLIP>
 __global__ void __launch_bounds__(256) facts_tile_kernel(const float* __restrict__ logits,
                                                          const float* __restrict__ grad_facts, long long B,
-                                                         float eps, float* __restrict__ out) {
+                                                         float eps, float hi, float* __restrict__ out) {
   constexpr int F = NG * N;
   constexpr int PITCH = F | 1;  // odd pitch: lane <-> row accesses of the staged tile are conflict-free
   extern __shared__ float tile_s[];
@@ -297,7 +262,20 @@ __global__ void __launch_bounds__(256) facts_tile_kernel(const float* __restrict
     facts_row<NG, N>(x, eps, y, zs);
     if (!BWD) {
 #pragma unroll
-      for (int c = 0; c < F; ++c) xs[lane * PITCH + c] = (y[c] + eps) / zs[c / N];
+      for (int c = 0; c < F; ++c) xs[lane * PITCH + c] = CLIP ? fminf(fmaxf(y[c], eps), hi) : (y[c] + eps) / zs[c / N];
+    } else if (CLIP) {
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        float dy[N], dot = 0.0f;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const float yi = y[g * N + i];
+          dy[i] = (yi >= eps && yi <= hi) ? gs[lane * PITCH + g * N + i] : 0.0f;
+          dot = fmaf(yi, dy[i], dot);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) xs[lane * PITCH + g * N + i] = y[g * N + i] * (dy[i] - dot);
+      }
     } else {
       // f = (y + eps) / Z with Z detached  ->  dL/dy_i = gf_i / Z ; softmax: dx_i = y_i (dy_i - sum_j y_j dy_j)
 #pragma unroll
@@ -317,35 +295,40 @@ __global__ void __launch_bounds__(256) facts_tile_kernel(const float* __restrict
   }
 }
 
-template <int NG, int N, bool BWD>
-static cudaError_t launch_facts_tile(const float* logits, const float* gf, long long B, float eps, float* out, int num_sms,
-                                     cudaStream_t st) {
+template <int NG, int N, bool BWD, bool CLIP>
+static cudaError_t launch_facts_tile(const float* logits, const float* gf, long long B, float eps, float hi, float* out,
+                                     int num_sms, cudaStream_t st) {
   constexpr int PITCH = (NG * N) | 1;
   const int nw = 8;
   const size_t smem = (size_t)nw * (BWD ? 2 : 1) * kWarp * PITCH * sizeof(float);
   const long long n_sub = (B + kWarp - 1) / kWarp;
   const int grid = (int)max(1LL, min((n_sub + nw - 1) / nw, (long long)num_sms * 4));
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(facts_tile_kernel<NG, N, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(facts_tile_kernel<NG, N, BWD, CLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  facts_tile_kernel<NG, N, BWD><<<grid, nw * 32, smem, st>>>(logits, gf, B, eps, out);
+  facts_tile_kernel<NG, N, BWD, CLIP><<<grid, nw * 32, smem, st>>>(logits, gf, B, eps, hi, out);
   return cudaGetLastError();
 }
 
 template <bool BWD>
 static bool facts_tile_dispatch(const float* logits, const float* gf, long long B, int n_groups, int group, float eps,
-                                float* out, int num_sms, cudaStream_t st, cudaError_t* err) {
-  if (n_groups == 2 && group == 10) { *err = launch_facts_tile<2, 10, BWD>(logits, gf, B, eps, out, num_sms, st); return true; }
-  if (n_groups == 3 && group == 10) { *err = launch_facts_tile<3, 10, BWD>(logits, gf, B, eps, out, num_sms, st); return true; }
-  if (n_groups == 2 && group == 9) { *err = launch_facts_tile<2, 9, BWD>(logits, gf, B, eps, out, num_sms, st); return true; }
-  if (n_groups == 1 && group == 9) { *err = launch_facts_tile<1, 9, BWD>(logits, gf, B, eps, out, num_sms, st); return true; }
+                                float hi, float* out, int num_sms, cudaStream_t st, cudaError_t* err) {
+  if (hi > 0.0f) {  // clip mode: the Mario shapes
+    if (n_groups == 2 && group == 9) { *err = launch_facts_tile<2, 9, BWD, true>(logits, gf, B, eps, hi, out, num_sms, st); return true; }
+    if (n_groups == 1 && group == 9) { *err = launch_facts_tile<1, 9, BWD, true>(logits, gf, B, eps, hi, out, num_sms, st); return true; }
+    return false;
+  }
+  if (n_groups == 2 && group == 10) { *err = launch_facts_tile<2, 10, BWD, false>(logits, gf, B, eps, hi, out, num_sms, st); return true; }
+  if (n_groups == 3 && group == 10) { *err = launch_facts_tile<3, 10, BWD, false>(logits, gf, B, eps, hi, out, num_sms, st); return true; }
+  if (n_groups == 2 && group == 9) { *err = launch_facts_tile<2, 9, BWD, false>(logits, gf, B, eps, hi, out, num_sms, st); return true; }
+  if (n_groups == 1 && group == 9) { *err = launch_facts_tile<1, 9, BWD, false>(logits, gf, B, eps, hi, out, num_sms, st); return true; }
   return false;
 }
 
 // generic shapes: one thread per (row, group); a group is `group` contiguous floats
 __global__ void __launch_bounds__(256) facts_forward_kernel(const float* __restrict__ logits, long long n_groups_total,
-                                                            int group, float eps, float* __restrict__ facts) {
+                                                            int group, float eps, float hi, float* __restrict__ facts) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < n_groups_total; gi += stride) {
     const float* x = logits + gi * group;
@@ -354,6 +337,10 @@ __global__ void __launch_bounds__(256) facts_forward_kernel(const float* __restr
     for (int i = 0; i < group; ++i) mx = fmaxf(mx, __ldg(x + i));
     float s = 0.0f;
     for (int i = 0; i < group; ++i) s += expf(__ldg(x + i) - mx);
+    if (hi > 0.0f) {  // clip mode
+      for (int i = 0; i < group; ++i) y[i] = fminf(fmaxf(expf(__ldg(x + i) - mx) / s, eps), hi);
+      continue;
+    }
     float zsum = 0.0f;
     for (int i = 0; i < group; ++i) {
       const float v = expf(__ldg(x + i) - mx) / s + eps;
@@ -367,7 +354,7 @@ __global__ void __launch_bounds__(256) facts_forward_kernel(const float* __restr
 __global__ void __launch_bounds__(256) facts_backward_kernel(const float* __restrict__ logits,
                                                              const float* __restrict__ grad_facts,
                                                              long long n_groups_total, int group, float eps,
-                                                             float* __restrict__ grad_logits) {
+                                                             float hi, float* __restrict__ grad_logits) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < n_groups_total; gi += stride) {
     const float* x = logits + gi * group;
@@ -377,6 +364,18 @@ __global__ void __launch_bounds__(256) facts_backward_kernel(const float* __rest
     for (int i = 0; i < group; ++i) mx = fmaxf(mx, __ldg(x + i));
     float s = 0.0f;
     for (int i = 0; i < group; ++i) s += expf(__ldg(x + i) - mx);
+    if (hi > 0.0f) {  // clip mode: dy_i = gf_i where eps <= y_i <= hi, else 0
+      float dotc = 0.0f;
+      for (int i = 0; i < group; ++i) {
+        const float yi = expf(__ldg(x + i) - mx) / s;
+        dotc = fmaf(yi, (yi >= eps && yi <= hi) ? __ldg(gf + i) : 0.0f, dotc);
+      }
+      for (int i = 0; i < group; ++i) {
+        const float yi = expf(__ldg(x + i) - mx) / s;
+        gx[i] = yi * (((yi >= eps && yi <= hi) ? __ldg(gf + i) : 0.0f) - dotc);
+      }
+      continue;
+    }
     float zsum = 0.0f;
     for (int i = 0; i < group; ++i) zsum += expf(__ldg(x + i) - mx) / s + eps;
     // f = (y + eps) / Z with Z detached  ->  dL/dy_i = gf_i / Z ; softmax: dx_i = y_i (dy_i - sum_j y_j dy_j)
@@ -389,22 +388,23 @@ __global__ void __launch_bounds__(256) facts_backward_kernel(const float* __rest
   }
 }
 
-cudaError_t facts_forward(const float* logits, long long B, int n_groups, int group, float eps, float* facts,
+// hi <= 0: (softmax + eps) / sum (MNIST); hi > 0: clamp(softmax, eps, hi) (Mario)
+cudaError_t facts_forward(const float* logits, long long B, int n_groups, int group, float eps, float hi, float* facts,
                           int num_sms, cudaStream_t st) {
   cudaError_t e;
-  if (facts_tile_dispatch<false>(logits, nullptr, B, n_groups, group, eps, facts, num_sms, st, &e)) return e;
+  if (facts_tile_dispatch<false>(logits, nullptr, B, n_groups, group, eps, hi, facts, num_sms, st, &e)) return e;
   const long long total = B * n_groups;
   const int grid = (int)max(1LL, min((total + 255) / 256, (long long)num_sms * 8));
-  facts_forward_kernel<<<grid, 256, 0, st>>>(logits, total, group, eps, facts);
+  facts_forward_kernel<<<grid, 256, 0, st>>>(logits, total, group, eps, hi, facts);
   return cudaGetLastError();
 }
 cudaError_t facts_backward(const float* logits, const float* grad_facts, long long B, int n_groups, int group,
-                           float eps, float* grad_logits, int num_sms, cudaStream_t st) {
+                           float eps, float hi, float* grad_logits, int num_sms, cudaStream_t st) {
   cudaError_t e;
-  if (facts_tile_dispatch<true>(logits, grad_facts, B, n_groups, group, eps, grad_logits, num_sms, st, &e)) return e;
+  if (facts_tile_dispatch<true>(logits, grad_facts, B, n_groups, group, eps, hi, grad_logits, num_sms, st, &e)) return e;
   const long long total = B * n_groups;
   const int grid = (int)max(1LL, min((total + 255) / 256, (long long)num_sms * 8));
-  facts_backward_kernel<<<grid, 256, 0, st>>>(logits, grad_facts, total, group, eps, grad_logits);
+  facts_backward_kernel<<<grid, 256, 0, st>>>(logits, grad_facts, total, group, eps, hi, grad_logits);
   return cudaGetLastError();
 }
 

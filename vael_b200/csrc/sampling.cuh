@@ -1,0 +1,53 @@
+// Device helpers shared by sampling.cu (the stand-alone facts-head / Gumbel kernels) and logic_fused.cu (the
+// fused training-mode logic kernel): the counter-based generator, the Gumbel transform and the facts-head row.
+#pragma once
+#include "common.cuh"
+
+namespace vael {
+
+// ---- Philox4x32-10 (Salmon et al. 2011), counter = (row, world), key = seed -------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+// Gumbel(0,1) = -log(E), E ~ Exp(1) = -log(U)  (torch: -empty.exponential_().log())
+// U = (k + 1/2) 2^-23 with k the top 23 random bits: exact in fp32 and strictly inside (0,1), so E > 0 without a
+// clamp.  The noise only has to be Gumbel-distributed, not bit-reproducible against a CPU libm, so the logarithms are
+// the fast ones — except where the fast one is not good enough: for U -> 1, E = -log U -> 0 and __logf's ABSOLUTE
+// error (2^-21.4 on [0.5, 2]) would be a large relative error of E, i.e. a wrong, possibly huge Gumbel value for
+// about one sample in 1e3 .. 1e7.  There E comes from the series of -log(1 - v), v = 1 - U exact (Sterbenz).
+__device__ __forceinline__ float gumbel_from_bits(uint32_t bits) {
+  const float u = (static_cast<float>(bits >> 9) + 0.5f) * (1.0f / 8388608.0f);
+  const float v = 1.0f - u;
+  const float e_series = v * fmaf(v, fmaf(v, 0.33333334f, 0.5f), 1.0f);   // v + v^2/2 + v^3/3, |rel err| < v^3/4
+  const float e = (v < 1.0f / 1024.0f) ? e_series : -__logf(u);
+  return -__logf(e);
+}
+
+
+template <int NG, int N>
+__device__ __forceinline__ void facts_row(const float* x, float eps, float* y, float* zs) {
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    float mx = x[g * N];
+#pragma unroll
+    for (int i = 1; i < N; ++i) mx = fmaxf(mx, x[g * N + i]);
+    float e[N], s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { e[i] = expf(x[g * N + i] - mx); s += e[i]; }
+    float zsum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { y[g * N + i] = e[i] / s; zsum += y[g * N + i] + eps; }
+    zs[g] = zsum;
+  }
+}
+
+}  // namespace vael

@@ -13,7 +13,7 @@ from typing import List, Tuple
 
 import numpy as np
 
-from .circuit import SEMIRING_LOG, SEMIRING_PROB, Circuit
+from .circuit import SEMIRING_LOG, SEMIRING_PROB, Circuit, CircuitBuilder
 from .compiler import CompiledFamily, circuit_from_world_table, compile_family
 
 MOVES = ("up", "down", "right", "left")          # label column order, utils/mario_utils/problog_model.py:53-56
@@ -79,3 +79,21 @@ def mario_tables(fam: CompiledFamily):
 def admissible_circuit(W_adm: np.ndarray) -> Circuit:
     """Log-semiring circuit of admissible_worlds_logprob (models/vael.py:368-375)."""
     return circuit_from_world_table(W_adm, semiring=SEMIRING_LOG, with_negatives=True)
+
+
+def admissible_evidence_circuit(W_adm: np.ndarray, WQ_adm: np.ndarray) -> Circuit:
+    """Probability-semiring circuit over the ADMISSIBLE worlds only: world w = product of its positive literals
+    (`exp(log p @ W_adm^T)`, models/vael.py:421-423), one query node per move = sum of the admissible worlds where
+    that move holds (WQ_adm column).  Evaluated with VAEL_FLAG_EVIDENCE it yields P(w | move) over the 24 worlds:
+    MarioVAELModel.compute_conditioned_worlds_prob / compute_query_prob_cond (models/vael.py:401-430)."""
+    W_adm, WQ_adm = np.asarray(W_adm), np.asarray(WQ_adm)
+    W, F = W_adm.shape
+    b = CircuitBuilder(F, SEMIRING_PROB)
+    pos = [b.leaf(f, True) for f in range(F)]
+    worlds = [b.prod(tuple(pos[f] for f in range(F) if W_adm[w, f] != 0)) for w in range(W)]
+    queries = []
+    for m in range(WQ_adm.shape[1]):
+        ws = [worlds[w] for w in range(W) if WQ_adm[w, m] != 0]
+        queries.append(b.sum(tuple(ws)) if len(ws) > 1 else (ws[0] if ws else b.const(0.0)))
+    return b.finish(worlds, queries, -1, fact_labels=fact_labels(), world_atoms=[f"adm{w}" for w in range(W)],
+                    query_atoms=[f"action({m})" for m in MOVES[:WQ_adm.shape[1]]])

@@ -12,7 +12,7 @@ from typing import Optional, Tuple, Union
 import torch
 
 from . import _lib
-from .circuit import FLAG_EVIDENCE, FLAG_FORCE_GENERIC, FLAG_NORMALIZE, Circuit
+from .circuit import FLAG_CHECK_QUERY, FLAG_EVIDENCE, FLAG_FORCE_GENERIC, FLAG_NORMALIZE, Circuit
 
 
 def _stream_ptr() -> C.c_void_p:
@@ -118,20 +118,22 @@ class _CircuitFunction(torch.autograd.Function):
         gf = torch.empty_like(f2)
         with torch.cuda.device(f2.device):
             _lib.check(dc.lib.vael_circuit_backward(dc.handle, _p(f2), _p(qidx), ctx.qscalar, B, _p(gw), _p(gq),
-                                                    _p(gf), ctx.flags & ~FLAG_EVIDENCE, _stream_ptr()))
+                                                    _p(gf), ctx.flags & ~(FLAG_EVIDENCE | FLAG_CHECK_QUERY), _stream_ptr()))
         return gf.reshape(ctx.shape), None, None, None, None, None, None
 
 
 def circuit_forward(dc: DeviceCircuit, facts: torch.Tensor, query=None, *, normalize: bool = False,
-                    evidence: bool = False, force_generic: bool = False, want_worlds: bool = True
-                    ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+                    evidence: bool = False, force_generic: bool = False, want_worlds: bool = True,
+                    check_query: bool = False) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """worlds [B,W], query [B,1] of the compiled program for the facts [B,F] (or [B,k,n]).
     `query`: None, an int (one query for the batch, the reference's behaviour,
-    models/vael.py:212-213) or an integer tensor [B] (one per row)."""
+    models/vael.py:212-213) or an integer tensor [B] (one per row; -1 = no query for that row, value 0).
+    `check_query`: validate a per-row index tensor on the device first and raise on an out-of-range entry
+    (synchronises the stream: not for CUDA-graph capture); unchecked, such a row's query is 0."""
     B = facts.shape[0]
     qidx, qs = _query_args(dc, query, B)
     flags = (FLAG_NORMALIZE if normalize else 0) | (FLAG_EVIDENCE if evidence else 0) | \
-            (FLAG_FORCE_GENERIC if force_generic else 0)
+            (FLAG_FORCE_GENERIC if force_generic else 0) | (FLAG_CHECK_QUERY if check_query else 0)
     if evidence and query is None:
         raise RuntimeError("vael_b200: evidence mode needs the evidence (query) index")
     want_query = query is not None
@@ -157,16 +159,19 @@ def circuit_queries_all(dc: DeviceCircuit, facts: torch.Tensor, *, normalize: bo
 # ---------------------------------------------------------------------------
 class _FactsFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, n_groups: int, eps: float):
+    def forward(ctx, logits, n_groups: int, eps: float, clip_hi: float):
         x = _require_cuda_f32(logits, "logits")
         B = x.shape[0]
         group = x.shape[1] // n_groups
         out = torch.empty_like(x)
         lib = _lib.load()
         with torch.cuda.device(x.device):
-            _lib.check(lib.vael_facts_forward(_p(x), B, n_groups, group, eps, _p(out), _stream_ptr()))
+            if clip_hi > 0.0:
+                _lib.check(lib.vael_facts_clip_forward(_p(x), B, n_groups, group, eps, clip_hi, _p(out), _stream_ptr()))
+            else:
+                _lib.check(lib.vael_facts_forward(_p(x), B, n_groups, group, eps, _p(out), _stream_ptr()))
         ctx.save_for_backward(x)
-        ctx.n_groups, ctx.group, ctx.eps = n_groups, group, eps
+        ctx.n_groups, ctx.group, ctx.eps, ctx.clip_hi = n_groups, group, eps, clip_hi
         return out
 
     @staticmethod
@@ -176,9 +181,13 @@ class _FactsFunction(torch.autograd.Function):
         gx = torch.empty_like(x)
         lib = _lib.load()
         with torch.cuda.device(x.device):
-            _lib.check(lib.vael_facts_backward(_p(x), _p(g), x.shape[0], ctx.n_groups, ctx.group, ctx.eps, _p(gx),
-                                               _stream_ptr()))
-        return gx, None, None
+            if ctx.clip_hi > 0.0:
+                _lib.check(lib.vael_facts_clip_backward(_p(x), _p(g), x.shape[0], ctx.n_groups, ctx.group, ctx.eps,
+                                                        ctx.clip_hi, _p(gx), _stream_ptr()))
+            else:
+                _lib.check(lib.vael_facts_backward(_p(x), _p(g), x.shape[0], ctx.n_groups, ctx.group, ctx.eps, _p(gx),
+                                                   _stream_ptr()))
+        return gx, None, None, None
 
 
 def facts_from_logits(logits: torch.Tensor, n_groups: int, eps: float = 1e-5) -> torch.Tensor:
@@ -186,7 +195,17 @@ def facts_from_logits(logits: torch.Tensor, n_groups: int, eps: float = 1e-5) ->
     (MNISTPairsVAELModel.compute_facts_probability, models/vael.py:159-177)."""
     if logits.shape[1] % n_groups:
         raise RuntimeError("vael_b200: logits width is not a multiple of n_groups")
-    return _FactsFunction.apply(logits, n_groups, float(eps))
+    return _FactsFunction.apply(logits, n_groups, float(eps), 0.0)
+
+
+def facts_from_logits_clipped(logits: torch.Tensor, n_groups: int, lo: float = 1e-5, hi: float = 0.9999) -> torch.Tensor:
+    """[B, n_groups*n] logits -> per group softmax, clamped to [lo, hi]
+    (MarioVAELModel.forward, models/vael.py:319-322: Softmax + torch.clip)."""
+    if logits.shape[1] % n_groups:
+        raise RuntimeError("vael_b200: logits width is not a multiple of n_groups")
+    if not (0.0 <= lo <= hi and hi > 0.0):
+        raise RuntimeError("vael_b200: bad clip range")
+    return _FactsFunction.apply(logits, n_groups, float(lo), float(hi))
 
 
 # ---------------------------------------------------------------------------
@@ -236,20 +255,87 @@ def gumbel_world(scores: torch.Tensor, herbrand: torch.Tensor, *, tau: float = 1
 
 
 # ---------------------------------------------------------------------------
-_elbo_ws = {}
+class _FusedLogicFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, dc: DeviceCircuit, qidx, qscalar: int, eps: float, tau: float, noise, seed: int, seed_dev,
+                want_y_soft: bool):
+        x = _require_cuda_f32(logits, "logits")
+        B, F = x.shape
+        if F != dc.n_facts:
+            raise RuntimeError(f"vael_b200: logits has {F} columns, the circuit has {dc.n_facts} facts")
+        W = dc.n_worlds
+        nz = _require_cuda_f32(noise, "noise") if noise is not None else None
+        if nz is not None and tuple(nz.shape) != (B, W):
+            raise RuntimeError("vael_b200: injected Gumbel noise must be [B, n_worlds]")
+        facts = torch.empty_like(x)
+        query = torch.empty((B, 1), device=x.device, dtype=torch.float32)
+        idx = torch.empty((B,), device=x.device, dtype=torch.int32)
+        world_h = torch.empty_like(x)
+        y_soft = torch.empty((B, W), device=x.device, dtype=torch.float32) if want_y_soft else None
+        has_q = qidx is not None or qscalar >= 0
+        with torch.cuda.device(x.device):
+            _lib.check(dc.lib.vael_logic_train_forward(dc.handle, _p(x), _p(qidx), qscalar, B, eps, tau, _p(nz), seed,
+                                                       _p(seed_dev), _p(facts), _p(query) if has_q else None, _p(idx),
+                                                       _p(world_h), _p(y_soft), _stream_ptr()))
+        if not has_q:
+            query.zero_()
+        ctx.dc, ctx.qscalar, ctx.eps, ctx.tau, ctx.seed, ctx.has_q = dc, qscalar, eps, tau, seed, has_q
+        ctx.save_for_backward(x, qidx, nz, seed_dev)
+        ctx.mark_non_differentiable(idx)
+        if y_soft is None:
+            y_soft = x.new_empty(0)
+        ctx.mark_non_differentiable(y_soft)
+        return facts, query, world_h, idx, y_soft
+
+    @staticmethod
+    def backward(ctx, g_facts, g_query, g_world_h, _gi, _gy):
+        x, qidx, nz, seed_dev = ctx.saved_tensors
+        dc = ctx.dc
+
+        def c(g):
+            return g.contiguous().float() if g is not None else None
+
+        gf, gq, gh = c(g_facts), c(g_query), c(g_world_h)
+        gq = gq.reshape(-1) if (gq is not None and ctx.has_q) else None
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(dc.lib.vael_logic_train_backward(dc.handle, _p(x), _p(qidx), ctx.qscalar, x.shape[0], ctx.eps,
+                                                        ctx.tau, _p(nz), ctx.seed, _p(seed_dev), _p(gh), _p(gq), _p(gf),
+                                                        _p(gx), _stream_ptr()))
+        return gx, None, None, None, None, None, None, None, None, None
 
 
-def _elbo_workspace(device: torch.device) -> torch.Tensor:
-    key = (device.type, device.index)
-    if key not in _elbo_ws:
-        n = int(_lib.load().vael_elbo_workspace_bytes())
-        _elbo_ws[key] = torch.zeros(n, dtype=torch.uint8, device=device)
-    return _elbo_ws[key]
+def fused_logic_supported(dc: DeviceCircuit) -> bool:
+    return bool(dc.lib.vael_logic_fused_supported(dc.handle))
+
+
+def logic_train(dc: DeviceCircuit, logits: torch.Tensor, query=None, *, eps: float = 1e-5, tau: float = 1.0,
+                noise: Optional[torch.Tensor] = None, seed: Optional[int] = None,
+                seed_dev: Optional[torch.Tensor] = None, want_y_soft: bool = False):
+    """The whole training-mode logic path of VAELModel.forward (models/vael.py:55-65) in one kernel, its adjoint
+    in another: MLP logits [B,2N] -> (facts [B,2N], query [B,1], world_h [B,2N], world_idx [B] int32, y_soft [B,W]
+    or empty).  `query` as in circuit_forward.  Gumbel noise: `noise` [B,W] injected (tests), else drawn in the
+    kernel from Philox keyed by `seed` (host int; default: one draw from torch's CPU generator) or by `seed_dev`
+    (a one-element int64 CUDA tensor — inside a CUDA graph fill it with a captured torch.randint so that every
+    replay gets a new seed).  The adjoint re-draws the same noise; nothing [B,W]-shaped is kept."""
+    B = logits.shape[0]
+    qidx, qs = _query_args(dc, query, B)
+    if seed_dev is not None:
+        if not (seed_dev.is_cuda and seed_dev.dtype == torch.int64 and seed_dev.numel() == 1):
+            raise RuntimeError("vael_b200: seed_dev must be a one-element int64 CUDA tensor")
+    elif noise is None and seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return _FusedLogicFunction.apply(logits, dc, qidx, qs, float(eps), float(tau), noise, int(seed or 0), seed_dev,
+                                     bool(want_y_soft))
+
+
+# ---------------------------------------------------------------------------
+REC_LOSS = {"LAPLACE": 0, "MSE": 1, "BCE": 2}
 
 
 class _ElboFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, recon, x, mu, logvar, query_prob, recon_w, kl_w, query_w):
+    def forward(ctx, recon, x, mu, logvar, query_prob, recon_w, kl_w, query_w, rec_loss):
         r = _require_cuda_f32(recon, "recon")
         xx = _require_cuda_f32(x, "x")
         m = _require_cuda_f32(mu, "mu")
@@ -259,14 +345,18 @@ class _ElboFunction(torch.autograd.Function):
         D = r.numel() // B
         if xx.numel() != r.numel():
             raise RuntimeError("vael_b200: recon and x differ in size")
+        lib = _lib.load()
         terms = torch.empty(4, device=r.device, dtype=torch.float32)
         g_r, g_m, g_lv = torch.empty_like(r), torch.empty_like(m), torch.empty_like(lv)
         g_q = torch.empty_like(q) if q is not None else None
-        lib = _lib.load()
+        # the arrival counter + per-CTA partials belong to ONE call in flight: a workspace per call (49 KB from the
+        # caching allocator, zeroed on this stream), so calls on different streams / models / graph replays
+        # overlapping eager work never share one
+        ws = torch.zeros(int(lib.vael_elbo_workspace_bytes()), dtype=torch.uint8, device=r.device)
         with torch.cuda.device(r.device):
             _lib.check(lib.vael_elbo_terms(_p(r), _p(xx), B, D, _p(m), _p(lv), m.shape[1], _p(q), recon_w, kl_w,
-                                           query_w, _p(terms), _p(g_r), _p(g_m), _p(g_lv), _p(g_q),
-                                           _p(_elbo_workspace(r.device)), _stream_ptr()))
+                                           query_w, rec_loss, _p(terms), _p(g_r), _p(g_m), _p(g_lv), _p(g_q),
+                                           _p(ws), _stream_ptr()))
         ctx.save_for_backward(g_r, g_m, g_lv, g_q if g_q is not None else terms.new_empty(0))
         ctx.has_q = q is not None
         ctx.q_shape = query_prob.shape if query_prob is not None else None
@@ -278,10 +368,14 @@ class _ElboFunction(torch.autograd.Function):
     def backward(ctx, g_loss, _g_terms):
         g_r, g_m, g_lv, g_q = ctx.saved_tensors
         gq = (g_q * g_loss).reshape(ctx.q_shape) if ctx.has_q else None
-        return g_r * g_loss, None, g_m * g_loss, g_lv * g_loss, gq, None, None, None
+        return g_r * g_loss, None, g_m * g_loss, g_lv * g_loss, gq, None, None, None, None
 
 
-def elbo_terms(recon, x, mu, logvar, query_prob=None, recon_w: float = 1.0, kl_w: float = 1.0, query_w: float = 1.0):
-    """(loss, terms[4] = {loss, recon, kl, qbce}) of loss_function(rec_loss='LAPLACE')
-    (utils/mnist_utils/train.py:13-55); the gradients are produced by the same kernel pass."""
-    return _ElboFunction.apply(recon, x, mu, logvar, query_prob, float(recon_w), float(kl_w), float(query_w))
+def elbo_terms(recon, x, mu, logvar, query_prob=None, recon_w: float = 1.0, kl_w: float = 1.0, query_w: float = 1.0,
+               rec_loss: str = "LAPLACE"):
+    """(loss, terms[4] = {loss, recon, kl, qbce}) of loss_function (utils/mnist_utils/train.py:13-55) for
+    rec_loss in {'LAPLACE', 'MSE', 'BCE'}; the gradients are produced by the same kernel pass."""
+    if rec_loss not in REC_LOSS:
+        raise ValueError("Unknown reconstruction loss! Valid input are 'BCE', 'LAPLACE', or 'MSE'")
+    return _ElboFunction.apply(recon, x, mu, logvar, query_prob, float(recon_w), float(kl_w), float(query_w),
+                               REC_LOSS[rec_loss])

@@ -2,8 +2,9 @@
 compiled circuit replicated, NO collective on the data path (every output row depends only on
 its own fact row — SURVEY.md §8(e)).  torch.distributed is plumbing: process group, barrier and
 the max-over-ranks reduction of device times that bench.py reports.  The only collective in
-training is DistributedDataParallel's NCCL all-reduce of the encoder/decoder gradients; the
-circuit has no parameters.
+training is the NCCL all-reduce of the encoder/decoder gradients (train.FlatGradBucket: one flat
+7.4 MB buffer between the two CUDA graphs of the step); the circuit has no parameters, and
+extract_worlds_probability's whole-batch normaliser (models/vael.py:263-266) stays shard-local.
 """
 from __future__ import annotations
 
@@ -18,16 +19,6 @@ def env_world() -> Tuple[int, int, int]:
     """(world_size, rank, local_rank) from the torchrun environment; (1, 0, 0) without it."""
     return (int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")),
             int(os.environ.get("LOCAL_RANK", "0")))
-
-
-def shard_rows(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
-    """Contiguous, balanced shard of `n_rows` batch rows -> (first row, row count).
-    The first n_rows % world ranks take one extra row; shards tile [0, n_rows) exactly."""
-    if world <= 0 or not 0 <= rank < world or n_rows < 0:
-        raise ValueError(f"bad shard request: rows={n_rows} world={world} rank={rank}")
-    base, extra = divmod(n_rows, world)
-    start = rank * base + min(rank, extra)
-    return start, base + (1 if rank < extra else 0)
 
 
 def rank_seed(base_seed: int, rank: int) -> int:
@@ -46,26 +37,6 @@ def max_over_ranks(value: float, device: Optional[torch.device] = None, group=No
     t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
-
-
-def sum_over_ranks(value: float, device: Optional[torch.device] = None, group=None) -> float:
-    if not _active(group):
-        return float(value)
-    t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
-    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    return float(t.item())
-
-
-def job_rate(units_local: float, seconds_local: float, device: Optional[torch.device] = None, group=None) -> float:
-    """Whole-job throughput: units processed by all ranks / the slowest rank's time."""
-    return sum_over_ranks(units_local, device, group) / max_over_ranks(seconds_local, device, group)
-
-
-def local_normaliser_note() -> str:
-    """extract_worlds_probability divides by the detached sum over the WHOLE batch
-    (models/vael.py:263-266).  Under data parallelism that is the local shard's sum: it only
-    shifts the Gumbel logits by a constant, so no collective is added for it."""
-    return "shard-local"
 
 
 def bind_to_gpu_numa_node(device_index: int) -> Optional[str]:

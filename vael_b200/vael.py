@@ -21,7 +21,8 @@ from torch import nn
 
 from .graph_semiring import GraphSemiring
 from .logic import Constant, Term
-from .ops import circuit_forward, circuit_queries_all, facts_from_logits, gumbel_world
+from .ops import (circuit_forward, circuit_queries_all, facts_from_logits, facts_from_logits_clipped, fused_logic_supported,
+                  gumbel_world, logic_train)
 from .program import CompiledProgramSet, EvaluationResult
 
 
@@ -46,7 +47,10 @@ class VAELModel(nn.Module):
     # ---- sampled world: kept as (index, y_soft), materialised one-hot on demand -----------------
     @property
     def world(self):
-        if isinstance(self._world_cache, tuple):
+        if isinstance(self._world_cache, tuple) and isinstance(self._world_cache[0], str):   # fused forward: index only
+            _, idx, n = self._world_cache
+            self._world_cache = torch.zeros(idx.shape[0], n * n, device=idx.device).scatter_(1, idx.long()[:, None], 1.0)
+        elif isinstance(self._world_cache, tuple):
             idx, y_soft = self._world_cache
             hard = torch.zeros_like(y_soft).scatter_(1, idx.long()[:, None], 1.0)
             self._world_cache = hard - y_soft.detach() + y_soft
@@ -72,6 +76,9 @@ class VAELModel(nn.Module):
 
     def forward(self, x, labels):
         mu, logvar = self.encoder(x)
+        return self._forward_after_encoder(mu, logvar, labels)
+
+    def _forward_after_encoder(self, mu, logvar, labels):
         z = self.reparametrize(mu, logvar)
         self.z_subsym = z[:, self.latent_dim_sym:]
         if self.dropout and self.training:
@@ -139,26 +146,87 @@ class MNISTPairsVAELModel(VAELModel):
         # True = one query per row from labels[:, -2] (mixed-label synthetic batches, no host sync)
         self.query_per_row = query_per_row
         self._pset = None
+        # forward() runs the logic path (facts head -> circuit -> Gumbel sampling -> Herbrand vector) as ONE kernel
+        # per direction when the compiled program allows it; False = the stage-by-stage kernels
+        self.fused_logic = True
+        self._worlds_prob = None
+
+    # worlds_prob: the reference sets it in problog_inference and nobody reads it during training; the fused
+    # forward never materialises it, so it is computed from facts_probs on first access
+    @property
+    def worlds_prob(self):
+        if self._worlds_prob is None and getattr(self, "facts_probs", None) is not None:
+            dc = self.program_set().device_circuit(self.facts_probs.device)
+            self._worlds_prob, _ = circuit_forward(dc, self.facts_probs, None)
+        return self._worlds_prob
+
+    @worlds_prob.setter
+    def worlds_prob(self, value):
+        self._worlds_prob = value
+
+    def mlp_logits(self, z):
+        return self.mlp.logits(z) if hasattr(self.mlp, "logits") else torch.cat(self.mlp(z), dim=1)
+
+    def forward(self, x, labels):
+        """models/vael.py:39-70.  With `fused_logic` the four logic stages are one kernel (ops.logic_train); the
+        side-effect attributes keep their meaning: facts_probs, query_prob, world_idx are written, worlds_prob and
+        world (the hard one-hot; its straight-through soft part lives inside the fused adjoint) on first access."""
+        if not self.fused_logic:
+            return super().forward(x, labels)
+        mu, logvar = self.encoder(x)
+        dc = self.program_set().device_circuit(mu.device)
+        if not fused_logic_supported(dc):
+            self.fused_logic = False
+            return self._forward_after_encoder(mu, logvar, labels)
+        z = self.reparametrize(mu, logvar)
+        self.z_subsym = z[:, self.latent_dim_sym:]
+        if self.dropout and self.training:
+            self.z_subsym = nn.functional.dropout(self.z_subsym, p=self.dropout)
+        logits = self.mlp_logits(z[:, :self.latent_dim_sym])
+        query = labels[:, -2] if self.query_per_row else int(labels[0][-2])
+        seed_dev = None
+        if self.gumbel_noise is None and self.graph_safe_rng:
+            seed_dev = torch.randint(0, 2 ** 62, (1,), device=logits.device, dtype=torch.int64)
+        facts, self.query_prob, world_h, idx, _ = logic_train(dc, logits, query, eps=1e-5, tau=1.0,
+                                                              noise=self.gumbel_noise, seed_dev=seed_dev)
+        self.facts_probs = facts.reshape(-1, 2, self.mlp.n_facts // 2)
+        self._worlds_prob = None
+        self.world_idx = idx
+        self._world_cache = ("hard", idx, self.mlp.n_facts // 2)
+        image = self.decode(self.z_subsym, world_h)
+        return image, mu, logvar, self.query_prob
 
     def program_set(self) -> CompiledProgramSet:
+        """The compiled addition family behind `problog_inference`.  The reference computes the query from the
+        caller's `w_q` matrix (models/vael.py:200-206); here it comes from the compiled circuit, so on first use
+        `w_q` is checked against the circuit's own world -> query table: a custom or permuted matrix raises
+        instead of being silently ignored.  Extra all-zero columns of `w_q` (the reference's column 19,
+        mnist_task_VAEL.py:226-228) are remembered: such a query is 0 for every row."""
         if self._pset is None:
             any_view = next(iter(self.model_dict["query"].values())) if self.model_dict else None
-            if any_view is not None and hasattr(any_view, "pset"):
-                self._pset = any_view.pset
-            else:  # no model_dict given (the reference's training loop never reads it for MNIST)
+            if any_view is not None and hasattr(any_view, "pset") and any_view.pset.circuit.n_queries > 1:
+                pset = any_view.pset
+            else:  # no model_dict (the reference's training loop never reads it for MNIST), or one compiled
+                #    program per label (the reference's own build_model_dict through vael_b200.compat)
                 from .mnist_task import compile_addition_family
-                self._pset = CompiledProgramSet(compile_addition_family(2, self.mlp.n_facts // 2))
+                pset = CompiledProgramSet(compile_addition_family(2, self.mlp.n_facts // 2))
+            if self.w_q is not None:
+                mine = torch.from_numpy(pset.circuit.worlds_queries_matrix()).to(torch.float32)
+                given = self.w_q.detach().to("cpu", torch.float32)
+                nq = mine.shape[1]
+                if given.shape[0] != mine.shape[0] or given.shape[1] < nq or not torch.equal(given[:, :nq], mine) \
+                        or bool(given[:, nq:].any()):
+                    raise RuntimeError("vael_b200: the worlds-queries matrix w_q passed to the model differs from the "
+                                       "compiled program's (build it with build_worlds_queries_matrix)")
+                self._n_wq_cols = given.shape[1]
+            self._pset = pset
         return self._pset
 
     def compute_facts_probability(self, z):
         """[B, latent_dim_sym] -> [B, 2, n]: MLP, then softmax / +1e-5 / detached renorm per digit
         (models/vael.py:159-177) in one kernel."""
-        if hasattr(self.mlp, "logits"):
-            logits = self.mlp.logits(z)
-        else:
-            logits = torch.cat(self.mlp(z), dim=1)
         n = self.mlp.n_facts // 2
-        return facts_from_logits(logits, n_groups=2, eps=1e-5).reshape(-1, 2, n)
+        return facts_from_logits(self.mlp_logits(z), n_groups=2, eps=1e-5).reshape(-1, 2, n)
 
     def define_herbrand_base(self, n_facts):
         """Row i*n+k = [onehot(i), onehot(k)] (models/vael.py:179-187)."""
@@ -180,6 +248,10 @@ class MNISTPairsVAELModel(VAELModel):
         if query is None:
             query = labels[:, -2] if self.query_per_row else int(labels[0][-2])
         dc = self.program_set().device_circuit(facts_probs.device)
+        if not torch.is_tensor(query) and dc.n_queries <= int(query) < getattr(self, "_n_wq_cols", 0):
+            # an all-zero column of w_q (sum 19 of two digits): no world satisfies it
+            self.worlds_prob, _ = circuit_forward(dc, facts_probs, None)
+            return torch.zeros(facts_probs.shape[0], 1, device=facts_probs.device), self.worlds_prob
         self.worlds_prob, query_prob = circuit_forward(dc, facts_probs, query)
         return query_prob, self.worlds_prob
 
@@ -249,9 +321,13 @@ class MarioVAELModel(VAELModel):
     def build_weights_dictionary(self, n_facts):
         return None
 
-    def mario_facts(self, z_sym):
-        """softmax over the 9 positions, clip(1e-5, 0.9999) (models/vael.py:319-322)."""
-        return torch.clip(torch.softmax(self.mlp(z_sym), dim=1), min=self.eps, max=0.9999)
+    def mario_facts(self, z_sym1, z_sym2=None):
+        """softmax over the 9 positions, clip(1e-5, 0.9999) (models/vael.py:319-322): ONE kernel for both frames
+        (facts_tile_kernel<2,9,clip>), returning the concatenated [B,18] fact matrix; a single frame -> [B,9]."""
+        if z_sym2 is None:
+            return facts_from_logits_clipped(self.mlp(z_sym1), 1, self.eps, 0.9999)
+        logits = torch.cat([self.mlp(z_sym1), self.mlp(z_sym2)], dim=1)
+        return facts_from_logits_clipped(logits, 2, self.eps, 0.9999)
 
     def forward(self, x, moves):
         x1, x2 = torch.split(x, x.shape[2] // 2, dim=2)
@@ -262,9 +338,8 @@ class MarioVAELModel(VAELModel):
         if self.dropout and self.training:
             self.z_subsym1 = nn.functional.dropout(self.z_subsym1, p=self.dropout)
             self.z_subsym2 = nn.functional.dropout(self.z_subsym2, p=self.dropout)
-        self.facts_probs1 = self.mario_facts(z1[:, :self.latent_dim_sym])
-        self.facts_probs2 = self.mario_facts(z2[:, :self.latent_dim_sym])
-        facts = torch.cat([self.facts_probs1, self.facts_probs2], dim=1)
+        facts = self.mario_facts(z1[:, :self.latent_dim_sym], z2[:, :self.latent_dim_sym])
+        self.facts_probs1, self.facts_probs2 = torch.split(facts, self.mlp.n_facts // 2, dim=1)
 
         self.worlds_probs = self.compute_worlds_prob_conj(facts)
         self.query_prob = self.compute_query_prob(moves, self.worlds_probs, facts=facts)
@@ -306,12 +381,41 @@ class MarioVAELModel(VAELModel):
         return p_q[:, 0] / (torch.sum(worlds_probs, dim=1) + self.eps)
 
     def compute_query_prob_cond(self, q, worlds_probs):
+        """P(move q | evidence) from conditioned admissible-world probabilities [.., 24] (models/vael.py:401-414)."""
         p_e = torch.sum(worlds_probs, dim=0) + self.eps
         return torch.sum(self.WQ_adm[:, int(q)] * worlds_probs, dim=0) / p_e
 
+    def _evidence_circuit(self, device):
+        if getattr(self, "_evid_pset", None) is None:
+            from .compiler import CompiledFamily
+            from .mario_task import admissible_evidence_circuit, mario_tables
+            _, _, W_adm, WQ_adm = mario_tables(self.program_sets()[0].family)
+            self._evid_pset = CompiledProgramSet(CompiledFamily(admissible_evidence_circuit(W_adm, WQ_adm), {}, [], [], []))
+        return self._evid_pset.device_circuit(device)
+
     def compute_conditioned_worlds_prob(self, probs, evidence):
-        """P(w | evidence move) over the admissible worlds (models/vael.py:416-430), evaluation only."""
-        evidence = torch.as_tensor(evidence).to(self.device)
-        p_w = torch.exp(torch.log(probs) @ self.W_adm.T)
-        w_q = torch.all(self.WQ_adm == evidence, dim=1)
-        return (p_w * w_q + self.eps) / (torch.sum(p_w * w_q) + self.eps)
+        """P(w | evidence move) over the 24 admissible worlds (models/vael.py:416-430), evaluation only:
+        (p_w [w |= e] + eps) / (sum p_w [w |= e] + eps), the sum running over the whole tensor as in the reference.
+        The masked products and P(e) come from the circuit kernel in evidence mode (VAEL_FLAG_EVIDENCE:
+        P(w|e) = [w |= e] P(w) / P(e) per row, and P(e) as the query output)."""
+        evidence = torch.as_tensor(evidence).to(probs.device).reshape(-1)
+        if evidence.numel() != 4 or float(evidence.sum()) != 1.0 or float(evidence.max()) != 1.0:
+            # no move matches an evidence row that is not one-hot: every world gets eps / eps
+            return torch.ones(probs.shape[0], self.W_adm.shape[0], device=probs.device)
+        move = int(torch.argmax(evidence))
+        with torch.no_grad():
+            cond, p_e = circuit_forward(self._evidence_circuit(probs.device), probs, move, evidence=True)
+        return (cond * p_e + self.eps) / (p_e.sum() + self.eps)
+
+    def encode_image(self, x):
+        """Crisp position facts of one frame (models/vael.py:432-451), evaluation only."""
+        with torch.no_grad():
+            mu, logvar = self.encoder(x)
+            z = self.reparametrize(mu, logvar)
+            z_subsym = z[:, self.latent_dim_sym:]
+            facts_probs_ = torch.softmax(self.mlp(z[:, :self.latent_dim_sym]), dim=1)
+            facts_probs = torch.zeros_like(facts_probs_)
+            mask = facts_probs_ >= facts_probs_.max()
+            facts_probs[mask] = facts_probs_[mask]
+            facts_probs[:, torch.where(facts_probs > 0.5)[1]] = 1.
+        return z_subsym, facts_probs
