@@ -23,6 +23,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# NCCL_DEBUG belongs to the caller (the driver reads the communicator lines) and is honoured as set.  Unset, under
+# torchrun: the communicator-init lines (ranks, transport) go to STDERR so that stdout stays the one JSON line.  Set
+# before torch (and with it NCCL) is loaded: NCCL latches its debug level the first time any of it runs.
+if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not os.environ.get("NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = "INFO"
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import torch  # noqa: E402
 
 EVALS_PER_ROW = 101            # Q of query-mode evaluate: 100 worlds + 1 addition query
@@ -369,12 +377,6 @@ def run_ours(args):
     distributed = world > 1
     numa = parallel.bind_to_gpu_numa_node(local) if distributed and not os.environ.get("VAEL_NO_NUMA_BIND") else None
     if distributed:
-        # NCCL_DEBUG belongs to the caller (the driver reads the communicator lines) and is honoured as set.  Unset:
-        # the communicator-init lines (ranks, NVLS / P2P transport) are logged to STDERR, stdout stays one JSON line.
-        if not os.environ.get("NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "INFO"
-            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():

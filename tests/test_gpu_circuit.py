@@ -246,9 +246,11 @@ def test_full_size_properties_and_host_path(dc, addition_family):
 @pytest.mark.parametrize("B", [1, 77, 3000])
 def test_admissible_worlds_literal_table_kernel(cuda_device, B):
     """Mario's admissible-world log-probabilities (models/vael.py:368-375) through the literal-table kernel
-    (fast_kind 4): within 1e-5 of the reference's two-matmul form (fp64) — like the generic CSR kernel, which folds
-    the same terms in CSR order —, adjoint against fp64 autograd of that form; tables with mostly-positive rows take
-    the base+ form; a table the kernel does not cover stays on the generic kernel."""
+    (fast_kind 4): log-probabilities within 1e-5 * max(1, |ref|) of the reference's two-matmul form in fp64 — an
+    absolute error of a log-probability is a relative error of the probability, which is what the 1e-5 bar is about
+    (the base + delta form cancels on peaked rows) —, the generic CSR kernel (accurate logf, CSR
+    order) to 1e-5 relative, adjoint against fp64 autograd; tables with mostly-positive rows take the base+ form; a
+    table the kernel does not cover stays on the generic kernel."""
     from vael_b200 import _lib
     from vael_b200.compiler import circuit_from_world_table
     from vael_b200.mario_task import admissible_circuit, compile_mario_family, mario_tables
@@ -258,6 +260,10 @@ def test_admissible_worlds_literal_table_kernel(cuda_device, B):
     assert dca.fast_kind == 4
     rng = np.random.default_rng(B)
     p = rng.dirichlet(np.ones(9), size=(B, 2)).astype(np.float32).clip(1e-5, 0.9999).reshape(B, 18)
+    if B > 10:   # peaked rows: one position at the clip ceiling, the others at the floor (the cancelling case)
+        p[:5] = 1e-5
+        p[np.arange(5), np.arange(5)] = 0.9999
+        p[np.arange(5), 9 + np.arange(5)] = 0.9999
     ga = rng.standard_normal((B, 24)).astype(np.float32)
     outs = []
     for generic in (False, True):
@@ -272,8 +278,10 @@ def test_admissible_worlds_literal_table_kernel(cuda_device, B):
     ref = torch.log(p64) @ Wt.T + torch.log(1 - p64) @ (1 - Wt).T          # models/vael.py:371-374
     (ref * torch.from_numpy(ga).double()).sum().backward()
     g_ref = p64.grad.numpy()
+    refn = ref.detach().numpy()
+    assert np.all(np.abs(outs[0][0] - refn) <= 1e-5 * np.maximum(1.0, np.abs(refn)))
+    assert rel_err(outs[1][0], refn) < 1e-5
     for o in outs:
-        assert rel_err(o[0], ref.detach().numpy()) < 1e-5
         assert rel_err(o[1], g_ref, floor=1e-3 * np.abs(g_ref).max()) < 1e-4
     # a random table with sparse, dense and half-set rows: base- and base+ forms side by side
     tab = np.zeros((12, 18), dtype=np.int8)
@@ -290,7 +298,8 @@ def test_admissible_worlds_literal_table_kernel(cuda_device, B):
     Tt = torch.from_numpy(tab.astype(np.float64))
     ref = torch.log(p64) @ Tt.T + torch.log(1 - p64) @ (1 - Tt).T
     (ref * torch.from_numpy(gt).double()).sum().backward()
-    assert rel_err(lw.detach().cpu().numpy(), ref.detach().numpy()) < 1e-5
+    refn = ref.detach().numpy()
+    assert np.all(np.abs(lw.detach().cpu().numpy() - refn) <= 1e-5 * np.maximum(1.0, np.abs(refn)))
     assert rel_err(f.grad.cpu().numpy(), p64.grad.numpy(), floor=1e-3 * np.abs(p64.grad.numpy()).max()) < 1e-4
     # 19 fact columns: not a shape the kernel is built for; 40 worlds all setting column 0: the per-column list
     # does not fit the kernel's tables

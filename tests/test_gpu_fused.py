@@ -87,20 +87,53 @@ def test_fused_logic_equals_the_stage_kernels(cuda_device, dc2, B):
     assert same.float().mean().item() > 0.999
     np.testing.assert_allclose(ysa[same].cpu().numpy(), ysb[same].cpu().numpy(), rtol=2e-5, atol=1e-9)
     assert torch.allclose(wha[same], whb[same], atol=2.4e-7, rtol=0)
-    (ga,) = torch.autograd.grad((wha * gh).sum() + (qa * gq).sum() + (fa * gf).sum(), [la])
-    (gb,) = torch.autograd.grad((whb * gh).sum() + (qb * gq).sum() + (fb * gf).sum(), [lb])
-    ga, gb = ga[same].cpu().numpy(), gb[same].cpu().numpy()
-    assert rel_err(ga, gb, floor=1e-3 * np.abs(gb).max()) < 1e-4
-    # each upstream alone (null pointers on the other inputs of the adjoint kernel)
-    for k, (out, up) in enumerate(((wha, gh), (qa, gq), (fa, gf))):
+    # The adjoint: y_i (a_i - sum_j y_j a_j) cancels, so two fp32 evaluations differ by more than 1e-4 of small
+    # entries; both are measured against fp64 autograd through the oracle's restatement of the reference chain
+    # (the test_facts_head_matches_oracle protocol): ours within 1e-4 (floor 1e-2 * max) and no worse than twice
+    # the stage kernels.  All three upstreams together, then each alone (null pointers on the others).
+    x64 = logits.double().cpu().requires_grad_(True)
+    f64 = dense_path.facts_probability(x64, n_groups=2)
+    q64, w64 = dense_path.dense_inference_rows(f64, dense_path.worlds_queries_matrix().double(), query.cpu().long())
+    world64, _, _ = dense_path.gumbel_hard(torch.log(w64), noise.double().cpu(), tau=1.0)
+    wh64 = world64 @ dense_path.herbrand_base(20).double()
+    outs64 = (f64.reshape(B, 20), q64, wh64)
+    keep = same.cpu().numpy()
+    for sel in ((0, 1, 2), (2,), (1,), (0,)):
+        ups = (gf, gq, gh)
+        (g64,) = torch.autograd.grad(sum((outs64[k] * ups[k].double().cpu()).sum() for k in sel), [x64], retain_graph=True)
         lc = logits.clone().requires_grad_(True)
-        outs = logic_train(dc2, lc, query, noise=noise)
-        (g1,) = torch.autograd.grad((outs[(2, 1, 0)[k]] * up).sum(), [lc])
+        oc = logic_train(dc2, lc, query, noise=noise)
+        (g1,) = torch.autograd.grad(sum((oc[k] * ups[k]).sum() for k in sel), [lc])
         ld = logits.clone().requires_grad_(True)
-        outs_d = unfused_chain(dc2, ld, query, noise)
-        (g2,) = torch.autograd.grad((outs_d[(2, 1, 0)[k]] * up).sum(), [ld])
-        g1, g2 = g1[same].cpu().numpy(), g2[same].cpu().numpy()
-        assert rel_err(g1, g2, floor=1e-3 * np.abs(g2).max() + 1e-12) < 1e-4, k
+        od = unfused_chain(dc2, ld, query, noise)
+        (g2,) = torch.autograd.grad(sum((od[k] * ups[k]).sum() for k in sel), [ld])
+        g64n = g64.numpy()[keep]
+        floor = 1e-2 * np.abs(g64n).max() + 1e-12
+        ours, theirs = rel_err(g1.cpu().numpy()[keep], g64n, floor=floor), rel_err(g2.cpu().numpy()[keep], g64n, floor=floor)
+        assert ours < 1e-4 and ours < 2 * theirs + 2e-5, (sel, ours, theirs)
+
+
+@pytest.mark.parametrize("tau", [0.3, 2.0])
+def test_fused_logic_temperature(cuda_device, dc2, tau):
+    """tau != 1 (F.gumbel_softmax's temperature): against the stage kernels with the same injected noise."""
+    from vael_b200.ops import circuit_forward, facts_from_logits, gumbel_world, logic_train
+    gen = torch.Generator().manual_seed(3)
+    B = 2000
+    logits = (2 * torch.randn(B, 20, generator=gen)).cuda()
+    noise = (-torch.empty(B, 100).exponential_(generator=gen).log()).cuda()
+    gh = torch.randn(B, 20, generator=gen).cuda()
+    la = logits.clone().requires_grad_(True)
+    _, _, wha, ia, ysa = logic_train(dc2, la, 4, noise=noise, tau=tau, want_y_soft=True)
+    lb = logits.clone().requires_grad_(True)
+    worlds, _ = circuit_forward(dc2, facts_from_logits(lb, 2, 1e-5), 4)
+    whb, ib, ysb = gumbel_world(worlds, dense_path.herbrand_base(20).cuda(), tau=tau, is_log=False, noise=noise)
+    same = ia == ib
+    assert same.float().mean().item() > 0.995
+    np.testing.assert_allclose(ysa[same].cpu().numpy(), ysb[same].cpu().numpy(), rtol=5e-5, atol=1e-9)
+    (ga,) = torch.autograd.grad((wha * gh).sum(), [la])
+    (gb,) = torch.autograd.grad((whb * gh).sum(), [lb])
+    ga, gb = ga[same].cpu().numpy(), gb[same].cpu().numpy()
+    assert rel_err(ga, gb, floor=1e-2 * np.abs(gb).max()) < 2e-4
 
 
 def test_fused_logic_scalar_query_and_unaligned_views(cuda_device, dc2):
@@ -141,6 +174,14 @@ def test_fused_logic_philox_mode(cuda_device, dc2):
     sd = torch.tensor([77], dtype=torch.int64, device="cuda")
     _, _, _, i4, _ = logic_train(dc2, logits, 9, seed_dev=sd)         # the device word overrides the host seed
     assert torch.equal(i1, i4)
+    # the single-pass production kernel (FAST) and the two-pass one (GENERAL, taken when y_soft is asked for) draw the
+    # same noise and form the same perturbed logits: identical worlds, for every tau the fast kernel accepts
+    for tau in (1.0, 0.5, 3.0):
+        fa, qa, wha, ia, _ = logic_train(dc2, logits[:50000], 9, seed=5, tau=tau)
+        fb, qb, whb, ib, ys = logic_train(dc2, logits[:50000], 9, seed=5, tau=tau, want_y_soft=True)
+        assert torch.equal(ia, ib) and torch.equal(fa, fb) and torch.equal(qa, qb)
+        assert torch.allclose(wha, whb, atol=2.4e-7, rtol=0)
+        assert torch.allclose(ys.sum(1), torch.ones(50000, device="cuda"), atol=1e-5)
     facts = facts_from_logits(logits[:1], 2, 1e-5)
     p = circuit_forward(dc2, facts, None)[0][0].double().cpu()
     counts = torch.bincount(i1.long(), minlength=100).double().cpu()
@@ -166,7 +207,7 @@ def test_fused_logic_philox_mode(cuda_device, dc2):
     _lib.check(lib.vael_gumbel_world_backward(_p(worlds.detach()), _p(ys), _p(gh), Bs, 100, 0, 1.0, _p(hb), 20, _p(gs),
                                               _stream_ptr()))
     (g_ref,) = torch.autograd.grad((worlds * gs).sum() + (q2 * gq).sum(), [lg2])
-    assert rel_err(g_fused.cpu().numpy(), g_ref.cpu().numpy(), floor=1e-3 * g_ref.abs().max().item()) < 1e-4
+    assert rel_err(g_fused.cpu().numpy(), g_ref.cpu().numpy(), floor=1e-2 * g_ref.abs().max().item()) < 2e-4
 
 
 def test_model_forward_fused_equals_stagewise(cuda_device):
@@ -182,6 +223,7 @@ def test_model_forward_fused_equals_stagewise(cuda_device):
                                 MNISTPairsMLP(in_features=15, n_facts=20), (15, 8), build_model_dict(2, 10, device=cuda_device),
                                 build_worlds_queries_matrix(2, 10).to(cuda_device), dropout=None, is_train=True,
                                 device=cuda_device, query_per_row=True).to(cuda_device)
+    model.eval()          # no dropout masks: the two passes must see the same network (reparametrize follows is_train)
     B = 64
     gen = torch.Generator().manual_seed(2)
     x = torch.randn(B, 1, 28, 56, generator=gen).cuda()
@@ -229,7 +271,8 @@ def test_clipped_facts_head(cuda_device, B, groups):
     near = ((y - 1e-5).abs() < 1e-9) | ((y - 0.9999).abs() < 1e-6)
     rows = ~near.any(1)
     gn, gr = g.cpu().numpy()[rows.numpy()], g_ref.numpy()[rows.numpy()]
-    assert rel_err(gn, gr, floor=1e-3 * np.abs(gr).max() + 1e-12) < 1e-4
+    if gr.size:   # y_i (a_i - sum_j y_j a_j) cancels: floor as in test_facts_head_matches_oracle
+        assert rel_err(gn, gr, floor=1e-2 * np.abs(gr).max() + 1e-12) < 1e-4
     # a width the tile kernels do not cover takes the generic one-thread-per-group kernel
     x7 = 4 * torch.randn(B, 14, generator=gen)
     o7 = facts_from_logits_clipped(x7.cuda(), 2, 1e-5, 0.9999).cpu()

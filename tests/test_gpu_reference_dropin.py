@@ -76,7 +76,8 @@ def test_reference_model_evidence_and_query_inference_on_cuda(ref, ref_model, cu
     # ... and it agrees with the reference's own dense restatement (models/vael.py:208-225) on the same facts
     qd, wd = ref_model.problog_inference(facts, labels=torch.tensor([[0, 0, 9, -1]] * 32))
     np.testing.assert_allclose(qp.cpu().numpy(), qd.cpu().numpy(), rtol=1e-5)
-    np.testing.assert_allclose((worlds * worlds.sum()).cpu().numpy(), (wd + 1e-7).cpu().numpy(), rtol=2e-5)
+    # extract_worlds_probability: (P(w) + 1e-7) / sum over the WHOLE batch (models/vael.py:260-266)
+    np.testing.assert_allclose(worlds.cpu().numpy(), ((wd + 1e-7) / (wd + 1e-7).sum()).cpu().numpy(), rtol=2e-5)
 
 
 def test_reference_model_gradients_flow_through_the_compiled_program(ref, ref_model, cuda_device):

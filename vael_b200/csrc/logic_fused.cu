@@ -16,19 +16,61 @@
 // lane <-> row, everything in registers (the W = N*N perturbed logits are a fully unrolled register array), no
 // shared memory, no barriers; rows are fetched with 128-bit loads (a row is 2N contiguous floats).  The kernel is
 // bound by FP32 / SFU issue, not by HBM: per row W x (a quarter Philox4x32-10 call, the Gumbel transform,
-// one expf) plus 2N logf — about 5.5 k instructions against 252 B.
+// one exp2) plus the facts head — about 5 k instructions against 252 B.
 //
 // Arithmetic notes.  facts: the same facts_row as the stand-alone kernel (bit-identical).  worlds and query:
 // __fmul_rn products folded in world order under the per-row query mask (bit-identical to ad2_forward_kernel).
-// logit(w) = log p1[i] + log p2[k] (2N logarithms instead of W; the reference takes log of the fp32 product —
-// both are within an ulp of the exact value).  Ties of the arg-max go to the lowest world index.
+// logit(w) = log p1[i] + log p2[k] (2N fast logarithms instead of W accurate ones; absolute error <= 3e-6, far
+// below the Gumbel noise it is added to; y_soft agrees with the reference's to ~1e-5 relative), softmax as
+// exp2 in the log2 domain.  Ties of the arg-max go to the lowest world index.
 // Adjoint: with y = softmax((logit + g)/tau), G_e = gh[i] + gh[N+k], d logit_e = y_e (G_e - sum y G) / tau;
 // d/d p1[i] of sum_e d logit_e log(p1[i] p2[k]) = (sum_k d logit_ik) / p1[i] — no division per world;
 // the query adds gq [e in query] p2[k] (resp. p1[i]); then the facts-head adjoint (detached normaliser).
+//
+// Two variants per direction.  GENERAL keeps the W perturbed logits in registers (two passes: max, then exp) and takes
+// any noise source and any tau.  FAST is the production path (in-kernel Philox noise, tau >= 0.5): Philox-drawn Gumbel
+// variates are bounded, so M = max_i log p1[i] + max_k log p2[k] + (largest variate) bounds every perturbed logit of
+// the row from above BEFORE any of them is drawn, and the largest one sits at most 57 binades below M — the softmax is
+// a single pass of exp2(z - M) with no running maximum, nothing W-sized lives in registers (70 / ~130 registers
+// instead of 157 / 255: 2-3x the resident warps), and the adjoint needs the per-column sums of p and p G only
+// (a[c] = A[c] - (sum p G / sum p) P[c]).
+#include <cstdlib>
+
 #include "params.cuh"
 #include "sampling.cuh"
 
 namespace vael {
+
+constexpr float kLog2e = 1.4426950408889634f;
+// log2 of the exponential variate E2 = -log2(U) behind a Gumbel variate, U = (k + 1/2) 2^-23 (sampling.cuh):
+// E2 in [2^-24 / ln 2, 24]  ->  log2 E2 in [-23.48, 4.59]
+constexpr float kLogE2Min = -23.5f, kLogE2Max = 4.6f;
+
+// The noise in the form the kernels consume: L = log2(E2), E2 = -log2(U) = E / ln 2 with E ~ Exp(1), so that the Gumbel
+// variate is g = -ln E = -ln2 (L + log2 ln2) and a perturbed logit in the log2 domain is
+//     log2(e)/tau (log p + g) = s log p - L / tau + const,    s = log2(e) / tau
+// (the constant shifts every world of the row alike: arg-max and softmax do not see it).  Same accuracy guard as
+// gumbel_from_bits: for U -> 1 the series of -log(1 - v) replaces the fast logarithm.
+__device__ __forceinline__ float log2_exp_variate(uint32_t bits) {
+  const float u = (static_cast<float>(bits >> 9) + 0.5f) * (1.0f / 8388608.0f);
+  const float v = 1.0f - u;
+  const float series = v * fmaf(v, fmaf(v, 0.48089835f, 0.72134752f), 1.44269504f);   // (v + v^2/2 + v^3/3) / ln 2
+  const float e2 = (v < 1.0f / 1024.0f) ? series : -__log2f(u);
+  return __log2f(e2);
+}
+__device__ __forceinline__ void noise_block(long long row, int blk, uint64_t seed, float* L4) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)blk, 0x5eedu),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  L4[0] = log2_exp_variate(r.x); L4[1] = log2_exp_variate(r.y);
+  L4[2] = log2_exp_variate(r.z); L4[3] = log2_exp_variate(r.w);
+}
+
+// 2^x, x <= 0 (MUFU.EX2; 2 ulp): the softmax runs in the log2 domain, the log2(e) factor folded into 1/tau
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 template <int F>
 __device__ __forceinline__ void load_row(const float* __restrict__ base, long long row, float* x, bool al16) {
@@ -57,17 +99,18 @@ __device__ __forceinline__ void store_row(float* __restrict__ base, long long ro
   }
 }
 
-// Perturbed logits z[e] = (log p1[i] + log p2[k] + g_e) / tau of one row, its maximum and arg-max; the query sum
-// under mask `m` when `qsum` is non-null.  The noise is injected (`noise`, [B,W]) or drawn from Philox4x32-10:
-// one call per four consecutive worlds, counter = (row, e / 4), key = seed.
+// GENERAL: perturbed logits z[e] of one row in the log2 domain (up to a row constant), their maximum and arg-max; the
+// query sum under mask `m` when `qsum` is non-null.  Noise: injected (`noise` [B,W], z = s (log p + g)) or Philox
+// (one call per four consecutive worlds, counter = (row, e / 4), key = seed; z = s log p - L / tau).
 template <int N>
 __device__ __forceinline__ void perturbed_logits(const FusedParams& P, long long row, uint64_t seed, const float* f,
                                                  const uint32_t* m, float inv_tau, float* z, float& mx, int& arg,
                                                  float* qsum) {
   constexpr int W = N * N;
-  float lp[2 * N];
+  const float s = inv_tau * kLog2e;
+  float lps[2 * N];
 #pragma unroll
-  for (int c = 0; c < 2 * N; ++c) lp[c] = logf(f[c]);
+  for (int c = 0; c < 2 * N; ++c) lps[c] = s * __logf(f[c]);   // absolute error of the log <= 3e-6: noise-level
   const bool nz_al = P.noise != nullptr && (W % 4 == 0) && aligned16(P.noise);
   mx = -INFINITY;
   arg = 0;
@@ -86,17 +129,26 @@ __device__ __forceinline__ void perturbed_logits(const FusedParams& P, long long
           for (int u = 0; u < 4; ++u) g4[u] = (e + u < W) ? __ldg(P.noise + row * W + e + u) : 0.0f;
         }
       } else {
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)(e >> 2), 0x5eedu),
-                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-        g4[0] = gumbel_from_bits(r.x); g4[1] = gumbel_from_bits(r.y);
-        g4[2] = gumbel_from_bits(r.z); g4[3] = gumbel_from_bits(r.w);
+        noise_block(row, e >> 2, seed, g4);
       }
     }
     if (qsum != nullptr && ((m[e >> 5] >> (e & 31)) & 1u)) acc = __fadd_rn(acc, __fmul_rn(f[i], f[N + k]));
-    z[e] = (lp[i] + lp[N + k] + g4[e & 3]) * inv_tau;
+    z[e] = (P.noise != nullptr) ? fmaf(g4[e & 3], s, lps[i] + lps[N + k]) : fmaf(g4[e & 3], -inv_tau, lps[i] + lps[N + k]);
     if (z[e] > mx) { mx = z[e]; arg = e; }
   }
   if (qsum != nullptr) *qsum = acc;
+}
+
+// FAST: s log p per column and the row's upper bound M of every perturbed logit (Philox noise only)
+template <int N>
+__device__ __forceinline__ float scaled_logs_and_bound(const float* f, float inv_tau, float* lps) {
+  const float s = inv_tau * kLog2e;
+#pragma unroll
+  for (int c = 0; c < 2 * N; ++c) lps[c] = s * __logf(f[c]);
+  float m1 = lps[0], m2 = lps[N];
+#pragma unroll
+  for (int i = 1; i < N; ++i) { m1 = fmaxf(m1, lps[i]); m2 = fmaxf(m2, lps[N + i]); }
+  return m1 + m2 - kLogE2Min * inv_tau;
 }
 
 template <int MW>
@@ -110,7 +162,7 @@ __device__ __forceinline__ void fused_mask(uint32_t* m, const FusedParams& P, lo
   }
 }
 
-template <int N>
+template <int N, bool FAST>
 __global__ void __launch_bounds__(128) fused_forward_kernel(const FusedParams P) {
   constexpr int F = 2 * N, W = N * N, MW = (W + 31) / 32;
   const uint64_t seed = P.seed_dev ? *P.seed_dev : P.seed;
@@ -126,23 +178,42 @@ __global__ void __launch_bounds__(128) fused_forward_kernel(const FusedParams P)
     if (P.facts != nullptr) store_row<F>(P.facts, row, f, aligned16(P.facts));
     uint32_t m[MW];
     fused_mask<MW>(m, P, row);
-    float z[W], mx, q;
+    float ys;   // y_soft of the selected world
     int arg;
-    perturbed_logits<N>(P, row, seed, f, m, inv_tau, z, mx, arg, &q);
-    if (P.query != nullptr) P.query[row] = q;
-    float sum = 0.0f;
+    if constexpr (FAST) {
+      float lps[F];
+      const float M = scaled_logs_and_bound<N>(f, inv_tau, lps);
+      float mx = -INFINITY, sum = 0.0f, q = 0.0f, L4[4];
+      arg = 0;
 #pragma unroll
-    for (int e = 0; e < W; ++e) {
-      z[e] = expf(z[e] - mx);
-      sum += z[e];
-    }
-    const float inv_sum = 1.0f / sum;
-    if (P.y_soft != nullptr) {
+      for (int e = 0; e < W; ++e) {
+        const int i = e / N, k = e % N;
+        if ((e & 3) == 0) noise_block(row, e >> 2, seed, L4);
+        if (P.query != nullptr && ((m[e >> 5] >> (e & 31)) & 1u)) q = __fadd_rn(q, __fmul_rn(f[i], f[N + k]));
+        const float z = fmaf(L4[e & 3], -inv_tau, lps[i] + lps[N + k]);
+        if (z > mx) { mx = z; arg = e; }
+        sum += fast_exp2(z - M);
+      }
+      if (P.query != nullptr) P.query[row] = q;
+      ys = fast_exp2(mx - M) / sum;
+    } else {
+      float z[W], mx, q;
+      perturbed_logits<N>(P, row, seed, f, m, inv_tau, z, mx, arg, &q);
+      if (P.query != nullptr) P.query[row] = q;
+      float sum = 0.0f;
 #pragma unroll
-      for (int e = 0; e < W; ++e) P.y_soft[row * W + e] = z[e] * inv_sum;
+      for (int e = 0; e < W; ++e) {
+        z[e] = fast_exp2(z[e] - mx);
+        sum += z[e];
+      }
+      const float inv_sum = 1.0f / sum;
+      if (P.y_soft != nullptr) {
+#pragma unroll
+        for (int e = 0; e < W; ++e) P.y_soft[row * W + e] = z[e] * inv_sum;
+      }
+      ys = 1.0f * inv_sum;   // exp2(0) / sum
     }
-    // straight-through forward value of the selected component: (1 - y_soft) + y_soft, y_soft[arg] = exp(0) / sum
-    const float ys = 1.0f * inv_sum;
+    // straight-through forward value of the selected component: (1 - y_soft) + y_soft
     const float one = (1.0f - ys) + ys;
     if (P.world_idx != nullptr) P.world_idx[row] = arg;
     if (P.world_h != nullptr) {
@@ -155,8 +226,10 @@ __global__ void __launch_bounds__(128) fused_forward_kernel(const FusedParams P)
   }
 }
 
-template <int N>
-__global__ void __launch_bounds__(128) fused_backward_kernel(const FusedParams P) {
+// MINB: resident CTAs per SM the register allocation is capped for (4 -> 128 registers with a few spilled words,
+// 1 -> 168 registers, no spills); VAEL_FUSED_BWD_MINB picks, the default is the measured optimum
+template <int N, bool FAST, int MINB = 1>
+__global__ void __launch_bounds__(128, MINB) fused_backward_kernel(const FusedParams P) {
   constexpr int F = 2 * N, W = N * N, MW = (W + 31) / 32;
   const uint64_t seed = P.seed_dev ? *P.seed_dev : P.seed;
   const float inv_tau = 1.0f / P.tau;
@@ -173,7 +246,29 @@ __global__ void __launch_bounds__(128) fused_backward_kernel(const FusedParams P
     float df[F];
 #pragma unroll
     for (int c = 0; c < F; ++c) df[c] = 0.0f;
-    if (P.grad_world_h != nullptr) {
+    if (P.grad_world_h != nullptr && FAST) {
+      float gh[F], lps[F], Pc[F], Ac[F];
+      load_row<F>(P.grad_world_h, row, gh, aligned16(P.grad_world_h));
+      const float M = scaled_logs_and_bound<N>(f, inv_tau, lps);
+#pragma unroll
+      for (int c = 0; c < F; ++c) Pc[c] = Ac[c] = 0.0f;
+      float L4[4];
+#pragma unroll
+      for (int e = 0; e < W; ++e) {
+        const int i = e / N, k = e % N;
+        if ((e & 3) == 0) noise_block(row, e >> 2, seed, L4);
+        const float pe = fast_exp2(fmaf(L4[e & 3], -inv_tau, lps[i] + lps[N + k]) - M);
+        const float t = pe * (gh[i] + gh[N + k]);
+        Pc[i] += pe; Pc[N + k] += pe;
+        Ac[i] += t; Ac[N + k] += t;
+      }
+      float S = 0.0f, D = 0.0f;
+#pragma unroll
+      for (int i = 0; i < N; ++i) { S += Pc[i]; D += Ac[i]; }
+      const float dot = D / S, scale = inv_tau / S;
+#pragma unroll
+      for (int c = 0; c < F; ++c) df[c] = fmaf(-dot, Pc[c], Ac[c]) * scale / f[c];
+    } else if (P.grad_world_h != nullptr) {
       float z[W], mx;
       int arg;
       perturbed_logits<N>(P, row, seed, f, m, inv_tau, z, mx, arg, nullptr);
@@ -182,7 +277,7 @@ __global__ void __launch_bounds__(128) fused_backward_kernel(const FusedParams P
       float S = 0.0f, D = 0.0f;
 #pragma unroll
       for (int e = 0; e < W; ++e) {
-        z[e] = expf(z[e] - mx);
+        z[e] = fast_exp2(z[e] - mx);
         S += z[e];
         D = fmaf(z[e], gh[e / N] + gh[N + e % N], D);
       }
@@ -217,6 +312,10 @@ __global__ void __launch_bounds__(128) fused_backward_kernel(const FusedParams P
       for (int c = 0; c < F; ++c) df[c] += gf[c];
     }
     // facts head: f = (y + eps) / Z with Z detached -> dy_i = df_i / Z; softmax: dx_i = y_i (dy_i - sum_j y_j dy_j)
+    if constexpr (FAST) {   // y was not kept across the world loop (registers): y = f Z - eps, one rounding away
+#pragma unroll
+      for (int c = 0; c < F; ++c) y[c] = fmaf(f[c], zs[c / N], -P.eps);
+    }
     float dx[F];
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
@@ -240,21 +339,40 @@ static void fused_shape(long long B, int num_sms, int* grid, int* block) {
   *grid = (int)max(1LL, min((B + *block - 1) / *block, (long long)num_sms * 4 * (128 / *block)));
 }
 
+// FAST needs bounded (Philox) noise and a tau that keeps the softmax terms inside fp32's range; y_soft is a
+// GENERAL-only output (it needs every term after the sum is known)
+static bool fused_fast_ok(const FusedParams& P) {
+  static const bool off = getenv("VAEL_FUSED_GENERAL") != nullptr;   // tests / A-B timing
+  return !off && P.noise == nullptr && P.tau >= 0.5f && P.y_soft == nullptr;
+}
+
+template <bool BWD, bool FAST>
+static cudaError_t fused_launch(int n, const FusedParams& P, int grid, int block, cudaStream_t st) {
+  static const int minb = getenv("VAEL_FUSED_BWD_MINB") ? atoi(getenv("VAEL_FUSED_BWD_MINB")) : 4;
+  if (n == 10) {
+    if (BWD && FAST && minb == 4) fused_backward_kernel<10, FAST, 4><<<grid, block, 0, st>>>(P);
+    else if (BWD && FAST && minb == 5) fused_backward_kernel<10, FAST, 5><<<grid, block, 0, st>>>(P);
+    else if (BWD && FAST && minb == 3) fused_backward_kernel<10, FAST, 3><<<grid, block, 0, st>>>(P);
+    else if (BWD) fused_backward_kernel<10, FAST><<<grid, block, 0, st>>>(P);
+    else fused_forward_kernel<10, FAST><<<grid, block, 0, st>>>(P);
+  } else if (n == 9) {
+    if (BWD) fused_backward_kernel<9, FAST><<<grid, block, 0, st>>>(P);
+    else fused_forward_kernel<9, FAST><<<grid, block, 0, st>>>(P);
+  } else {
+    return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
 cudaError_t fused_forward(int n, const FusedParams& P, int num_sms, cudaStream_t st) {
   int grid, block;
   fused_shape(P.B, num_sms, &grid, &block);
-  if (n == 10) fused_forward_kernel<10><<<grid, block, 0, st>>>(P);
-  else if (n == 9) fused_forward_kernel<9><<<grid, block, 0, st>>>(P);
-  else return cudaErrorInvalidValue;
-  return cudaGetLastError();
+  return fused_fast_ok(P) ? fused_launch<false, true>(n, P, grid, block, st) : fused_launch<false, false>(n, P, grid, block, st);
 }
 cudaError_t fused_backward(int n, const FusedParams& P, int num_sms, cudaStream_t st) {
   int grid, block;
   fused_shape(P.B, num_sms, &grid, &block);
-  if (n == 10) fused_backward_kernel<10><<<grid, block, 0, st>>>(P);
-  else if (n == 9) fused_backward_kernel<9><<<grid, block, 0, st>>>(P);
-  else return cudaErrorInvalidValue;
-  return cudaGetLastError();
+  return fused_fast_ok(P) ? fused_launch<true, true>(n, P, grid, block, st) : fused_launch<true, false>(n, P, grid, block, st);
 }
 
 }  // namespace vael
