@@ -643,7 +643,7 @@ def secondary_probe(args, dev, rank, world, barrier, max_over_ranks, lib):
                           lambda: None, 10, barrier, max_over_ranks)
     out["all_queries_3digit"] = {"workload": "all 28 sums per row of the 3-digit circuit (worlds not materialised)",
                                  "rows_per_gpu": B, "kernel_family": _lib.last_kernel(), "ms": a3_ms,
-                                 "bytes_per_row": 120 + 112, "GBs": B * 232 / a3_ms / 1e6,
+                                 "bytes_per_row": 120 + 112, "GBs": B * 232 / a3_ms / 1e6, "frac": B * 232 / a3_ms / 1e6 / peak,
                                  "rows_per_sec": world * B / (a3_ms * 1e-3)}
     del qa3
     Bg = B // 4   # the same circuit through the generic CSR kernels (1163 nodes: R = 1 tiles, chunked staging)
@@ -711,7 +711,14 @@ def secondary_probe(args, dev, rank, world, barrier, max_over_ranks, lib):
             "admissible_logprob": {"kernel_family": _lib.last_kernel(),
                                    "fwd": {"ms": fa_ms, "bytes_per_row": fab, "GBs": Bm * fab / fa_ms / 1e6, "frac": Bm * fab / fa_ms / 1e6 / peak},
                                    "bwd": {"ms": ba_ms, "bytes_per_row": bab, "GBs": Bm * bab / ba_ms / 1e6, "frac": Bm * bab / ba_ms / 1e6 / peak}}}
-        del wm, gwm, la, gla, pm
+        qam = torch.empty(Bm, 5, device=dev)
+        qa_ms, _ = _time_pair(lambda: _lib.check(lib.vael_circuit_queries_all(dcm.handle, _p(pm), Bm, _p(qam), 0, sp)),
+                              lambda: None, 10, barrier, max_over_ranks)
+        out["mario_circuits"]["all_queries"] = {
+            "workload": "the four move queries + constraint of every row (member-list kernel; worlds not materialised)",
+            "kernel_family": _lib.last_kernel(), "ms": qa_ms, "bytes_per_row": 72 + 20, "GBs": Bm * 92 / qa_ms / 1e6,
+            "frac": Bm * 92 / qa_ms / 1e6 / peak}
+        del wm, gwm, la, gla, pm, qam
         torch.cuda.empty_cache()
     except Exception as exc:  # noqa: BLE001 - a secondary probe must not take the headline down
         out["mario_circuits"] = {"error": repr(exc)[:300]}
@@ -729,7 +736,7 @@ def secondary_probe(args, dev, rank, world, barrier, max_over_ranks, lib):
                          lambda: None, 10, barrier, max_over_ranks)
     out["all_queries_2digit"] = {"workload": "all 19 sums per row (worlds @ w_q fused, worlds not materialised)",
                                  "rows_per_gpu": B2, "kernel_family": _lib.last_kernel(), "ms": a_ms,
-                                 "bytes_per_row": 80 + 76, "GBs": B2 * 156 / a_ms / 1e6,
+                                 "bytes_per_row": 80 + 76, "GBs": B2 * 156 / a_ms / 1e6, "frac": B2 * 156 / a_ms / 1e6 / peak,
                                  "rows_per_sec": world * B2 / (a_ms * 1e-3)}
     return out
 

@@ -422,23 +422,29 @@ __global__ void __launch_bounds__(256) ad2_backward_kernel(const Ad2Params P) {
 // all query nodes at once: queries_all[b, q] = sum over the member worlds of q, in world order
 // (the worlds[B,W] @ w_q[W,Q] mask contraction of utils/mnist_utils/metrics.py:71-75 and
 // compute_query, models/vael.py:200-206, fused after the product level: the worlds never leave the SM).
-// One warp per 32-row tile, lane <-> row.  The W products of the tile live in shared memory WORLD-major
-// (ws[w][lane]: every access is 32 consecutive words, conflict-free), plus one all-zero row the padded
-// member lists point at.  The member lists (byte offsets of world rows, padded to multiples of four) are
-// fetched 128 bits at a time and four queries are folded side by side: four independent FADD chains per
-// lane, each sequential in world order, so the result is bit-exact against the CSR fold.  The [32,Q]
-// result tile is contiguous in global memory.
+// One warp per 32-row tile, lane <-> row (round 2: no world-major tile of all W products any more).  A query is the
+// sum of its member worlds' products p1[i] p2[k]; only the MEMBERS are formed — Mario's five queries hold 48 of the
+// 81 worlds' products between them, the 81 STS + gathers of the first version become 2 gathers per member.  The
+// facts tile arrives by one bulk copy per tile (WarpTileLoader), the lane's row is re-laid column-major
+// (ps[c][lane], plus an all-zero row for the list padding) so that "p of column c", c a warp-uniform table entry,
+// is one conflict-free LDS.  Member lists: per member the two byte offsets {i * 128, (NA + k) * 128}, padded per
+// query to a multiple of four with the zero row, staged in shared memory once per CTA and fetched 128 bits at a
+// time (broadcast); up to four queries are folded side by side — independent FADD chains, each sequential in
+// world order with __fmul_rn / __fadd_rn: bit-exact against the CSR fold.  The [32,Q] result tile leaves by one
+// bulk store.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float q_lds(uint32_t a) {
   float x;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(a));
   return x;
 }
-__device__ __forceinline__ void q_sts(uint32_t a, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); }
 
+constexpr int kQStages = 2;
 template <int NA, int NB>
-constexpr int queries_per_warp_bytes(int Q) {
-  return Ad2Shape<NA, NB>::FACT_BYTES + (Ad2Shape<NA, NB>::W + 1) * kWarp * 4 + ((kWarp * Q * 4 + 127) / 128) * 128;
+__host__ __device__ constexpr int queries_per_warp_bytes(int Q) {
+  // [barriers 128][facts stages][ps (F+1) x 32][result stages 32 x Q]
+  return 128 + kQStages * Ad2Shape<NA, NB>::FACT_BYTES + ((Ad2Shape<NA, NB>::F + 1) * kWarp * 4 + 127) / 128 * 128 +
+         kQStages * ((kWarp * Q * 4 + 127) / 128 * 128);
 }
 
 template <int NA, int NB, bool NORM>
@@ -449,48 +455,53 @@ __global__ void __launch_bounds__(256) ad2_queries_kernel(const Ad2QParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int Q = P.n_queries;
   const int per_warp = queries_per_warp_bytes<NA, NB>(Q);
-  float* fs = reinterpret_cast<float*>(smem + (size_t)warp * per_warp);                               // [32][F]
-  float* ws = reinterpret_cast<float*>(smem + (size_t)warp * per_warp + Sh::FACT_BYTES);               // [W + 1][32]
-  float* qs = reinterpret_cast<float*>(smem + (size_t)warp * per_warp + Sh::FACT_BYTES + (W + 1) * kWarp * 4);  // [32][Q]
-  const uint32_t wl = smem_u32(ws) + lane * 4;
-  q_sts(wl + W * 128, 0.0f);   // the zero row (written once)
-  // the member lists live in shared memory too (a few hundred bytes): the streaming fact loads would keep
-  // evicting them from L1 and every list fetch would pay an L2 round trip
+  const int qbytes = (kWarp * Q * 4 + 127) / 128 * 128;
+  uint8_t* wb = smem + (size_t)warp * per_warp;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wb);
+  float* fstage = reinterpret_cast<float*>(wb + 128);
+  float* ps = reinterpret_cast<float*>(wb + 128 + kQStages * Sh::FACT_BYTES);                          // [F+1][32]
+  float* qstage = reinterpret_cast<float*>(wb + 128 + kQStages * Sh::FACT_BYTES + ((F + 1) * kWarp * 4 + 127) / 128 * 128);
+  // member tables (a few hundred bytes), shared by the CTA
   int32_t* tab_ptr = reinterpret_cast<int32_t*>(smem + (size_t)nwarps * per_warp);   // [Q + 1], 16-byte aligned
-  int32_t* tab_idx = tab_ptr + ((Q + 1 + 3) & ~3);                                   // [qm_len]
+  int2* tab_off = reinterpret_cast<int2*>(tab_ptr + ((Q + 1 + 3) & ~3));             // [qm_len] {off p1, off p2}
   for (int i = threadIdx.x; i <= Q; i += blockDim.x) tab_ptr[i] = __ldg(P.qm_ptr + i);
-  for (int i = threadIdx.x; i < P.qm_len; i += blockDim.x) tab_idx[i] = __ldg(P.qm_idx + i);
+  for (int i = threadIdx.x; i < P.qm_len; i += blockDim.x) {
+    const int w = __ldg(P.qm_idx + i) >> 7;   // the host table holds world * 128; W = the padding entry
+    tab_off[i] = (w >= W) ? make_int2(F * 128, F * 128) : make_int2((w / NB) * 128, (NA + w % NB) * 128);
+  }
   __syncthreads();
 
   const long long n_sub = (P.B + kWarp - 1) / kWarp;
   const long long gw = (long long)blockIdx.x * nwarps + warp;
   const long long GW = (long long)gridDim.x * nwarps;
-  // the next tile's facts are requested one iteration ahead (coalesced, F registers per lane) so that the HBM
-  // latency of the load hides behind the current tile's folds
-  float nx[F];
-  auto fetch = [&](long long sub) {
-    const long long r0 = sub * kWarp;
-    const int n = (sub < n_sub) ? (int)min((long long)kWarp, P.B - r0) * F : 0;
-    const float* src = P.facts + r0 * F;
-#pragma unroll
-    for (int k = 0; k < F; ++k) nx[k] = (k * kWarp + lane < n) ? __ldg(src + k * kWarp + lane) : 0.5f;
+  if (gw >= n_sub) return;
+  const bool in_al = aligned16(P.facts), out_al = aligned16(P.queries_all) && ((kWarp * Q * 4) % 16 == 0);
+  WarpTileLoader<kQStages> ld;
+  ld.init(fstage, bars, Sh::FACT_BYTES / 4, lane);
+  auto request = [&](long long sub, int s) {
+    if (sub < n_sub) ld.issue(s, P.facts + sub * kWarp * F, (int)min((long long)kWarp, P.B - sub * kWarp) * F, in_al, lane, 0.5f);
   };
-  fetch(gw);
-  for (long long sub = gw; sub < n_sub; sub += GW) {
-    const long long row0 = sub * kWarp;
-    const int rows = (int)min((long long)kWarp, P.B - row0);
-    __syncwarp();
 #pragma unroll
-    for (int k = 0; k < F; ++k) fs[k * kWarp + lane] = nx[k];
-    __syncwarp();
-    fetch(sub + GW);
+  for (int s = 0; s < kQStages; ++s) request(gw + s * GW, s);
+  ps[F * kWarp + lane] = 0.0f;   // the zero row (written once)
+  const uint32_t pl = smem_u32(ps) + lane * 4;
+  long long it = 0;
+  for (long long sub = gw; sub < n_sub; sub += GW, ++it) {
+    const int s = (int)(it % kQStages);
+    const int rows = (int)min((long long)kWarp, P.B - sub * kWarp);
+    ld.wait(s);
     float p[F];
 #pragma unroll
-    for (int c = 0; c < F / FV; ++c) lds_vec<FV>(p + c * FV, fs + lane * F + c * FV);
+    for (int c = 0; c < F / FV; ++c) lds_vec<FV>(p + c * FV, ld.stage(s) + lane * F + c * FV);
+    __syncwarp();
+    request(sub + kQStages * GW, s);
+#pragma unroll
+    for (int c = 0; c < F; ++c) ps[c * kWarp + lane] = p[c];
     float z = 1.0f;
     if constexpr (NORM) z = ad2_normaliser<NA, NB>(p);
-#pragma unroll
-    for (int w = 0; w < W; ++w) q_sts(wl + w * 128, __fmul_rn(p[w / NB], p[NA + (w % NB)]));
+    if (lane == 0) bulk_wait_read<kQStages - 1>();   // the store of kQStages tiles ago has read its stage
+    __syncwarp();
+    float* qs = qstage + s * (qbytes / 4);
     for (int q = 0; q < Q; q += 4) {
       int b[4], n[4];
       int nmax = 0;
@@ -498,7 +509,7 @@ __global__ void __launch_bounds__(256) ad2_queries_kernel(const Ad2QParams P) {
       for (int u = 0; u < 4; ++u) {
         const int qq = min(q + u, Q - 1);
         b[u] = tab_ptr[qq];
-        n[u] = tab_ptr[qq + 1] - b[u];
+        n[u] = (q + u < Q) ? tab_ptr[qq + 1] - b[u] : 0;   // a group past the last query folds nothing
         nmax = max(nmax, n[u]);
       }
       float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -506,8 +517,12 @@ __global__ void __launch_bounds__(256) ad2_queries_kernel(const Ad2QParams P) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           if (e < n[u]) {
-            const int4 o = *reinterpret_cast<const int4*>(tab_idx + b[u] + e);
-            const float v0 = q_lds(wl + o.x), v1 = q_lds(wl + o.y), v2 = q_lds(wl + o.z), v3 = q_lds(wl + o.w);
+            const int4 o01 = *reinterpret_cast<const int4*>(tab_off + b[u] + e);
+            const int4 o23 = *reinterpret_cast<const int4*>(tab_off + b[u] + e + 2);
+            const float v0 = __fmul_rn(q_lds(pl + o01.x), q_lds(pl + o01.y));
+            const float v1 = __fmul_rn(q_lds(pl + o01.z), q_lds(pl + o01.w));
+            const float v2 = __fmul_rn(q_lds(pl + o23.x), q_lds(pl + o23.y));
+            const float v3 = __fmul_rn(q_lds(pl + o23.z), q_lds(pl + o23.w));
             acc[u] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc[u], v0), v1), v2), v3);
           }
         }
@@ -516,10 +531,11 @@ __global__ void __launch_bounds__(256) ad2_queries_kernel(const Ad2QParams P) {
       for (int u = 0; u < 4; ++u)
         if (q + u < Q) qs[lane * Q + q + u] = NORM ? acc[u] / z : acc[u];
     }
+    fence_proxy_async();
     __syncwarp();
-    float* dst = P.queries_all + row0 * Q;
-    for (int i = lane; i < rows * Q; i += kWarp) dst[i] = qs[i];
+    warp_tile_store(P.queries_all + sub * kWarp * Q, qs, rows * Q, kWarp * Q, out_al, lane);
   }
+  if (lane == 0) bulk_wait_all<0>();
 }
 
 // Addition-shaped queries (the MNIST-addition task itself: query s holds exactly the worlds (j, k) with j + k = s,
@@ -670,11 +686,12 @@ static cudaError_t launch_queries(const Ad2QParams& P, bool norm, int num_sms, c
   int nw = 8;
   while (nw > 1 && nw * per_warp > 110 * 1024) --nw;  // two CTAs per SM
   auto kern = norm ? ad2_queries_kernel<NA, NB, true> : ad2_queries_kernel<NA, NB, false>;
-  const int smem_bytes = nw * per_warp + (((P.n_queries + 1 + 3) & ~3) + P.qm_len) * 4;
+  const int smem_bytes = nw * per_warp + ((P.n_queries + 1 + 3) & ~3) * 4 + P.qm_len * 8;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return e;
   const long long n_sub = (P.B + kWarp - 1) / kWarp;
-  const long long grid = min((n_sub + nw - 1) / nw, (long long)num_sms * 2);
+  const int ctas_per_sm = max(1, min(8, (227 * 1024) / (smem_bytes + 1024)));
+  const long long grid = min((n_sub + nw - 1) / nw, (long long)num_sms * ctas_per_sm);
   kern<<<(unsigned)grid, nw * 32, smem_bytes, st>>>(P);
   return cudaGetLastError();
 }

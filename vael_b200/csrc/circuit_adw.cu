@@ -635,21 +635,29 @@ __global__ void __launch_bounds__(256) adw_queries_diag_kernel(const float* __re
     }
     float z = 1.0f;
     if constexpr (NORM) z = adw_normaliser<NP, NA, NB>(p, p + NP, p + NP + NA);
-    float ab[NP * NA];   // the pair products the left-deep world products share
+    // Two-stage contraction (round 2): bc[t] = sum_{j+k=t} p2[j] p3[k] (NA NB FMAs), then query s =
+    // sum_i p1[i] bc[s-i] (<= NP FMAs each) — 100 + 190 FMAs per row instead of the 100 + 2 x 1000 of folding every
+    // world product (p1[i] p2[j]) p3[k] in world order.  Same terms, other association and order: agrees with the
+    // CSR fold (the generic kernel, the oracle) to a few ulp; the test bar is 1e-6 relative, the north star's 1e-5.
+    float bc[NA + NB - 1];
 #pragma unroll
-    for (int i = 0; i < NP; ++i)
+    for (int t = 0; t < NA + NB - 1; ++t) {
+      float acc = 0.0f;
 #pragma unroll
-      for (int j = 0; j < NA; ++j) ab[i * NA + j] = __fmul_rn(p[i], p[NP + j]);
+      for (int j = 0; j < NA; ++j) {
+        const int k = t - j;
+        if (k >= 0 && k < NB) acc = fmaf(p[NP + j], p[NP + NA + (k >= 0 && k < NB ? k : 0)], acc);
+      }
+      bc[t] = acc;
+    }
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
       float acc = 0.0f;
 #pragma unroll
-      for (int i = 0; i < NP; ++i)
-#pragma unroll
-        for (int j = 0; j < NA; ++j) {
-          const int k = q - i - j;
-          if (k >= 0 && k < NB) acc = __fadd_rn(acc, __fmul_rn(ab[i * NA + j], p[NP + NA + (k >= 0 && k < NB ? k : 0)]));
-        }
+      for (int i = 0; i < NP; ++i) {
+        const int t = q - i;
+        if (t >= 0 && t < NA + NB - 1) acc = fmaf(p[i], bc[(t >= 0 && t < NA + NB - 1) ? t : 0], acc);
+      }
       qs[lane * Q + q] = NORM ? acc / z : acc;
     }
     __syncwarp();

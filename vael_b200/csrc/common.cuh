@@ -93,6 +93,71 @@ __device__ __forceinline__ void bulk_wait_all() {
 // order this thread's generic-proxy shared-memory writes before later async-proxy reads
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- warp-private tile pipeline ----------------------------------------------
+// A ring of S shared-memory stages owned by ONE warp and fed by 1-D bulk copies: a [32, K] tile of a row-major
+// [B, K] tensor is one contiguous span of global memory, so a tile is a single cp.async.bulk (SASS UBLKCP) issued by
+// lane 0 and completing on the stage's mbarrier — no LSU traffic, no per-lane address arithmetic.  Tails
+// (fewer than 32 rows with a byte count that is not a multiple of 16) and unaligned bases take a plain coalesced
+// copy by the whole warp.  All methods are called by the whole warp (converged).
+template <int S>
+struct WarpTileLoader {
+  float* stages;        // S stages of `stage_floats` floats, 128-byte aligned
+  uint64_t* bars;       // S mbarriers
+  int stage_floats;
+  uint32_t phase;       // bit s: parity the next wait on stage s uses
+  uint32_t via_bulk;    // bit s: the in-flight load of stage s went through the bulk engine
+  __device__ __forceinline__ void init(float* st, uint64_t* b, int floats_per_stage, int lane) {
+    stages = st; bars = b; stage_floats = floats_per_stage; phase = 0u; via_bulk = 0u;
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ float* stage(int s) const { return stages + s * stage_floats; }
+  // request `n` floats from `src` into stage s (n <= stage_floats); `fill` pads the stage for tail tiles
+  __device__ __forceinline__ void issue(int s, const float* src, int n, bool base_aligned, int lane, float fill) {
+    float* dst = stage(s);
+    const uint32_t bytes = (uint32_t)n * 4u;
+    if (base_aligned && (bytes & 15u) == 0u && n > 0) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&bars[s], bytes);
+        bulk_g2s(dst, src, bytes, &bars[s]);
+      }
+      if (n < stage_floats)
+        for (int i = n + lane; i < stage_floats; i += 32) dst[i] = fill;
+      via_bulk |= 1u << s;
+    } else {
+      for (int i = lane; i < stage_floats; i += 32) dst[i] = (i < n) ? __ldg(src + i) : fill;
+      via_bulk &= ~(1u << s);
+    }
+  }
+  __device__ __forceinline__ void wait(int s) {
+    if (via_bulk & (1u << s)) {
+      mbar_wait(&bars[s], (phase >> s) & 1u);
+      phase ^= 1u << s;
+    }
+    __syncwarp();
+  }
+};
+
+// Row-major [32, K] result tile in shared memory -> global: one bulk store when the tile is whole and aligned
+// (the caller has fenced its generic-proxy writes: fence_proxy_async() by every lane + __syncwarp()), else a plain
+// coalesced copy.  Lane 0 commits a bulk group; bulk_wait_read<N>() before the stage is rewritten.
+__device__ __forceinline__ void warp_tile_store(float* gdst, const float* stage, int n, int n_full, bool base_aligned,
+                                                int lane) {
+  if (base_aligned && n == n_full) {
+    if (lane == 0) {
+      bulk_s2g(gdst, stage, (uint32_t)n * 4u);
+      bulk_commit();
+    }
+  } else {
+    for (int i = lane; i < n; i += 32) gdst[i] = stage[i];
+    if (lane == 0) bulk_commit();   // keep the group count in step with the bulk path
+  }
+}
+
 __host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 struct GenProgram;

@@ -7,12 +7,35 @@ no fallback path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple, Union
 
 import torch
 
 from . import _lib
 from .circuit import FLAG_CHECK_QUERY, FLAG_EVIDENCE, FLAG_FORCE_GENERIC, FLAG_NORMALIZE, Circuit
+
+
+# NVTX ranges around every library call (tracing), for `ncu --nvtx --nvtx-include "vael/..."` and
+# timeline tools.  Off by default (two host calls per op matter in the launch-bound B = 32 eager step);
+# VAEL_NVTX=1 switches them on.
+_NVTX = os.environ.get("VAEL_NVTX", "0") not in ("", "0")
+
+
+class _nvtx:
+    __slots__ = ("name",)
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push("vael/" + self.name)
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 def _stream_ptr() -> C.c_void_p:
@@ -101,7 +124,7 @@ class _CircuitFunction(torch.autograd.Function):
         f2 = _require_cuda_f32(facts, "facts").reshape(B, dc.n_facts)
         worlds = torch.empty((B, dc.n_worlds), device=f2.device, dtype=torch.float32) if want_worlds else None
         query = torch.empty((B, 1), device=f2.device, dtype=torch.float32) if want_query else None
-        with torch.cuda.device(f2.device):
+        with torch.cuda.device(f2.device), _nvtx("circuit_forward"):
             _lib.check(dc.lib.vael_circuit_forward(dc.handle, _p(f2), _p(qidx), qscalar, B, _p(worlds), _p(query),
                                                    flags, _stream_ptr()))
         ctx.dc, ctx.qscalar, ctx.flags, ctx.shape = dc, qscalar, flags, facts.shape
@@ -116,7 +139,7 @@ class _CircuitFunction(torch.autograd.Function):
         gw = g_worlds.contiguous().float() if (g_worlds is not None and g_worlds.numel()) else None
         gq = g_query.contiguous().float().reshape(-1) if (g_query is not None and g_query.numel()) else None
         gf = torch.empty_like(f2)
-        with torch.cuda.device(f2.device):
+        with torch.cuda.device(f2.device), _nvtx("circuit_backward"):
             _lib.check(dc.lib.vael_circuit_backward(dc.handle, _p(f2), _p(qidx), ctx.qscalar, B, _p(gw), _p(gq),
                                                     _p(gf), ctx.flags & ~(FLAG_EVIDENCE | FLAG_CHECK_QUERY), _stream_ptr()))
         return gf.reshape(ctx.shape), None, None, None, None, None, None
@@ -149,7 +172,7 @@ def circuit_queries_all(dc: DeviceCircuit, facts: torch.Tensor, *, normalize: bo
     utils/mnist_utils/metrics.py:71-75).  Evaluation-only."""
     f2 = _require_cuda_f32(facts.detach(), "facts").reshape(facts.shape[0], dc.n_facts)
     out = torch.empty((f2.shape[0], dc.n_queries), device=f2.device, dtype=torch.float32)
-    with torch.cuda.device(f2.device):
+    with torch.cuda.device(f2.device), _nvtx("queries_all"):
         _lib.check(dc.lib.vael_circuit_queries_all(dc.handle, _p(f2), f2.shape[0], _p(out),
                                                    (FLAG_NORMALIZE if normalize else 0) |
                                                    (FLAG_FORCE_GENERIC if force_generic else 0), _stream_ptr()))
@@ -165,7 +188,7 @@ class _FactsFunction(torch.autograd.Function):
         group = x.shape[1] // n_groups
         out = torch.empty_like(x)
         lib = _lib.load()
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _nvtx("facts_forward"):
             if clip_hi > 0.0:
                 _lib.check(lib.vael_facts_clip_forward(_p(x), B, n_groups, group, eps, clip_hi, _p(out), _stream_ptr()))
             else:
@@ -180,7 +203,7 @@ class _FactsFunction(torch.autograd.Function):
         g = g.contiguous().float()
         gx = torch.empty_like(x)
         lib = _lib.load()
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _nvtx("facts_backward"):
             if ctx.clip_hi > 0.0:
                 _lib.check(lib.vael_facts_clip_backward(_p(x), _p(g), x.shape[0], ctx.n_groups, ctx.group, ctx.eps,
                                                         ctx.clip_hi, _p(gx), _stream_ptr()))
@@ -223,7 +246,7 @@ class _GumbelFunction(torch.autograd.Function):
         idx = torch.empty((B,), device=s.device, dtype=torch.int32)
         world_h = torch.empty((B, H), device=s.device, dtype=torch.float32)
         lib = _lib.load()
-        with torch.cuda.device(s.device):
+        with torch.cuda.device(s.device), _nvtx("gumbel_forward"):
             _lib.check(lib.vael_gumbel_world_forward(_p(s), _p(nz), seed, B, W, int(is_log), tau, _p(hb), H,
                                                      _p(y_soft), _p(idx), _p(world_h), _stream_ptr()))
         ctx.save_for_backward(s, y_soft, hb)
@@ -237,7 +260,7 @@ class _GumbelFunction(torch.autograd.Function):
         g = g_world_h.contiguous().float()
         gs = torch.empty_like(s)
         lib = _lib.load()
-        with torch.cuda.device(s.device):
+        with torch.cuda.device(s.device), _nvtx("gumbel_backward"):
             _lib.check(lib.vael_gumbel_world_backward(_p(s), _p(y_soft), _p(g), s.shape[0], s.shape[1],
                                                       int(ctx.is_log), ctx.tau, _p(hb), hb.shape[1], _p(gs),
                                                       _stream_ptr()))
@@ -273,7 +296,7 @@ class _FusedLogicFunction(torch.autograd.Function):
         world_h = torch.empty_like(x)
         y_soft = torch.empty((B, W), device=x.device, dtype=torch.float32) if want_y_soft else None
         has_q = qidx is not None or qscalar >= 0
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _nvtx("logic_train_forward"):
             _lib.check(dc.lib.vael_logic_train_forward(dc.handle, _p(x), _p(qidx), qscalar, B, eps, tau, _p(nz), seed,
                                                        _p(seed_dev), _p(facts), _p(query) if has_q else None, _p(idx),
                                                        _p(world_h), _p(y_soft), _stream_ptr()))
@@ -298,7 +321,7 @@ class _FusedLogicFunction(torch.autograd.Function):
         gf, gq, gh = c(g_facts), c(g_query), c(g_world_h)
         gq = gq.reshape(-1) if (gq is not None and ctx.has_q) else None
         gx = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _nvtx("logic_train_backward"):
             _lib.check(dc.lib.vael_logic_train_backward(dc.handle, _p(x), _p(qidx), ctx.qscalar, x.shape[0], ctx.eps,
                                                         ctx.tau, _p(nz), ctx.seed, _p(seed_dev), _p(gh), _p(gq), _p(gf),
                                                         _p(gx), _stream_ptr()))
@@ -353,7 +376,7 @@ class _ElboFunction(torch.autograd.Function):
         # caching allocator, zeroed on this stream), so calls on different streams / models / graph replays
         # overlapping eager work never share one
         ws = torch.zeros(int(lib.vael_elbo_workspace_bytes()), dtype=torch.uint8, device=r.device)
-        with torch.cuda.device(r.device):
+        with torch.cuda.device(r.device), _nvtx("elbo_terms"):
             _lib.check(lib.vael_elbo_terms(_p(r), _p(xx), B, D, _p(m), _p(lv), m.shape[1], _p(q), recon_w, kl_w,
                                            query_w, rec_loss, _p(terms), _p(g_r), _p(g_m), _p(g_lv), _p(g_q),
                                            _p(ws), _stream_ptr()))
