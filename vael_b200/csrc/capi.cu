@@ -337,6 +337,41 @@ extern "C" int vael_circuit_create(const vael_circuit_desc_t* d, vael_circuit_t*
     if (qm_idx.empty()) qm_idx.assign(4, d->n_worlds * 128);
     up(&c->d_qm_ptr, qm_ptr); up(&c->d_qm_idx, qm_idx);
     c->qm_len = (int32_t)qm_idx.size();
+    // the same lists in the form the two-AD all-queries kernel takes in its parameter block: grouped by the
+    // first AD's value i, `len[q]` slots per (q, i) (circuit_ad2.cu: ad2_queries_kernel)
+    c->q_members_ok = false;
+    if (c->fast_kind == 2 && d->n_queries <= kQMaxQueries) {
+      const int NA = c->ad_na, NB = c->ad_nb;
+      std::vector<uint16_t> slots;
+      bool fits = true;
+      for (int q = 0; q < d->n_queries && fits; ++q) {
+        int L = 0;
+        for (int i = 0; i < NA; ++i) {
+          int n = 0;
+          for (int k = 0; k < NB; ++k) {
+            const int w = i * NB + k;
+            n += (qmask[(size_t)q * c->mask_words + (w >> 5)] >> (w & 31)) & 1u;
+          }
+          L = std::max(L, n);
+        }
+        c->q_ptr[q] = (uint16_t)slots.size();
+        c->q_len[q] = (uint8_t)L;
+        for (int i = 0; i < NA; ++i) {
+          int n = 0;
+          for (int k = 0; k < NB; ++k) {
+            const int w = i * NB + k;
+            if ((qmask[(size_t)q * c->mask_words + (w >> 5)] >> (w & 31)) & 1u) { slots.push_back((uint16_t)(k * 128)); ++n; }
+          }
+          for (; n < L; ++n) slots.push_back((uint16_t)(NB * 128));
+        }
+        fits = slots.size() <= (size_t)kQMaxSlots;
+      }
+      if (fits) {
+        memcpy(c->q_slot, slots.data(), slots.size() * sizeof(uint16_t));
+        c->q_nslots = (int32_t)slots.size();
+        c->q_members_ok = true;
+      }
+    }
     // addition-shaped queries over a two-AD outer product: query s = { (j, k) : j + k = s }
     c->queries_diagonal = false;
     if (c->fast_kind == 3 && d->n_queries == c->ad_np + c->ad_na + c->ad_nb - 2) {
@@ -480,11 +515,16 @@ extern "C" int vael_circuit_queries_all(const vael_circuit_t* c, const float* fa
   if (flags & VAEL_FLAG_EVIDENCE) return fail(VAEL_E_INVALID, "EVIDENCE is meaningless for queries_all");
   if (B == 0) return VAEL_OK;
   if (!queries_all) return fail(VAEL_E_INVALID, "null output");
-  if (pick_kernel(c, flags, nullptr) == 2 && c->n_queries <= 64) {
+  if (pick_kernel(c, flags, nullptr) == 2 && c->n_queries <= kQMaxQueries && (c->queries_diagonal || c->q_members_ok)) {
     Ad2QParams P{};
-    P.facts = facts; P.B = B; P.n_queries = c->n_queries; P.qm_ptr = c->d_qm_ptr; P.qm_idx = c->d_qm_idx; P.qm_len = c->qm_len;
+    P.facts = facts; P.B = B; P.n_queries = c->n_queries;
     P.diagonal = c->queries_diagonal ? 1 : 0;
     P.queries_all = queries_all;
+    if (!c->queries_diagonal) {
+      memcpy(P.ptr, c->q_ptr, sizeof(P.ptr));
+      memcpy(P.len, c->q_len, sizeof(P.len));
+      memcpy(P.slot, c->q_slot, sizeof(uint16_t) * c->q_nslots);
+    }
     CK(ad2_queries_all(c->ad_na, c->ad_nb, P, flags & VAEL_FLAG_NORMALIZE, c->num_sms, static_cast<cudaStream_t>(stream)));
     g_last_kernel = "ad2-queries";
     g_launches++;

@@ -15,6 +15,8 @@
 // so each transfer is a single bulk copy; lanes touch shared memory with
 // conflict-free 128-bit accesses (row strides 80 B / 400 B land 8 consecutive
 // lanes on 8 distinct 16-byte bank groups).  There is no block-level barrier.
+#include <type_traits>
+
 #include "params.cuh"
 
 namespace vael {
@@ -424,14 +426,16 @@ __global__ void __launch_bounds__(256) ad2_backward_kernel(const Ad2Params P) {
 // compute_query, models/vael.py:200-206, fused after the product level: the worlds never leave the SM).
 // One warp per 32-row tile, lane <-> row (round 2: no world-major tile of all W products any more).  A query is the
 // sum of its member worlds' products p1[i] p2[k]; only the MEMBERS are formed — Mario's five queries hold 48 of the
-// 81 worlds' products between them, the 81 STS + gathers of the first version become 2 gathers per member.  The
-// facts tile arrives by one bulk copy per tile (WarpTileLoader), the lane's row is re-laid column-major
-// (ps[c][lane], plus an all-zero row for the list padding) so that "p of column c", c a warp-uniform table entry,
-// is one conflict-free LDS.  Member lists: per member the two byte offsets {i * 128, (NA + k) * 128}, padded per
-// query to a multiple of four with the zero row, staged in shared memory once per CTA and fetched 128 bits at a
-// time (broadcast); up to four queries are folded side by side — independent FADD chains, each sequential in
-// world order with __fmul_rn / __fadd_rn: bit-exact against the CSR fold.  The [32,Q] result tile leaves by one
-// bulk store.
+// 81 worlds' products between them.  World order is i-major, so the fold runs over i = 0 .. NA-1 as a COMPILE-TIME
+// loop (p1[i] is a register operand) and, per (query, i), over that pair's k's: ONE shared-memory gather per member,
+// from a column-major tile of the lane's p2 values (p2s[k][lane], plus an all-zero row for the padding) where "p2 of
+// column k", k a warp-uniform table entry, is one conflict-free LDS.  The table — per (query, i) `len[q]` byte
+// offsets, padded with the zero row — sits in the kernel's PARAMETER block (constant bank): its warp-uniform
+// fetches cost no shared-memory wavefront, which together with instruction issue is what bounds this kernel
+// (profiles/r02d_queries_ncu.md: the first round-2 version, both literals gathered and the table in shared memory,
+// spent 251 wavefronts per tile).  The facts tile arrives by one bulk copy per tile (WarpTileLoader), the [32,Q]
+// result tile leaves by one bulk store.  Every fold is sequential in world order with __fmul_rn / __fadd_rn
+// (padding adds p1[i] * 0 = +0): bit-exact against the CSR fold.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float q_lds(uint32_t a) {
   float x;
@@ -442,15 +446,15 @@ __device__ __forceinline__ float q_lds(uint32_t a) {
 constexpr int kQStages = 2;
 template <int NA, int NB>
 __host__ __device__ constexpr int queries_per_warp_bytes(int Q) {
-  // [barriers 128][facts stages][ps (F+1) x 32][result stages 32 x Q]
-  return 128 + kQStages * Ad2Shape<NA, NB>::FACT_BYTES + ((Ad2Shape<NA, NB>::F + 1) * kWarp * 4 + 127) / 128 * 128 +
+  // [barriers 128][facts stages][p2s (NB+1) x 32][result stages 32 x Q]
+  return 128 + kQStages * Ad2Shape<NA, NB>::FACT_BYTES + ((NB + 1) * kWarp * 4 + 127) / 128 * 128 +
          kQStages * ((kWarp * Q * 4 + 127) / 128 * 128);
 }
 
 template <int NA, int NB, bool NORM>
 __global__ void __launch_bounds__(256) ad2_queries_kernel(const Ad2QParams P) {
   using Sh = Ad2Shape<NA, NB>;
-  constexpr int F = Sh::F, W = Sh::W, FV = Sh::FV;
+  constexpr int F = Sh::F, FV = Sh::FV;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int Q = P.n_queries;
@@ -459,18 +463,8 @@ __global__ void __launch_bounds__(256) ad2_queries_kernel(const Ad2QParams P) {
   uint8_t* wb = smem + (size_t)warp * per_warp;
   uint64_t* bars = reinterpret_cast<uint64_t*>(wb);
   float* fstage = reinterpret_cast<float*>(wb + 128);
-  float* ps = reinterpret_cast<float*>(wb + 128 + kQStages * Sh::FACT_BYTES);                          // [F+1][32]
-  float* qstage = reinterpret_cast<float*>(wb + 128 + kQStages * Sh::FACT_BYTES + ((F + 1) * kWarp * 4 + 127) / 128 * 128);
-  // member tables (a few hundred bytes), shared by the CTA
-  int32_t* tab_ptr = reinterpret_cast<int32_t*>(smem + (size_t)nwarps * per_warp);   // [Q + 1], 16-byte aligned
-  int2* tab_off = reinterpret_cast<int2*>(tab_ptr + ((Q + 1 + 3) & ~3));             // [qm_len] {off p1, off p2}
-  for (int i = threadIdx.x; i <= Q; i += blockDim.x) tab_ptr[i] = __ldg(P.qm_ptr + i);
-  for (int i = threadIdx.x; i < P.qm_len; i += blockDim.x) {
-    const int w = __ldg(P.qm_idx + i) >> 7;   // the host table holds world * 128; W = the padding entry
-    tab_off[i] = (w >= W) ? make_int2(F * 128, F * 128) : make_int2((w / NB) * 128, (NA + w % NB) * 128);
-  }
-  __syncthreads();
-
+  float* p2s = reinterpret_cast<float*>(wb + 128 + kQStages * Sh::FACT_BYTES);                          // [NB+1][32]
+  float* qstage = reinterpret_cast<float*>(wb + 128 + kQStages * Sh::FACT_BYTES + ((NB + 1) * kWarp * 4 + 127) / 128 * 128);
   const long long n_sub = (P.B + kWarp - 1) / kWarp;
   const long long gw = (long long)blockIdx.x * nwarps + warp;
   const long long GW = (long long)gridDim.x * nwarps;
@@ -483,8 +477,8 @@ __global__ void __launch_bounds__(256) ad2_queries_kernel(const Ad2QParams P) {
   };
 #pragma unroll
   for (int s = 0; s < kQStages; ++s) request(gw + s * GW, s);
-  ps[F * kWarp + lane] = 0.0f;   // the zero row (written once)
-  const uint32_t pl = smem_u32(ps) + lane * 4;
+  p2s[NB * kWarp + lane] = 0.0f;   // the zero row (written once)
+  const uint32_t pl = smem_u32(p2s) + lane * 4;
   long long it = 0;
   for (long long sub = gw; sub < n_sub; sub += GW, ++it) {
     const int s = (int)(it % kQStages);
@@ -496,40 +490,36 @@ __global__ void __launch_bounds__(256) ad2_queries_kernel(const Ad2QParams P) {
     __syncwarp();
     request(sub + kQStages * GW, s);
 #pragma unroll
-    for (int c = 0; c < F; ++c) ps[c * kWarp + lane] = p[c];
+    for (int k = 0; k < NB; ++k) p2s[k * kWarp + lane] = p[NA + k];
     float z = 1.0f;
     if constexpr (NORM) z = ad2_normaliser<NA, NB>(p);
     if (lane == 0) bulk_wait_read<kQStages - 1>();   // the store of kQStages tiles ago has read its stage
     __syncwarp();
     float* qs = qstage + s * (qbytes / 4);
-    for (int q = 0; q < Q; q += 4) {
-      int b[4], n[4];
-      int nmax = 0;
+    // slots per (q, i): 1, 2 and 4 are unrolled (all gathers of a query in flight before its add chain starts)
+    auto fold = [&](int t, auto Lc) {
+      constexpr int LL = decltype(Lc)::value;
+      float v[NA * LL];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int qq = min(q + u, Q - 1);
-        b[u] = tab_ptr[qq];
-        n[u] = (q + u < Q) ? tab_ptr[qq + 1] - b[u] : 0;   // a group past the last query folds nothing
-        nmax = max(nmax, n[u]);
+      for (int j = 0; j < NA * LL; ++j) v[j] = q_lds(pl + P.slot[t + j]);
+      float acc = 0.0f;
+#pragma unroll
+      for (int j = 0; j < NA * LL; ++j) acc = __fadd_rn(acc, __fmul_rn(p[j / LL], v[j]));
+      return acc;
+    };
+    for (int q = 0; q < Q; ++q) {
+      const int L = P.len[q];
+      int t = P.ptr[q];
+      float acc = 0.0f;
+      if (L == 1) acc = fold(t, std::integral_constant<int, 1>{});
+      else if (L == 2) acc = fold(t, std::integral_constant<int, 2>{});
+      else if (L == 4) acc = fold(t, std::integral_constant<int, 4>{});
+      else {
+#pragma unroll
+        for (int i = 0; i < NA; ++i)
+          for (int l = 0; l < L; ++l, ++t) acc = __fadd_rn(acc, __fmul_rn(p[i], q_lds(pl + P.slot[t])));
       }
-      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      for (int e = 0; e < nmax; e += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (e < n[u]) {
-            const int4 o01 = *reinterpret_cast<const int4*>(tab_off + b[u] + e);
-            const int4 o23 = *reinterpret_cast<const int4*>(tab_off + b[u] + e + 2);
-            const float v0 = __fmul_rn(q_lds(pl + o01.x), q_lds(pl + o01.y));
-            const float v1 = __fmul_rn(q_lds(pl + o01.z), q_lds(pl + o01.w));
-            const float v2 = __fmul_rn(q_lds(pl + o23.x), q_lds(pl + o23.y));
-            const float v3 = __fmul_rn(q_lds(pl + o23.z), q_lds(pl + o23.w));
-            acc[u] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc[u], v0), v1), v2), v3);
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (q + u < Q) qs[lane * Q + q + u] = NORM ? acc[u] / z : acc[u];
+      qs[lane * Q + q] = NORM ? acc / z : acc;
     }
     fence_proxy_async();
     __syncwarp();
@@ -686,7 +676,7 @@ static cudaError_t launch_queries(const Ad2QParams& P, bool norm, int num_sms, c
   int nw = 8;
   while (nw > 1 && nw * per_warp > 110 * 1024) --nw;  // two CTAs per SM
   auto kern = norm ? ad2_queries_kernel<NA, NB, true> : ad2_queries_kernel<NA, NB, false>;
-  const int smem_bytes = nw * per_warp + ((P.n_queries + 1 + 3) & ~3) * 4 + P.qm_len * 8;
+  const int smem_bytes = nw * per_warp;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return e;
   const long long n_sub = (P.B + kWarp - 1) / kWarp;

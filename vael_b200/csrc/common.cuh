@@ -189,6 +189,11 @@ struct vael_circuit {
   int32_t* d_qm_ptr;         // [n_queries+1] member worlds of every query node (CSR, world order) — set with d_qmask
   int32_t* d_qm_idx;
   int32_t qm_len;
+  bool q_members_ok;         // fast_kind 2: the member lists below fit the all-queries kernel's parameter block
+  uint16_t q_ptr[64];        // first slot of query q
+  uint8_t q_len[64];         // slots per (q, i)
+  uint16_t q_slot[1024];     // byte offset (k * 128) of the second literal's row, or NB * 128 (zero row)
+  int32_t q_nslots;
   uint32_t lt_mask[64];      // fast_kind 4: per world, the fact columns that enter as positive literals
   bool queries_diagonal;     // fast_kind 2: query s = the worlds (j, k) with j + k = s (all-queries register kernel)
   uint32_t* d_qmask_c;       // fast_kind 3: [n_queries][np][ceil(na*nb/32)] chunked membership masks

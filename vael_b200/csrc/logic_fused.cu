@@ -163,7 +163,7 @@ __device__ __forceinline__ void fused_mask(uint32_t* m, const FusedParams& P, lo
 }
 
 template <int N, bool FAST>
-__global__ void __launch_bounds__(128) fused_forward_kernel(const FusedParams P) {
+__global__ void __launch_bounds__(128, FAST ? 6 : 1) fused_forward_kernel(const FusedParams P) {
   constexpr int F = 2 * N, W = N * N, MW = (W + 31) / 32;
   const uint64_t seed = P.seed_dev ? *P.seed_dev : P.seed;
   const float inv_tau = 1.0f / P.tau;
@@ -334,9 +334,9 @@ bool fused_supported(int na, int nb) { return na == nb && (na == 10 || na == 9);
 // one row per thread.  Small batches (the B = 32 .. 4096 training configurations) use one-warp CTAs so that the
 // rows spread over as many SMs as possible — a row is a ~5 k-instruction serial chain; large batches use
 // four-warp CTAs, a few per SM, grid-striding.
-static void fused_shape(long long B, int num_sms, int* grid, int* block) {
+static void fused_shape(long long B, int num_sms, int ctas_per_sm, int* grid, int* block) {
   *block = (B <= (long long)num_sms * 128) ? 32 : 128;
-  *grid = (int)max(1LL, min((B + *block - 1) / *block, (long long)num_sms * 4 * (128 / *block)));
+  *grid = (int)max(1LL, min((B + *block - 1) / *block, (long long)num_sms * ctas_per_sm * (128 / *block)));
 }
 
 // FAST needs bounded (Philox) noise and a tau that keeps the softmax terms inside fp32's range; y_soft is a
@@ -366,13 +366,15 @@ static cudaError_t fused_launch(int n, const FusedParams& P, int grid, int block
 
 cudaError_t fused_forward(int n, const FusedParams& P, int num_sms, cudaStream_t st) {
   int grid, block;
-  fused_shape(P.B, num_sms, &grid, &block);
-  return fused_fast_ok(P) ? fused_launch<false, true>(n, P, grid, block, st) : fused_launch<false, false>(n, P, grid, block, st);
+  const bool fast = fused_fast_ok(P);
+  fused_shape(P.B, num_sms, fast ? 6 : 3, &grid, &block);   // resident CTAs per SM by registers: 80 / 157
+  return fast ? fused_launch<false, true>(n, P, grid, block, st) : fused_launch<false, false>(n, P, grid, block, st);
 }
 cudaError_t fused_backward(int n, const FusedParams& P, int num_sms, cudaStream_t st) {
   int grid, block;
-  fused_shape(P.B, num_sms, &grid, &block);
-  return fused_fast_ok(P) ? fused_launch<true, true>(n, P, grid, block, st) : fused_launch<true, false>(n, P, grid, block, st);
+  const bool fast = fused_fast_ok(P);
+  fused_shape(P.B, num_sms, fast ? 4 : 2, &grid, &block);   // 128 / 255 registers
+  return fast ? fused_launch<true, true>(n, P, grid, block, st) : fused_launch<true, false>(n, P, grid, block, st);
 }
 
 }  // namespace vael

@@ -21,15 +21,22 @@ struct Ad2Params {
   float* grad_facts;         // [B,F]
   int32_t l2_hint;           // 0 none, 1 = evict_first on the streaming stores, 2 = on loads and stores
 };
+constexpr int kQMaxSlots = 1024;    // (query, first-AD value, slot) entries the all-queries list kernel takes in its parameter block
+constexpr int kQMaxQueries = 64;
 struct Ad2QParams {           // all query nodes at once
   const float* facts;         // [B,F]
   long long B;
   int32_t n_queries;
-  const int32_t* qm_ptr;      // [Q+1] CSR of the member worlds of every query node, in world order; lists padded to x4
-  const int32_t* qm_idx;      // byte offsets (world * 128) into the kernel's world-major tile; padding -> the zero row
-  int32_t qm_len;             // length of qm_idx
   int32_t diagonal;           // query s holds exactly the worlds (j, k) with j + k = s (addition-shaped)
   float* queries_all;         // [B,Q]
+  // Member lists, grouped by the FIRST annotated disjunction's value i (world order = i-major): for query q and
+  // every i, `len[q]` slots holding the byte offset (k * 128) of the second literal's row in the kernel's
+  // column-major p2 tile, padded with the tile's zero row (NB * 128).  p1[i] is a register operand (i is a
+  // compile-time loop index): ONE gather per member.  The table lives in the PARAMETER block (constant bank):
+  // its warp-uniform fetches cost no shared-memory wavefront.
+  uint16_t ptr[kQMaxQueries];     // first slot of query q
+  uint8_t len[kQMaxQueries];      // slots per (q, i)
+  uint16_t slot[kQMaxSlots];
 };
 cudaError_t ad2_queries_all(int na, int nb, const Ad2QParams& P, bool norm, int num_sms, cudaStream_t st);
 bool ad2_supported(int na, int nb);
