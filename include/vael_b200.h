@@ -68,6 +68,8 @@ extern "C" {
 #define VAEL_FLAG_NORMALIZE 1u /* divide every output by the normaliser node Z (GraphSemiring.normalize, :54-55) */
 #define VAEL_FLAG_EVIDENCE 2u  /* condition the worlds on the selected query node: P(w | q) (models/vael.py:119-135) */
 #define VAEL_FLAG_FORCE_GENERIC 4u /* run the generic level-by-level CSR kernel even if a structured fast path exists */
+#define VAEL_FLAG_FORCE_JIT 16u    /* run the circuit-specialised straight-line kernel (compiled with NVRTC on first use)
+                                      even if a structured fast path exists; VAEL_E_UNSUPPORTED when it cannot be built */
 #define VAEL_FLAG_CHECK_QUERY 8u   /* validate the per-row query indices first: any index outside [-1, Q) makes the
                                       call return VAEL_E_INVALID before the circuit kernel is launched (-1 is the
                                       "no query for this row" sentinel: its query value is 0).  The check
@@ -113,7 +115,8 @@ VAEL_API int vael_abi_version(void);
 VAEL_API const char* vael_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 VAEL_API int64_t vael_launch_count(void);
-/* name of the kernel family the last forward/backward used: "ad2-tma", "adw-tma2d", "generic-csr" */
+/* name of the kernel family the last forward/backward used: "ad2-tma", "adw-tma2d", "lt-log", "jit-straightline",
+ * "generic-csr", "logic-fused" */
 VAEL_API const char* vael_last_kernel(void);
 
 /* ---- circuit lifetime ---------------------------------------------------- */
@@ -129,6 +132,16 @@ VAEL_API void vael_circuit_destroy(vael_circuit_t* c);
  * semiring (every world one literal per fact column: MarioVAELModel.admissible_worlds_logprob,
  * models/vael.py:368-375) */
 VAEL_API int vael_circuit_fast_kind(const vael_circuit_t* c);
+/* Circuits without a recognised shape run, when possible, a kernel SPECIALISED to the circuit: the level-ordered CSR
+ * unrolled into straight-line register code (lane <-> row), generated once per circuit, compiled with NVRTC for
+ * sm_100a on first use and loaded through the driver API; the level-by-level CSR interpreter is the fallback (no
+ * libnvrtc, VAEL_JIT=0, log semiring, more than 128 worlds) and stays reachable with VAEL_FLAG_FORCE_GENERIC.
+ * vael_circuit_jit_status compiles now if that has not happened yet and returns 1 when the kernels exist (the NVRTC
+ * log / the reason otherwise is copied to `log`, up to n bytes).  vael_jit_compile_check generates and compiles
+ * the source for a description WITHOUT loading it (works without a GPU): 0 = compiled, 1 = circuit outside the
+ * generator's scope, 2 = NVRTC unavailable, 3 = compile error. */
+VAEL_API int vael_circuit_jit_status(const vael_circuit_t* c, char* log, int32_t n);
+VAEL_API int vael_jit_compile_check(const vael_circuit_desc_t* desc, char* log, int32_t n);
 /* 64-bit FNV-1a hash of the uploaded arrays (bit-exact circuit identity) */
 VAEL_API uint64_t vael_circuit_hash(const vael_circuit_t* c);
 

@@ -15,7 +15,7 @@ from vael_b200.mario_task import admissible_circuit, compile_mario_family, mario
 from vael_b200.mnist_task import compile_addition_family  # noqa: E402
 from vael_b200.ops import DeviceCircuit, _p  # noqa: E402
 
-which = set(sys.argv[1:]) or {"fused", "lt", "gumbel", "facts", "elbo", "generic", "queries"}
+which = set(sys.argv[1:]) or {"fused", "lt", "gumbel", "facts", "elbo", "generic", "queries", "jit"}
 dev = torch.device("cuda", 0)
 lib = _lib.load()
 sp = torch.cuda.current_stream().cuda_stream
@@ -110,4 +110,39 @@ if "generic" in which or "queries" in which:
         p3 = torch.softmax(3.0 * torch.randn(B3, 3, 10, device=dev, generator=g), -1).reshape(B3, 30).contiguous()
         qa3 = torch.empty(B3, 28, device=dev)
         timeit("adw_queries_diag", lambda: ck(lib.vael_circuit_queries_all(dc3.handle, _p(p3), B3, _p(qa3), 0, sp)), B3 * 232)
+if "jit" in which:
+    B = 1 << 21
+    for tag, circ, F, W, Q in (("2digit", compile_addition_family(2, 10).circuit, 20, 100, 19),
+                               ("mario", compile_mario_family((3, 3)).circuit, 18, 81, 5)):
+        dc = DeviceCircuit(circ, dev)
+        ok, log = dc.jit_status()
+        if not ok:
+            out["jit_" + tag] = {"error": log[:300]}
+            continue
+        n = F // 2
+        pr = torch.softmax(3.0 * torch.randn(B, 2, n, device=dev, generator=g), -1) + 1e-5
+        facts = (pr / pr.sum(-1, keepdim=True)).reshape(B, F).contiguous()
+        q = torch.randint(0, min(Q, 4), (B,), device=dev, dtype=torch.int32, generator=g)
+        w, qo, gf = torch.empty(B, W, device=dev), torch.empty(B, device=dev), torch.empty(B, F, device=dev)
+        gw, gq = torch.randn(B, W, device=dev, generator=g), torch.randn(B, device=dev, generator=g)
+        fb, bb = F * 4 + 4 + W * 4 + 4, W * 4 + 4 + F * 4 + 4 + F * 4
+        timeit(f"jit_forward_{tag}", lambda: ck(lib.vael_circuit_forward(dc.handle, _p(facts), _p(q), -1, B, _p(w), _p(qo), 16, sp)), B * fb)
+        timeit(f"jit_backward_{tag}", lambda: ck(lib.vael_circuit_backward(dc.handle, _p(facts), _p(q), -1, B, _p(gw), _p(gq), _p(gf), 16, sp)), B * bb)
+        timeit(f"structured_forward_{tag}", lambda: ck(lib.vael_circuit_forward(dc.handle, _p(facts), _p(q), -1, B, _p(w), _p(qo), 0, sp)), B * fb)
+        timeit(f"structured_backward_{tag}", lambda: ck(lib.vael_circuit_backward(dc.handle, _p(facts), _p(q), -1, B, _p(gw), _p(gq), _p(gf), 0, sp)), B * bb)
+if "jitwide" in which:
+    B = 1 << 19
+    dc = DeviceCircuit(compile_addition_family(3, 10).circuit, dev)
+    ok, log = dc.jit_status()
+    if ok:
+        pr = torch.softmax(3.0 * torch.randn(B, 3, 10, device=dev, generator=g), -1)
+        facts = pr.reshape(B, 30).contiguous()
+        q = torch.randint(0, 28, (B,), device=dev, dtype=torch.int32, generator=g)
+        w, qo, gf = torch.empty(B, 1000, device=dev), torch.empty(B, device=dev), torch.empty(B, 30, device=dev)
+        gw, gq = torch.randn(B, 1000, device=dev, generator=g), torch.randn(B, device=dev, generator=g)
+        for tag, flag in (("jit", 16), ("structured", 0), ("interpreter", 4)):
+            timeit(f"{tag}_forward_3digit", lambda: ck(lib.vael_circuit_forward(dc.handle, _p(facts), _p(q), -1, B, _p(w), _p(qo), flag, sp)), B * 4128)
+            timeit(f"{tag}_backward_3digit", lambda: ck(lib.vael_circuit_backward(dc.handle, _p(facts), _p(q), -1, B, _p(gw), _p(gq), _p(gf), flag, sp)), B * 4248)
+    else:
+        out["jitwide"] = {"error": log[:300]}
 print(json.dumps(out))

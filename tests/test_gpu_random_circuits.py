@@ -1,7 +1,8 @@
-"""Randomised circuits through the generic level-ordered CSR kernels: every node kind (negative literals,
-constants, unary / binary / n-ary products, sums and complements), both semirings, with and without the
-normaliser, ragged batches — forward against the fp32 CSR-order interpreter (bit-exact in the probability
-semiring), adjoint against fp64 autograd through the node-by-node semantics."""
+"""Randomised circuits through the two paths a circuit without a recognised shape can take — the circuit-specialised
+straight-line kernels (generated + NVRTC-compiled per circuit; probability semiring) and the level-ordered CSR
+interpreter: every node kind (negative literals, constants, unary / binary / n-ary products, sums and complements),
+both semirings, with and without the normaliser, ragged batches — forward against the fp32 CSR-order oracle
+(bit-exact in the probability semiring), adjoint against fp64 autograd through the node-by-node semantics."""
 import numpy as np
 import pytest
 import torch
@@ -45,22 +46,29 @@ def random_circuit(seed, log_semiring, n_facts=7, n_levels=4, width=9):
                     world_atoms=[f"w{i}" for i in range(len(worlds))], query_atoms=[f"q{i}" for i in range(5)])
 
 
+@pytest.mark.parametrize("path", ["default", "interpreter"])
 @pytest.mark.parametrize("log_semiring", [False, True])
 @pytest.mark.parametrize("seed", range(6))
-def test_random_circuit_forward_and_adjoint(cuda_device, seed, log_semiring):
+def test_random_circuit_forward_and_adjoint(cuda_device, seed, log_semiring, path):
     from vael_b200 import _lib
-    from vael_b200.ops import DeviceCircuit, circuit_forward
+    from vael_b200.ops import DeviceCircuit, circuit_forward, circuit_queries_all
     circ = random_circuit(seed, log_semiring)
     dc = DeviceCircuit(circ, cuda_device)
     assert dc.fast_kind == 0
+    generic = path == "interpreter"
+    if log_semiring and not generic:
+        pytest.skip("the log semiring always runs the interpreter")
+    jit_ok, why = dc.jit_status()
+    assert jit_ok == (not log_semiring), why
+    kernel = "generic-csr" if (generic or log_semiring) else "jit-straightline"
     rng = np.random.default_rng(100 + seed)
     for B in (1, 33, 200):
         facts = rng.uniform(0.05, 0.95, size=(B, circ.n_facts)).astype(np.float32)
         qi = rng.integers(0, circ.n_queries, size=B)
         for normalize in ([False] if log_semiring else [False, True]):
             f = torch.from_numpy(facts).cuda().requires_grad_(True)
-            w, q = circuit_forward(dc, f, torch.from_numpy(qi).cuda(), normalize=normalize)
-            assert _lib.last_kernel() == "generic-csr"
+            w, q = circuit_forward(dc, f, torch.from_numpy(qi).cuda(), normalize=normalize, force_generic=generic)
+            assert _lib.last_kernel() == kernel
             w_ref, q_ref = fp_interp.forward(circ, facts, query=qi, normalize=normalize)
             if log_semiring:   # logf / expf differ by a few ulp between libm and the device
                 np.testing.assert_allclose(w.detach().cpu().numpy(), w_ref, rtol=2e-5, atol=2e-6)
@@ -75,7 +83,12 @@ def test_random_circuit_forward_and_adjoint(cuda_device, seed, log_semiring):
             w64, q64 = torch_interp.forward(circ, f64, torch.from_numpy(qi), normalize=normalize)
             ((w64 * torch.from_numpy(gw).double()).sum() + (q64 * torch.from_numpy(gq).double()).sum()).backward()
             g_ref = f64.grad.numpy()
+            assert _lib.last_kernel() == kernel
             assert rel_err(f.grad.cpu().numpy(), g_ref, floor=1e-3 * np.abs(g_ref).max() + 1e-12) < 1e-4
+            if not log_semiring:   # every query node of every row, and P(w | query) — same bits on both paths
+                qa = circuit_queries_all(dc, f.detach(), normalize=normalize, force_generic=generic)
+                assert _lib.last_kernel() == kernel
+                np.testing.assert_array_equal(qa.cpu().numpy(), fp_interp.queries_all(circ, facts, normalize=normalize))
 
 
 @pytest.mark.parametrize("env", [{"VAEL_GEN_R": "1"}, {"VAEL_GEN_R": "4"}, {"VAEL_GEN_R": "4", "VAEL_GEN_CTAS": "3"},

@@ -45,6 +45,8 @@ _PROTOTYPES = {
     "vael_circuit_destroy": (None, [_P]),
     "vael_circuit_fast_kind": (C.c_int, [_P]),
     "vael_circuit_hash": (C.c_uint64, [_P]),
+    "vael_circuit_jit_status": (C.c_int, [_P, C.c_char_p, C.c_int32]),
+    "vael_jit_compile_check": (C.c_int, [C.POINTER(CircuitDesc), C.c_char_p, C.c_int32]),
     "vael_circuit_forward": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, _P, _P, C.c_uint32, _P]),
     "vael_circuit_backward": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, _P, _P, _P, C.c_uint32, _P]),
     "vael_circuit_queries_all": (C.c_int, [_P, _P, C.c_int64, _P, C.c_uint32, _P]),

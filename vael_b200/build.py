@@ -13,7 +13,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libvael_b200.so"
-SOURCES = ["capi.cu", "circuit_ad2.cu", "circuit_adw.cu", "circuit_generic.cu", "circuit_lt.cu", "sampling.cu", "logic_fused.cu", "elbo.cu"]
+SOURCES = ["capi.cu", "circuit_ad2.cu", "circuit_adw.cu", "circuit_generic.cu", "circuit_jit.cu", "circuit_lt.cu", "sampling.cu", "logic_fused.cu", "elbo.cu"]
 HEADERS = [CSRC / "common.cuh", CSRC / "params.cuh", CSRC / "sampling.cuh", PKG.parent / "include" / "vael_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -62,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             print(out)
         objs.append(str(obj))
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
-           "-cudart", "static", "-o", str(LIB), *objs]
+           "-cudart", "static", "-o", str(LIB), *objs, "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

@@ -18,7 +18,7 @@ import numpy as np
 # node kinds / semirings — keep in sync with include/vael_b200.h
 LEAF_POS, LEAF_NEG, CONST, PROD, SUM, COMPL = 0, 1, 2, 3, 4, 5
 SEMIRING_PROB, SEMIRING_LOG = 0, 1
-FLAG_NORMALIZE, FLAG_EVIDENCE, FLAG_FORCE_GENERIC, FLAG_CHECK_QUERY = 1, 2, 4, 8
+FLAG_NORMALIZE, FLAG_EVIDENCE, FLAG_FORCE_GENERIC, FLAG_CHECK_QUERY, FLAG_FORCE_JIT = 1, 2, 4, 8, 16
 KIND_NAMES = {LEAF_POS: "leaf+", LEAF_NEG: "leaf-", CONST: "const", PROD: "prod", SUM: "sum", COMPL: "compl"}
 
 

@@ -126,6 +126,7 @@ extern "C" void vael_circuit_destroy(vael_circuit_t* c) {
   cudaGetDevice(&prev);
   cudaSetDevice(c->device);
   gen_program_destroy(c->gen);
+  jit_destroy(c->jit);
   cudaFree(c->d_qmask); cudaFree(c->d_qm_ptr); cudaFree(c->d_qm_idx); cudaFree(c->d_qmask_c);
   cudaFree(c->d_bad_query);
   if (c->h_bad_query) cudaFreeHost(c->h_bad_query);
@@ -203,6 +204,15 @@ extern "C" int vael_circuit_create(const vael_circuit_desc_t* d, vael_circuit_t*
   c->n_facts = d->n_facts; c->n_nodes = d->n_nodes; c->n_levels = d->n_levels; c->n_edges = d->n_edges;
   c->n_worlds = d->n_worlds; c->n_queries = d->n_queries; c->semiring = d->semiring;
   c->norm_node = d->norm_node < 0 ? -1 : d->norm_node;
+  c->n_consts = d->n_consts;
+  c->h_node_kind.assign(d->node_kind, d->node_kind + d->n_nodes);
+  c->h_node_arg.assign(d->node_arg, d->node_arg + d->n_nodes);
+  c->h_level_ptr.assign(d->level_ptr, d->level_ptr + d->n_levels + 1);
+  c->h_child_ptr.assign(d->child_ptr, d->child_ptr + d->n_nodes + 1);
+  if (d->n_edges) c->h_child_idx.assign(d->child_idx, d->child_idx + d->n_edges);
+  if (d->n_consts) c->h_const_val.assign(d->const_val, d->const_val + d->n_consts);
+  if (d->n_worlds) c->h_world_node.assign(d->world_node, d->world_node + d->n_worlds);
+  if (d->n_queries) c->h_query_node.assign(d->query_node, d->query_node + d->n_queries);
 
   // identity hash of the arrays as given
   uint64_t h = 1469598103934665603ull;
@@ -438,6 +448,40 @@ static int check_query_indices(const vael_circuit_t* c, const int32_t* qidx, int
   return VAEL_OK;
 }
 
+static vael_circuit_desc_t desc_of(const vael_circuit_t* c) {
+  vael_circuit_desc_t d{};
+  d.n_facts = c->n_facts; d.n_nodes = c->n_nodes; d.n_levels = c->n_levels; d.n_edges = c->n_edges;
+  d.n_worlds = c->n_worlds; d.n_queries = c->n_queries; d.n_consts = c->n_consts; d.semiring = c->semiring;
+  d.norm_node = c->norm_node;
+  d.node_kind = c->h_node_kind.data(); d.node_arg = c->h_node_arg.data(); d.level_ptr = c->h_level_ptr.data();
+  d.child_ptr = c->h_child_ptr.data(); d.child_idx = c->h_child_idx.data(); d.const_val = c->h_const_val.data();
+  d.world_node = c->h_world_node.data(); d.query_node = c->h_query_node.data();
+  return d;
+}
+// the circuit's specialised kernels, compiled on first use (thread-safe); null when they cannot be built
+static const JitProgram* jit_of(const vael_circuit_t* c) {
+  std::call_once(c->jit_once, [c] {
+    const vael_circuit_desc_t d = desc_of(c);
+    c->jit = jit_create(&d);
+    if (!jit_ok(c->jit) && getenv("VAEL_JIT_VERBOSE")) fprintf(stderr, "vael_b200: no JIT kernels for this circuit: %s\n", jit_log(c->jit));
+  });
+  return jit_ok(c->jit) ? c->jit : nullptr;
+}
+extern "C" int vael_circuit_jit_status(const vael_circuit_t* c, char* log, int32_t n) {
+  if (!c) return 0;
+  const JitProgram* J = jit_of(c);
+  if (log && n > 0) { strncpy(log, jit_log(c->jit), (size_t)n - 1); log[n - 1] = 0; }
+  return J ? 1 : 0;
+}
+extern "C" int vael_jit_compile_check(const vael_circuit_desc_t* d, char* log, int32_t n) {
+  if (!d) return 3;
+  std::string l;
+  size_t bytes = 0;
+  const int rc = jit_compile_check(d, &l, &bytes);
+  if (log && n > 0) { strncpy(log, l.c_str(), (size_t)n - 1); log[n - 1] = 0; }
+  return rc;
+}
+
 static GenCall make_call(const vael_circuit_t* c, const float* facts, const int32_t* qidx, int32_t qs, int64_t B,
                          uint32_t flags) {
   GenCall G;
@@ -466,8 +510,11 @@ static int check_common(const vael_circuit_t* c, const float* facts, const int32
 
 // 0 = generic CSR kernel, 2 = ad2 (1-D bulk tiles), 3 = adw (2-D tensor-map tiles); `wide` is the [B,W] tensor
 // of the call, whose base address the tensor map needs 16-byte aligned
+// 5 = the circuit-specialised straight-line kernel (circuit_jit.cu)
 static int pick_kernel(const vael_circuit_t* c, uint32_t flags, const float* wide) {
-  if (c->fast_kind == 0 || (flags & VAEL_FLAG_FORCE_GENERIC)) return 0;
+  if (flags & VAEL_FLAG_FORCE_GENERIC) return 0;
+  if ((flags & VAEL_FLAG_FORCE_JIT) || c->fast_kind == 0)
+    return jit_can(jit_of(c), flags, wide) ? 5 : ((flags & VAEL_FLAG_FORCE_JIT) ? -1 : 0);
   if (c->fast_kind == 4) return (flags & VAEL_FLAG_EVIDENCE) ? 0 : 4;   // no normaliser node: NORMALIZE is a no-op
   if ((flags & VAEL_FLAG_NORMALIZE) && !c->norm_fast_ok) return 0;
   if (c->fast_kind == 3 && !adw_usable(wide)) return 0;
@@ -483,7 +530,13 @@ extern "C" int vael_circuit_forward(const vael_circuit_t* c, const float* facts,
   if ((flags & VAEL_FLAG_CHECK_QUERY) && needq)
     if (int rc = check_query_indices(c, qidx, B, st)) return rc;
   const int kern = pick_kernel(c, flags, worlds);
-  if (kern == 2) {
+  if (kern < 0) return fail(VAEL_E_UNSUPPORTED, std::string("no specialised kernel for this circuit: ") + jit_log(c->jit));
+  if (kern == 5) {
+    GenCall G = make_call(c, facts, qidx, needq ? qs : -1, B, flags);
+    G.worlds = worlds; G.query = query;
+    CK(jit_forward(jit_of(c), G, c->num_sms, st));
+    g_last_kernel = "jit-straightline";
+  } else if (kern == 2) {
     Ad2Params P{};
     P.facts = facts; P.qidx = qidx; P.qscalar = needq ? qs : -1; P.n_queries = c->n_queries; P.qmask = c->d_qmask;
     P.B = B; P.worlds = worlds; P.query = query;
@@ -539,6 +592,12 @@ extern "C" int vael_circuit_queries_all(const vael_circuit_t* c, const float* fa
   }
   GenCall G = make_call(c, facts, nullptr, -1, B, flags);
   G.queries_all = queries_all;
+  if (pick_kernel(c, flags, nullptr) == 5) {
+    CK(jit_forward(jit_of(c), G, c->num_sms, static_cast<cudaStream_t>(stream)));
+    g_last_kernel = "jit-straightline";
+    g_launches++;
+    return VAEL_OK;
+  }
   if (!gen_fits(c->gen, false)) return fail(VAEL_E_UNSUPPORTED, "circuit too large for the shared-memory tile");
   CK(gen_forward(c->gen, G, c->num_sms, static_cast<cudaStream_t>(stream)));
   g_last_kernel = "generic-csr";
@@ -558,7 +617,13 @@ extern "C" int vael_circuit_backward(const vael_circuit_t* c, const float* facts
   if ((flags & VAEL_FLAG_CHECK_QUERY) && needq)
     if (int rc = check_query_indices(c, qidx, B, st)) return rc;
   const int kern = pick_kernel(c, flags, grad_worlds);
-  if (kern == 2) {
+  if (kern < 0) return fail(VAEL_E_UNSUPPORTED, std::string("no specialised kernel for this circuit: ") + jit_log(c->jit));
+  if (kern == 5) {
+    GenCall G = make_call(c, facts, qidx, needq ? qs : -1, B, flags);
+    G.grad_worlds = grad_worlds; G.grad_query = grad_query; G.grad_facts = grad_facts;
+    CK(jit_backward(jit_of(c), G, c->num_sms, st));
+    g_last_kernel = "jit-straightline";
+  } else if (kern == 2) {
     Ad2Params P{};
     P.facts = facts; P.qidx = qidx; P.qscalar = needq ? qs : -1; P.n_queries = c->n_queries; P.qmask = c->d_qmask;
     P.B = B; P.grad_worlds = grad_worlds; P.grad_query = grad_query; P.grad_facts = grad_facts;

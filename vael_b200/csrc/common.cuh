@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <mutex>
+#include <vector>
 
 #include "../../include/vael_b200.h"
 
@@ -161,6 +162,7 @@ __device__ __forceinline__ void warp_tile_store(float* gdst, const float* stage,
 __host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 struct GenProgram;
+struct JitProgram;
 
 }  // namespace vael
 
@@ -197,6 +199,14 @@ struct vael_circuit {
   uint32_t lt_mask[64];      // fast_kind 4: per world, the fact columns that enter as positive literals
   bool queries_diagonal;     // fast_kind 2: query s = the worlds (j, k) with j + k = s (all-queries register kernel)
   uint32_t* d_qmask_c;       // fast_kind 3: [n_queries][np][ceil(na*nb/32)] chunked membership masks
+  // circuit-specialised straight-line kernels (circuit_jit.cu), compiled with NVRTC on first use; the description is
+  // kept for that (a few kB)
+  mutable std::once_flag jit_once;
+  mutable vael::JitProgram* jit;
+  std::vector<uint8_t> h_node_kind;
+  std::vector<int32_t> h_node_arg, h_level_ptr, h_child_ptr, h_child_idx, h_world_node, h_query_node;
+  std::vector<float> h_const_val;
+  int32_t n_consts;
   // VAEL_FLAG_CHECK_QUERY: device flag word + its pinned host mirror, one check at a time
   int32_t* d_bad_query;
   int32_t* h_bad_query;

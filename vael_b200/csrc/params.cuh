@@ -1,5 +1,7 @@
 // Parameter blocks and host launchers shared between the kernel translation units and capi.cu.
 #pragma once
+#include <string>
+
 #include "common.cuh"
 
 namespace vael {
@@ -99,6 +101,19 @@ struct GenCall {  // the per-call part
 bool gen_fits(const GenProgram* g, bool backward);
 cudaError_t gen_forward(const GenProgram* g, const GenCall& C, int num_sms, cudaStream_t st);
 cudaError_t gen_backward(const GenProgram* g, const GenCall& C, int num_sms, cudaStream_t st);
+
+// ---- circuit_jit.cu (circuit-specialised straight-line kernels, NVRTC) ----
+struct JitProgram;
+bool jit_eligible(const vael_circuit_desc_t* d);
+JitProgram* jit_create(const vael_circuit_desc_t* d);   // never null; jit_ok() tells whether the kernels exist
+void jit_destroy(JitProgram* J);
+bool jit_ok(const JitProgram* J);
+bool jit_can(const JitProgram* J, uint32_t flags, const float* wide_tensor);
+const char* jit_log(const JitProgram* J);
+cudaError_t jit_forward(const JitProgram* J, const GenCall& C, int num_sms, cudaStream_t st);
+cudaError_t jit_backward(const JitProgram* J, const GenCall& C, int num_sms, cudaStream_t st);
+int jit_compile_check(const vael_circuit_desc_t* d, std::string* log, size_t* cubin_bytes);
+std::string jit_source(const vael_circuit_desc_t* d);
 
 // ---- sampling.cu -----------------------------------------------------------
 struct GumbelParams {

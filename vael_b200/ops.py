@@ -13,7 +13,7 @@ from typing import Optional, Tuple, Union
 import torch
 
 from . import _lib
-from .circuit import FLAG_CHECK_QUERY, FLAG_EVIDENCE, FLAG_FORCE_GENERIC, FLAG_NORMALIZE, Circuit
+from .circuit import FLAG_CHECK_QUERY, FLAG_EVIDENCE, FLAG_FORCE_GENERIC, FLAG_FORCE_JIT, FLAG_NORMALIZE, Circuit
 
 
 # NVTX ranges around every library call (tracing), for `ncu --nvtx --nvtx-include "vael/..."` and
@@ -74,6 +74,13 @@ class DeviceCircuit:
         self.handle = handle
         self.fast_kind = int(self.lib.vael_circuit_fast_kind(handle))
         self.hash = int(self.lib.vael_circuit_hash(handle))
+
+    def jit_status(self):
+        """(True, log) when the circuit-specialised kernels exist (compiling them now if need be), else (False, why)."""
+        buf = C.create_string_buffer(1 << 16)
+        with torch.cuda.device(self.device):
+            ok = bool(self.lib.vael_circuit_jit_status(self.handle, buf, len(buf)))
+        return ok, buf.value.decode(errors="replace")
 
     def __del__(self):
         try:
@@ -147,16 +154,20 @@ class _CircuitFunction(torch.autograd.Function):
 
 def circuit_forward(dc: DeviceCircuit, facts: torch.Tensor, query=None, *, normalize: bool = False,
                     evidence: bool = False, force_generic: bool = False, want_worlds: bool = True,
-                    check_query: bool = False) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+                    check_query: bool = False, force_jit: bool = False
+                    ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """worlds [B,W], query [B,1] of the compiled program for the facts [B,F] (or [B,k,n]).
     `query`: None, an int (one query for the batch, the reference's behaviour,
     models/vael.py:212-213) or an integer tensor [B] (one per row; -1 = no query for that row, value 0).
     `check_query`: validate a per-row index tensor on the device first and raise on an out-of-range entry
-    (synchronises the stream: not for CUDA-graph capture); unchecked, such a row's query is 0."""
+    (synchronises the stream: not for CUDA-graph capture); unchecked, such a row's query is 0.
+    `force_generic` / `force_jit`: run the level-by-level CSR interpreter / the circuit-specialised straight-line kernel
+    (NVRTC) instead of whatever the library would pick for this circuit."""
     B = facts.shape[0]
     qidx, qs = _query_args(dc, query, B)
     flags = (FLAG_NORMALIZE if normalize else 0) | (FLAG_EVIDENCE if evidence else 0) | \
-            (FLAG_FORCE_GENERIC if force_generic else 0) | (FLAG_CHECK_QUERY if check_query else 0)
+            (FLAG_FORCE_GENERIC if force_generic else 0) | (FLAG_CHECK_QUERY if check_query else 0) | \
+            (FLAG_FORCE_JIT if force_jit else 0)
     if evidence and query is None:
         raise RuntimeError("vael_b200: evidence mode needs the evidence (query) index")
     want_query = query is not None
@@ -167,7 +178,7 @@ def circuit_forward(dc: DeviceCircuit, facts: torch.Tensor, query=None, *, norma
 
 
 def circuit_queries_all(dc: DeviceCircuit, facts: torch.Tensor, *, normalize: bool = False,
-                        force_generic: bool = False) -> torch.Tensor:
+                        force_generic: bool = False, force_jit: bool = False) -> torch.Tensor:
     """[B,Q] values of every query node (the worlds @ w_q contraction of
     utils/mnist_utils/metrics.py:71-75).  Evaluation-only."""
     f2 = _require_cuda_f32(facts.detach(), "facts").reshape(facts.shape[0], dc.n_facts)
@@ -175,7 +186,8 @@ def circuit_queries_all(dc: DeviceCircuit, facts: torch.Tensor, *, normalize: bo
     with torch.cuda.device(f2.device), _nvtx("queries_all"):
         _lib.check(dc.lib.vael_circuit_queries_all(dc.handle, _p(f2), f2.shape[0], _p(out),
                                                    (FLAG_NORMALIZE if normalize else 0) |
-                                                   (FLAG_FORCE_GENERIC if force_generic else 0), _stream_ptr()))
+                                                   (FLAG_FORCE_GENERIC if force_generic else 0) |
+                                                   (FLAG_FORCE_JIT if force_jit else 0), _stream_ptr()))
     return out
 
 
