@@ -23,10 +23,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# NCCL_DEBUG belongs to the caller (the driver reads the communicator lines) and is honoured as set.  Unset, under
-# torchrun: the communicator-init lines (ranks, transport) go to STDERR so that stdout stays the one JSON line.  Set
-# before torch (and with it NCCL) is loaded: NCCL latches its debug level the first time any of it runs.
-if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not os.environ.get("NCCL_DEBUG"):
+# NCCL_DEBUG belongs to the caller (the driver reads the communicator lines): INFO / TRACE are honoured exactly as
+# set, destination included.  Anything quieter (unset, or this image's default NCCL_DEBUG=VERSION, or WARN) is raised
+# under torchrun to INFO for the INIT subsystem — the "rank r nranks N ... Init COMPLETE" lines and the transport — and
+# sent to STDERR, so that stdout stays the one JSON line.  Done before torch (and with it NCCL) is loaded.
+if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
     os.environ["NCCL_DEBUG"] = "INFO"
     os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -565,12 +566,13 @@ def run_ours(args):
             "secondary": secondary,
         }
     if distributed:
-        dist.barrier()        # nothing else writes to stdout while rank 0 prints the line
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if distributed:
+        # the JSON line goes LAST: with NCCL_DEBUG=INFO on stdout the communicator teardown logs too
         dist.barrier()
         dist.destroy_process_group()
+        if rank == 0:
+            time.sleep(1.5)   # the other ranks' teardown lines are out
+    if rank == 0:
+        print(json.dumps(line), flush=True)
 
 
 def _time_pair(fwd, bwd, n, barrier, max_over_ranks):
@@ -652,9 +654,21 @@ def secondary_probe(args, dev, rank, world, barrier, max_over_ranks, lib):
         lambda: _lib.check(lib.vael_circuit_backward(dc3.handle, _p(facts), _p(qidx), -1, Bg, _p(gw), _p(gq), _p(gf), 4, sp)),
         5, barrier, max_over_ranks)
     out["generic_csr_3digit"] = {
-        "workload": "3-digit circuit through the generic level-ordered CSR kernels", "rows_per_gpu": Bg,
+        "workload": "3-digit circuit through the level-ordered CSR interpreter (VAEL_FLAG_FORCE_GENERIC)", "rows_per_gpu": Bg,
         "fwd": {"ms": f_ms, "GBs": Bg * 4128 / f_ms / 1e6, "frac": Bg * 4128 / f_ms / 1e6 / peak},
         "bwd": {"ms": b_ms, "GBs": Bg * 4248 / b_ms / 1e6, "frac": Bg * 4248 / b_ms / 1e6 / peak}}
+    try:   # the same circuit through its circuit-specialised straight-line kernels (NVRTC, VAEL_FLAG_FORCE_JIT)
+        f_ms, b_ms = _time_pair(
+            lambda: _lib.check(lib.vael_circuit_forward(dc3.handle, _p(facts), _p(qidx), -1, Bg, _p(worlds), _p(query), 16, sp)),
+            lambda: _lib.check(lib.vael_circuit_backward(dc3.handle, _p(facts), _p(qidx), -1, Bg, _p(gw), _p(gq), _p(gf), 16, sp)),
+            5, barrier, max_over_ranks)
+        out["jit_3digit"] = {
+            "workload": "3-digit circuit through its generated straight-line kernels (column chunks of 100 worlds)",
+            "rows_per_gpu": Bg, "kernel_family": _lib.last_kernel(),
+            "fwd": {"ms": f_ms, "GBs": Bg * 4128 / f_ms / 1e6, "frac": Bg * 4128 / f_ms / 1e6 / peak},
+            "bwd": {"ms": b_ms, "GBs": Bg * 4248 / b_ms / 1e6, "frac": Bg * 4248 / b_ms / 1e6 / peak}}
+    except Exception as exc:  # noqa: BLE001
+        out["jit_3digit"] = {"error": repr(exc)[:300]}
     del worlds, gw, facts, p
     torch.cuda.empty_cache()
 
@@ -670,9 +684,21 @@ def secondary_probe(args, dev, rank, world, barrier, max_over_ranks, lib):
         lambda: _lib.check(lib.vael_circuit_backward(dc2.handle, _p(facts2), _p(q2), -1, B2, _p(gw2), _p(gq2), _p(gf2), 4, sp)),
         10, barrier, max_over_ranks)
     out["generic_csr_2digit"] = {
-        "workload": "2-digit circuit through the generic level-ordered CSR kernels", "rows_per_gpu": B2,
+        "workload": "2-digit circuit through the level-ordered CSR interpreter (VAEL_FLAG_FORCE_GENERIC)", "rows_per_gpu": B2,
         "fwd": {"ms": f_ms, "GBs": B2 * FWD_BYTES / f_ms / 1e6, "frac": B2 * FWD_BYTES / f_ms / 1e6 / peak},
         "bwd": {"ms": b_ms, "GBs": B2 * BWD_BYTES / b_ms / 1e6, "frac": B2 * BWD_BYTES / b_ms / 1e6 / peak}}
+    try:   # what a circuit WITHOUT a recognised shape runs: its generated straight-line kernels (here forced)
+        f_ms, b_ms = _time_pair(
+            lambda: _lib.check(lib.vael_circuit_forward(dc2.handle, _p(facts2), _p(q2), -1, B2, _p(w2), _p(qo2), 16, sp)),
+            lambda: _lib.check(lib.vael_circuit_backward(dc2.handle, _p(facts2), _p(q2), -1, B2, _p(gw2), _p(gq2), _p(gf2), 16, sp)),
+            10, barrier, max_over_ranks)
+        out["jit_2digit"] = {
+            "workload": "2-digit circuit through its generated straight-line kernels (NVRTC; the path of every circuit "
+                        "without a recognised shape)", "rows_per_gpu": B2, "kernel_family": _lib.last_kernel(),
+            "fwd": {"ms": f_ms, "GBs": B2 * FWD_BYTES / f_ms / 1e6, "frac": B2 * FWD_BYTES / f_ms / 1e6 / peak},
+            "bwd": {"ms": b_ms, "GBs": B2 * BWD_BYTES / b_ms / 1e6, "frac": B2 * BWD_BYTES / b_ms / 1e6 / peak}}
+    except Exception as exc:  # noqa: BLE001
+        out["jit_2digit"] = {"error": repr(exc)[:300]}
     del w2, gw2, facts2
     torch.cuda.empty_cache()
 

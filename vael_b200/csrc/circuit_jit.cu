@@ -1028,12 +1028,15 @@ bool jit_can(const JitProgram* J, uint32_t flags, const float* wide_tensor) {
 
 cudaError_t jit_forward(const JitProgram* J, const GenCall& C, int num_sms, cudaStream_t st) {
   const bool norm = C.flags & VAEL_FLAG_NORMALIZE, evid = C.flags & VAEL_FLAG_EVIDENCE;
-  static const int wps = jit_env("VAEL_JIT_FWD_WARPS", 5);
+  // warps per SM (one persistent CTA), measured on B200 (scripts/gpu_r2j.sh): the write-dominated forward wants few
+  // store streams in flight for 12.8 KB world tiles (5) and more for smaller tiles / column chunks (7)
+  static const int forced = jit_env("VAEL_JIT_FWD_WARPS", 0);
+  const int wps = forced ? forced : ((!J->wide && J->W >= 96) ? 5 : 7);
   if (C.queries_all != nullptr) return jit_launch(J, J->qall[norm ? 1 : 0], J->fwd_warp_bytes, wps, C, num_sms, st);
   return jit_launch(J, J->fwd[norm ? 1 : 0][evid ? 1 : 0], J->fwd_warp_bytes, wps, C, num_sms, st);
 }
 cudaError_t jit_backward(const JitProgram* J, const GenCall& C, int num_sms, cudaStream_t st) {
-  static const int wps = jit_env("VAEL_JIT_BWD_WARPS", 6);
+  static const int wps = jit_env("VAEL_JIT_BWD_WARPS", 7);   // read-dominated: more loads in flight
   return jit_launch(J, J->bwd[(C.flags & VAEL_FLAG_NORMALIZE) ? 1 : 0], J->bwd_warp_bytes, wps, C, num_sms, st);
 }
 
