@@ -403,3 +403,38 @@ def test_mario_conditioned_worlds_on_the_evidence_kernel(cuda_device):
         assert abs(pq.item() - ref_q.item()) <= 1e-5 * abs(ref_q.item())
     ones = model.compute_conditioned_worlds_prob(facts[:2], torch.tensor([1., 1., 0., 0.]))   # matches no world
     assert torch.equal(ones, torch.ones(2, 24).cuda())
+
+
+def test_epoch_without_a_host_synchronisation(cuda_device):
+    """on-device loader + CUDA-graphed step.  A whole epoch — batches gathered and
+    standardised in HBM (vael_b200/data.py), forward / ELBO / adjoint / Adam replayed from the graph — under
+    torch.cuda.set_sync_debug_mode('error'): not one implicit device synchronisation; the reference's loop does two
+    H2D copies and five `.cpu()` reads per step (utils/mnist_utils/train.py:115-144)."""
+    from vael_b200.data import SyntheticPairsLoader
+    from vael_b200.mnist_task import build_model_dict, build_worlds_queries_matrix
+    from vael_b200.networks import MNISTPairsDecoder, MNISTPairsEncoder, MNISTPairsMLP
+    from vael_b200.train import GraphedTrainStep
+    from vael_b200.vael import MNISTPairsVAELModel
+    torch.manual_seed(0)
+    model = MNISTPairsVAELModel(MNISTPairsEncoder(hidden_channels=64, latent_dim=23),
+                                MNISTPairsDecoder(label_dim=20, hidden_channels=64, latent_dim=8),
+                                MNISTPairsMLP(in_features=15, n_facts=20), (15, 8), build_model_dict(2, 10, device=cuda_device),
+                                build_worlds_queries_matrix(2, 10).to(cuda_device), dropout=0.5, is_train=True,
+                                device=cuda_device, query_per_row=True).to(cuda_device)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+    before = [p.detach().clone() for p in model.parameters()]
+    loader = SyntheticPairsLoader(samples_per_world=32, batch_size=32, device=cuda_device, seed=3)
+    step = GraphedTrainStep(model, opt, (32, 1, 28, 56), (32, 4), device=cuda_device)
+    assert all(torch.equal(a, b) for a, b in zip(before, model.parameters())), "building the step changed the weights"
+    assert all(float(v["step"]) == 0.0 for v in opt.state.values())
+    losses = []
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        for images, labels in loader:
+            terms = step(images[:, None], labels)
+            losses.append(terms[0].clone())
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    losses = torch.stack(losses).cpu()
+    assert len(losses) == 100 and torch.isfinite(losses).all() and losses[-10:].mean() < losses[:10].mean()

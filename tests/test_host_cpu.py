@@ -450,3 +450,24 @@ def test_generated_circuit_kernels_compile_for_sm100a(addition_family):
         if rc == 2:
             pytest.skip("NVRTC not available: " + buf.value.decode())
         assert rc == want, buf.value.decode()[:2000]
+
+
+def test_device_pairs_loader_serves_the_reference_batch_composition():
+    """vael_b200/data.py: one world per batch, worlds without replacement, every sample once per epoch, labels
+    [d1, d2, sum, -1], whole-array standardisation (utils/mnist_utils/mnist_addition_dataset.py:37,67-121)."""
+    import torch
+    from vael_b200.data import SyntheticPairsLoader
+    ld = SyntheticPairsLoader(samples_per_world=12, batch_size=4, digits=3, device="cpu", seed=7)
+    assert len(ld.worlds) == 9 and len(ld) == 27 and ld.samples_x_world == 12
+    seen = []
+    for images, labels in ld:
+        assert images.shape == (4, 28, 56) and images.dtype == torch.float32 and labels.shape == (4, 4)
+        assert (labels == labels[0]).all() and int(labels[0, 2]) == int(labels[0, 0] + labels[0, 1]) and int(labels[0, 3]) == -1
+        seen.append(tuple(labels[0, :2].tolist()))
+    assert sorted(set(seen)) == sorted(ld.worlds) and all(seen.count(c) == 3 for c in ld.worlds)
+    with pytest.raises(IndexError):
+        ld[0]
+    ld.reset_counter()
+    images, _ = ld[0]
+    raw = ld.images.float()
+    assert abs(float(raw.mean()) - ld.mean) < 1e-4 and abs(((images * ld.std + ld.mean) - images * ld.std - ld.mean).abs().max()) < 1e-3

@@ -216,97 +216,115 @@ cudaError_t gumbel_backward(const GumbelParams& P, int num_sms, cudaStream_t st)
 // CLIP: out = clamp(softmax, eps, hi) instead of (softmax + eps) / sum — MarioVAELModel's facts
 // (models/vael.py:319-322: Softmax then torch.clip(min=1e-5, max=0.9999)); its gradient passes where
 // eps <= softmax <= hi (torch.clip's rule) and is zero elsewhere.
+// row of K floats of a [32, K] shared-memory tile <-> registers, with the widest access the row pitch allows
+// (pitches of 80 / 120 / 72 / 36 bytes: 128 / 64 / 64 / 32-bit accesses are conflict-free per quarter / half warp)
+template <int K>
+__device__ __forceinline__ void tile_row_load(const float* row, float* x) {
+  constexpr int V = (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1);
+#pragma unroll
+  for (int c = 0; c < K; c += V) {
+    if constexpr (V == 4) { const float4 t = *reinterpret_cast<const float4*>(row + c); x[c] = t.x; x[c + 1] = t.y; x[c + 2] = t.z; x[c + 3] = t.w; }
+    else if constexpr (V == 2) { const float2 t = *reinterpret_cast<const float2*>(row + c); x[c] = t.x; x[c + 1] = t.y; }
+    else x[c] = row[c];
+  }
+}
+template <int K>
+__device__ __forceinline__ void tile_row_store(float* row, const float* x) {
+  constexpr int V = (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1);
+#pragma unroll
+  for (int c = 0; c < K; c += V) {
+    if constexpr (V == 4) *reinterpret_cast<float4*>(row + c) = make_float4(x[c], x[c + 1], x[c + 2], x[c + 3]);
+    else if constexpr (V == 2) *reinterpret_cast<float2*>(row + c) = make_float2(x[c], x[c + 1]);
+    else row[c] = x[c];
+  }
+}
+
+constexpr int kFactsStages = 2;
+template <int F, bool BWD>
+__host__ __device__ constexpr int facts_warp_bytes() {
+  // [barriers 128][input stages: logits (+ grad_facts)][result stages]
+  return 128 + kFactsStages * (BWD ? 2 : 1) * ((kWarp * F * 4 + 127) / 128 * 128) + kFactsStages * ((kWarp * F * 4 + 127) / 128 * 128);
+}
+
+// Round 2: the tiles move by bulk copies through a warp-private two-stage ring (WarpTileLoader) instead of being
+// staged through the LSU at an odd pitch (ncu, profiles/r02a_stage_ncu.md: L1 45-55 % busy, 2.6 M bank conflicts).
 template <int NG, int N, bool BWD, bool CLIP>
-__global__ void __launch_bounds__(256) facts_tile_kernel(const float* __restrict__ logits,
+__global__ void __launch_bounds__(128) facts_tile_kernel(const float* __restrict__ logits,
                                                          const float* __restrict__ grad_facts, long long B,
                                                          float eps, float hi, float* __restrict__ out) {
-  constexpr int F = NG * N;
-  constexpr int PITCH = F | 1;  // odd pitch: lane <-> row accesses of the staged tile are conflict-free
-  extern __shared__ float tile_s[];
+  constexpr int F = NG * N, FT = kWarp * F, TB = (FT * 4 + 127) / 128 * 128;
+  extern __shared__ __align__(128) uint8_t facts_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  float* xs = tile_s + (size_t)warp * (BWD ? 2 : 1) * kWarp * PITCH;
-  float* gs = xs + kWarp * PITCH;
+  uint8_t* wb = facts_smem + (size_t)warp * facts_warp_bytes<F, BWD>();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wb);
+  float* istage = reinterpret_cast<float*>(wb + 128);
+  float* ostage = reinterpret_cast<float*>(wb + 128 + kFactsStages * (BWD ? 2 : 1) * TB);
   const long long n_sub = (B + kWarp - 1) / kWarp;
   const long long gw = (long long)blockIdx.x * nwarps + warp, GW = (long long)gridDim.x * nwarps;
-  // the next tile (a contiguous span: coalesced) is requested one iteration ahead into registers, so that a warp
-  // does not sit out a full HBM round trip before every tile
-  float nx[F], ng[BWD ? F : 1];
-  auto fetch = [&](long long sub) {
-    const long long r0 = sub * kWarp;
-    const int n = (sub < n_sub) ? (int)min((long long)kWarp, B - r0) * F : 0;
-#pragma unroll
-    for (int k = 0; k < F; ++k) {
-      const int i = k * kWarp + lane;
-      nx[k] = (i < n) ? __ldg(logits + r0 * F + i) : 0.0f;
-      if (BWD) ng[k] = (i < n) ? __ldg(grad_facts + r0 * F + i) : 0.0f;
-    }
+  if (gw >= n_sub) return;
+  const bool in_al = aligned16(logits) && (!BWD || aligned16(grad_facts)), out_al = aligned16(out);
+  WarpTileLoader<kFactsStages> lx, lg;
+  lx.init(istage, bars, TB / 4, lane);
+  if (BWD) lg.init(istage + kFactsStages * (TB / 4), bars + kFactsStages, TB / 4, lane);
+  auto request = [&](long long sub, int s) {
+    if (sub >= n_sub) return;
+    const int n = (int)min((long long)kWarp, B - sub * kWarp) * F;
+    lx.issue(s, logits + sub * FT, n, in_al, lane, 0.0f);
+    if (BWD) lg.issue(s, grad_facts + sub * FT, n, in_al, lane, 0.0f);
   };
-  fetch(gw);
-  for (long long sub = gw; sub < n_sub; sub += GW) {
-    const long long row0 = sub * kWarp;
-    const int rows = (int)min((long long)kWarp, B - row0);
-    const int n = rows * F;
-    __syncwarp();
 #pragma unroll
-    for (int k = 0; k < F; ++k) {
-      const int i = k * kWarp + lane;
-      const int r = i / F, c = i - r * F;               // F is a compile-time constant: mul-shift, no division
-      xs[r * PITCH + c] = nx[k];
-      if (BWD) gs[r * PITCH + c] = ng[k];
-    }
+  for (int s = 0; s < kFactsStages; ++s) request(gw + s * GW, s);
+  long long it = 0;
+  for (long long sub = gw; sub < n_sub; sub += GW, ++it) {
+    const int s = (int)(it % kFactsStages);
+    const int rows = (int)min((long long)kWarp, B - sub * kWarp);
+    lx.wait(s);
+    if (BWD) lg.wait(s);
+    float x[F], y[F], zs[NG], gfr[BWD ? F : 1], o[F];
+    tile_row_load<F>(lx.stage(s) + lane * F, x);
+    if (BWD) tile_row_load<F>(lg.stage(s) + lane * F, gfr);
     __syncwarp();
-    fetch(sub + GW);
-    float x[F], y[F], zs[NG];
-#pragma unroll
-    for (int c = 0; c < F; ++c) x[c] = xs[lane * PITCH + c];
+    request(sub + kFactsStages * GW, s);
     facts_row<NG, N>(x, eps, y, zs);
     if (!BWD) {
 #pragma unroll
-      for (int c = 0; c < F; ++c) xs[lane * PITCH + c] = CLIP ? fminf(fmaxf(y[c], eps), hi) : (y[c] + eps) / zs[c / N];
-    } else if (CLIP) {
+      for (int c = 0; c < F; ++c) o[c] = CLIP ? fminf(fmaxf(y[c], eps), hi) : (y[c] + eps) / zs[c / N];
+    } else {
+      // f = (y + eps) / Z with Z detached -> dL/dy_i = gf_i / Z (CLIP: gf_i where eps <= y_i <= hi, else 0);
+      // softmax: dx_i = y_i (dy_i - sum_j y_j dy_j)
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
         float dy[N], dot = 0.0f;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
           const float yi = y[g * N + i];
-          dy[i] = (yi >= eps && yi <= hi) ? gs[lane * PITCH + g * N + i] : 0.0f;
+          dy[i] = CLIP ? ((yi >= eps && yi <= hi) ? gfr[g * N + i] : 0.0f) : gfr[g * N + i] / zs[g];
           dot = fmaf(yi, dy[i], dot);
         }
 #pragma unroll
-        for (int i = 0; i < N; ++i) xs[lane * PITCH + g * N + i] = y[g * N + i] * (dy[i] - dot);
-      }
-    } else {
-      // f = (y + eps) / Z with Z detached  ->  dL/dy_i = gf_i / Z ; softmax: dx_i = y_i (dy_i - sum_j y_j dy_j)
-#pragma unroll
-      for (int g = 0; g < NG; ++g) {
-        float dy[N], dot = 0.0f;
-#pragma unroll
-        for (int i = 0; i < N; ++i) { dy[i] = gs[lane * PITCH + g * N + i] / zs[g]; dot = fmaf(y[g * N + i], dy[i], dot); }
-#pragma unroll
-        for (int i = 0; i < N; ++i) xs[lane * PITCH + g * N + i] = y[g * N + i] * (dy[i] - dot);
+        for (int i = 0; i < N; ++i) o[g * N + i] = y[g * N + i] * (dy[i] - dot);
       }
     }
+    if (lane == 0) bulk_wait_read<kFactsStages - 1>();   // the store of two tiles ago has read its stage
     __syncwarp();
-    for (int i = lane; i < n; i += kWarp) {
-      const int r = i / F, c = i - r * F;
-      out[row0 * F + i] = xs[r * PITCH + c];
-    }
+    tile_row_store<F>(ostage + s * (TB / 4) + lane * F, o);
+    fence_proxy_async();
+    __syncwarp();
+    warp_tile_store(out + sub * FT, ostage + s * (TB / 4), rows * F, FT, out_al, lane);
   }
+  if (lane == 0) bulk_wait_all<0>();
 }
 
 template <int NG, int N, bool BWD, bool CLIP>
 static cudaError_t launch_facts_tile(const float* logits, const float* gf, long long B, float eps, float hi, float* out,
                                      int num_sms, cudaStream_t st) {
-  constexpr int PITCH = (NG * N) | 1;
-  const int nw = 8;
-  const size_t smem = (size_t)nw * (BWD ? 2 : 1) * kWarp * PITCH * sizeof(float);
+  const int nw = 4;
+  const int smem = nw * facts_warp_bytes<NG * N, BWD>();
   const long long n_sub = (B + kWarp - 1) / kWarp;
-  const int grid = (int)max(1LL, min((n_sub + nw - 1) / nw, (long long)num_sms * 4));
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(facts_tile_kernel<NG, N, BWD, CLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
+  const int ctas = max(1, min(8, (227 * 1024) / (smem + 1024)));
+  const int grid = (int)max(1LL, min((n_sub + nw - 1) / nw, (long long)num_sms * ctas));
+  cudaError_t e = cudaFuncSetAttribute(facts_tile_kernel<NG, N, BWD, CLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
   facts_tile_kernel<NG, N, BWD, CLIP><<<grid, nw * 32, smem, st>>>(logits, gf, B, eps, hi, out);
   return cudaGetLastError();
 }
