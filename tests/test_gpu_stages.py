@@ -73,7 +73,9 @@ def test_gumbel_world_matches_reference_golden(cuda_device):
     assert rel_err(gw.cpu().numpy(), ref, floor=1e-4 * np.abs(ref).max()) < 1e-4
 
 
-@pytest.mark.parametrize("W,H,is_log", [(100, 20, False), (24, 18, True), (81, 18, False), (1000, 30, False), (7, 3, True)])
+# (100, 20), (24, 18), (128, 32), (16, 5), (64, 7): lane <-> row kernels (gumbel_rows.cu); the rest: one warp per row
+@pytest.mark.parametrize("W,H,is_log", [(100, 20, False), (24, 18, True), (81, 18, False), (1000, 30, False), (7, 3, True),
+                                        (128, 32, False), (16, 5, True), (64, 7, False), (100, 33, False)])
 def test_gumbel_world_matches_oracle(cuda_device, W, H, is_log):
     from vael_b200.ops import gumbel_world
     B = 193
@@ -94,6 +96,76 @@ def test_gumbel_world_matches_oracle(cuda_device, W, H, is_log):
     np.testing.assert_allclose(wh.detach().cpu().numpy(), wh_ref.detach().numpy(), atol=2.4e-7)
     (g2,) = torch.autograd.grad((wh * up.cuda()).sum(), [sc])
     assert rel_err(g2.cpu().numpy(), g_ref.numpy(), floor=1e-3 * g_ref.abs().max().item()) < 1e-4
+
+
+@pytest.mark.parametrize("tau", [1.0, 0.4, 2.5])
+def test_gumbel_rows_kernels_equal_warp_per_row_kernels(cuda_device, tau, tmp_path):
+    """The two kernel families on the same inputs (real Herbrand base, injected noise, a temperature, a tail tile, views
+    that are only 4-byte aligned): same worlds, y_soft within 1e-5, adjoints within 1e-5 of the largest entry."""
+    import subprocess, sys, os, json
+    from vael_b200.ops import gumbel_world
+    gen = torch.Generator().manual_seed(int(tau * 10))
+    B, W, H = 32 * 9 + 5, 100, 20
+    p = torch.softmax(3 * torch.randn(B, W, generator=gen), 1)
+    noise = -torch.empty(B, W).exponential_(generator=gen).log()
+    up = torch.randn(B, H, generator=gen)
+    hb = dense_path.herbrand_base(20).cuda()
+
+    def run(offset):
+        base = torch.empty(B * W + 1).cuda()
+        sc = (base[1:] if offset else base[:-1]).view(B, W)
+        sc.copy_(p)
+        sc = sc.detach().requires_grad_(True)
+        assert (sc.data_ptr() % 16 != 0) == bool(offset)
+        wh, idx, ys = gumbel_world(sc, hb, tau=tau, is_log=False, noise=noise.cuda())
+        (g,) = torch.autograd.grad((wh * up.cuda()).sum(), [sc])
+        return wh.detach(), idx, ys, g
+
+    a, b = run(0), run(1)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    # the one-warp-per-row kernels on the same inputs: a child process with VAEL_GUMBEL_ROWS=0 (read once per process)
+    case, out = str(tmp_path / "case.pt"), str(tmp_path / "out.pt")
+    torch.save({"p": p, "noise": noise, "up": up, "tau": tau}, case)
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from vael_b200.ops import gumbel_world\n"
+        "from oracle import dense_path\n"
+        "c = torch.load(%r)\n"
+        "sc = c['p'].cuda().requires_grad_(True)\n"
+        "wh, idx, ys = gumbel_world(sc, dense_path.herbrand_base(20).cuda(), tau=c['tau'], is_log=False, noise=c['noise'].cuda())\n"
+        "(g,) = torch.autograd.grad((wh * c['up'].cuda()).sum(), [sc])\n"
+        "torch.save({'wh': wh.detach().cpu(), 'idx': idx.cpu(), 'ys': ys.cpu(), 'g': g.cpu()}, %r)\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), case, out)
+    env = dict(os.environ, VAEL_GUMBEL_ROWS="0")
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
+    o = torch.load(out)
+    assert torch.equal(a[1].cpu(), o["idx"])
+    np.testing.assert_allclose(a[2].cpu().numpy(), o["ys"].numpy(), rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(a[0].cpu().numpy(), o["wh"].numpy(), atol=2.4e-7)
+    gm = o["g"].abs().max().item()
+    assert (a[3].cpu() - o["g"]).abs().max().item() <= 1e-5 * gm
+
+
+def test_gumbel_rows_philox_sampling_follows_world_distribution(cuda_device):
+    """The lane <-> row kernel's own Philox stream (W = 100, the training shape): deterministic per seed, worlds
+    distributed like P(w), y_soft a distribution whose arg-max is the sampled world."""
+    from vael_b200.ops import gumbel_world
+    W, B = 100, 600000
+    p = torch.softmax(1.5 * torch.randn(1, W, generator=torch.Generator().manual_seed(5)), 1)
+    scores = p.expand(B, W).contiguous().cuda()
+    hb = dense_path.herbrand_base(20).cuda()
+    wh, idx, ys = gumbel_world(scores, hb, seed=99)
+    _, idx2, _ = gumbel_world(scores, hb, seed=99)
+    _, idx3, _ = gumbel_world(scores, hb, seed=100)
+    assert torch.equal(idx, idx2) and not torch.equal(idx, idx3)
+    assert torch.equal(ys.argmax(1).int(), idx)
+    assert float((ys.sum(1) - 1).abs().max()) < 1e-5
+    assert torch.equal((wh > 0.5).float(), hb[idx.long()])
+    counts = torch.bincount(idx.long(), minlength=W).double().cpu()
+    expected = p[0].double() * B
+    chi2 = ((counts - expected) ** 2 / expected).sum().item()
+    assert chi2 < 190.0, chi2  # 99 dof: P(chi2 > 190) ~ 1e-7
 
 
 def test_gumbel_world_philox_sampling_follows_world_distribution(cuda_device):

@@ -13,7 +13,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libvael_b200.so"
-SOURCES = ["capi.cu", "circuit_ad2.cu", "circuit_adw.cu", "circuit_generic.cu", "circuit_jit.cu", "circuit_lt.cu", "sampling.cu", "logic_fused.cu", "elbo.cu"]
+SOURCES = ["capi.cu", "circuit_ad2.cu", "circuit_adw.cu", "circuit_generic.cu", "circuit_jit.cu", "circuit_lt.cu", "sampling.cu", "gumbel_rows.cu", "logic_fused.cu", "elbo.cu"]
 HEADERS = [CSRC / "common.cuh", CSRC / "params.cuh", CSRC / "sampling.cuh", PKG.parent / "include" / "vael_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

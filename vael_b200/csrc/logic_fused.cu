@@ -41,35 +41,11 @@
 
 namespace vael {
 
-constexpr float kLog2e = 1.4426950408889634f;
-// log2 of the exponential variate E2 = -log2(U) behind a Gumbel variate, U = (k + 1/2) 2^-23 (sampling.cuh):
-// E2 in [2^-24 / ln 2, 24]  ->  log2 E2 in [-23.48, 4.59]
-constexpr float kLogE2Min = -23.5f, kLogE2Max = 4.6f;
-
-// The noise in the form the kernels consume: L = log2(E2), E2 = -log2(U) = E / ln 2 with E ~ Exp(1), so that the Gumbel
-// variate is g = -ln E = -ln2 (L + log2 ln2) and a perturbed logit in the log2 domain is
-//     log2(e)/tau (log p + g) = s log p - L / tau + const,    s = log2(e) / tau
-// (the constant shifts every world of the row alike: arg-max and softmax do not see it).  Same accuracy guard as
-// gumbel_from_bits: for U -> 1 the series of -log(1 - v) replaces the fast logarithm.
-__device__ __forceinline__ float log2_exp_variate(uint32_t bits) {
-  const float u = (static_cast<float>(bits >> 9) + 0.5f) * (1.0f / 8388608.0f);
-  const float v = 1.0f - u;
-  const float series = v * fmaf(v, fmaf(v, 0.48089835f, 0.72134752f), 1.44269504f);   // (v + v^2/2 + v^3/3) / ln 2
-  const float e2 = (v < 1.0f / 1024.0f) ? series : -__log2f(u);
-  return __log2f(e2);
-}
 __device__ __forceinline__ void noise_block(long long row, int blk, uint64_t seed, float* L4) {
   const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)blk, 0x5eedu),
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   L4[0] = log2_exp_variate(r.x); L4[1] = log2_exp_variate(r.y);
   L4[2] = log2_exp_variate(r.z); L4[3] = log2_exp_variate(r.w);
-}
-
-// 2^x, x <= 0 (MUFU.EX2; 2 ulp): the softmax runs in the log2 domain, the log2(e) factor folded into 1/tau
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
 }
 
 template <int F>

@@ -133,6 +133,10 @@ struct GumbelParams {
 };
 cudaError_t gumbel_forward(const GumbelParams& P, int num_sms, cudaStream_t st);
 cudaError_t gumbel_backward(const GumbelParams& P, int num_sms, cudaStream_t st);
+// gumbel_rows.cu: lane <-> row kernels for W % 4 == 0, W <= 128, H <= 32 (the dispatchers above pick them)
+bool gumbel_rows_ok(const GumbelParams& P, bool backward);
+cudaError_t gumbel_rows_forward(const GumbelParams& P, int num_sms, cudaStream_t st);
+cudaError_t gumbel_rows_backward(const GumbelParams& P, int num_sms, cudaStream_t st);
 cudaError_t facts_forward(const float* logits, long long B, int n_groups, int group, float eps, float hi, float* facts,
                           int num_sms, cudaStream_t st);
 cudaError_t facts_backward(const float* logits, const float* grad_facts, long long B, int n_groups, int group,

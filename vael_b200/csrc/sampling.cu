@@ -6,7 +6,9 @@
 //
 // One warp per batch row, lane <-> world: global accesses are coalesced and the
 // max / argmax / sum reductions are warp shuffles; nothing is staged in shared
-// memory except the small 0/1 Herbrand table.
+// memory except the small 0/1 Herbrand table.  These are the kernels of wide or odd shapes (W > 128, W % 4 != 0,
+// H > 32: e.g. the 3-digit circuit's 1000 worlds); the shapes VAEL trains on take the lane <-> row kernels of
+// gumbel_rows.cu.
 #include "params.cuh"
 #include "sampling.cuh"
 
@@ -163,6 +165,7 @@ static int launch_grid(long long B, int num_sms) {
 }
 
 cudaError_t gumbel_forward(const GumbelParams& P, int num_sms, cudaStream_t st) {
+  if (gumbel_rows_ok(P, false)) return gumbel_rows_forward(P, num_sms, st);
   const int grid = launch_grid(P.B, num_sms);
   switch (pick_items(P.W)) {
     case 1: gumbel_forward_kernel<1><<<grid, 256, 0, st>>>(P); break;
@@ -191,6 +194,7 @@ static cudaError_t launch_gumbel_bwd(GumbelParams P, int grid, cudaStream_t st) 
 }
 
 cudaError_t gumbel_backward(const GumbelParams& P, int num_sms, cudaStream_t st) {
+  if (gumbel_rows_ok(P, true)) return gumbel_rows_backward(P, num_sms, st);
   const int grid = launch_grid(P.B, num_sms);
   switch (pick_items(P.W)) {
     case 1: return launch_gumbel_bwd<1>(P, grid, st);

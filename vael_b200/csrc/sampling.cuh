@@ -32,6 +32,30 @@ __device__ __forceinline__ float gumbel_from_bits(uint32_t bits) {
   return -__logf(e);
 }
 
+constexpr float kLog2e = 1.4426950408889634f;
+// log2 of the exponential variate E2 = -log2(U) behind a Gumbel variate, U = (k + 1/2) 2^-23 (sampling.cuh):
+// E2 in [2^-24 / ln 2, 24]  ->  log2 E2 in [-23.48, 4.59]
+constexpr float kLogE2Min = -23.5f, kLogE2Max = 4.6f;
+
+// The noise in the form the kernels consume: L = log2(E2), E2 = -log2(U) = E / ln 2 with E ~ Exp(1), so that the Gumbel
+// variate is g = -ln E = -ln2 (L + log2 ln2) and a perturbed logit in the log2 domain is
+//     log2(e)/tau (log p + g) = s log p - L / tau + const,    s = log2(e) / tau
+// (the constant shifts every world of the row alike: arg-max and softmax do not see it).  Same accuracy guard as
+// gumbel_from_bits: for U -> 1 the series of -log(1 - v) replaces the fast logarithm.
+__device__ __forceinline__ float log2_exp_variate(uint32_t bits) {
+  const float u = (static_cast<float>(bits >> 9) + 0.5f) * (1.0f / 8388608.0f);
+  const float v = 1.0f - u;
+  const float series = v * fmaf(v, fmaf(v, 0.48089835f, 0.72134752f), 1.44269504f);   // (v + v^2/2 + v^3/3) / ln 2
+  const float e2 = (v < 1.0f / 1024.0f) ? series : -__log2f(u);
+  return __log2f(e2);
+}
+// 2^x, x <= 0 (MUFU.EX2; 2 ulp): the softmax runs in the log2 domain, the log2(e) factor folded into 1/tau
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 
 template <int NG, int N>
 __device__ __forceinline__ void facts_row(const float* x, float eps, float* y, float* zs) {
