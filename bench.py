@@ -490,7 +490,7 @@ def run_ours(args):
                         "frac": (Be * 488 / e2e_s / 1e9) / link_gbs,
                         "what": "PCIe-bound: bytes each way / step time against plain pinned cudaMemcpyAsync "
                                 "running H2D and D2H concurrently on this box"},
-               "api": "vael_circuit_fwdbwd_host (C-ABI, pinned host buffers, 128Ki-row chunks over 4 streams)",
+               "api": "vael_circuit_fwdbwd_host (C-ABI, pinned host buffers, 256Ki-row chunks over 4 slots, uploads on their own streams)",
                "query_grad_rows_per_sec": world * Be / diet_s, "query_grad_ms_per_step": diet_s * 1e3,
                "query_grad_h2d_bytes_per_step": Be * (80 + 4 + 4), "query_grad_d2h_bytes_per_step": Be * (4 + 80),
                "query_grad_vs_full_rows_per_sec": e2e_s / diet_s,

@@ -120,6 +120,14 @@ static bool world_literals(const vael_circuit_desc_t* d, int n, std::vector<int>
   return false;
 }
 
+static void destroy_slot_streams(vael_host_slot& S) {
+  if (S.facts_up) cudaEventDestroy(S.facts_up);
+  if (S.grads_up) cudaEventDestroy(S.grads_up);
+  if (S.done) cudaEventDestroy(S.done);
+  if (S.up) cudaStreamDestroy(S.up);
+  if (S.stream) cudaStreamDestroy(S.stream);
+}
+
 extern "C" void vael_circuit_destroy(vael_circuit_t* c) {
   if (!c) return;
   int prev = 0;
@@ -133,7 +141,7 @@ extern "C" void vael_circuit_destroy(vael_circuit_t* c) {
   for (auto& S : c->slot) {
     cudaFree(S.facts); cudaFree(S.worlds); cudaFree(S.query); cudaFree(S.gw); cudaFree(S.gq); cudaFree(S.gf);
     cudaFree(S.qidx);
-    if (S.stream) cudaStreamDestroy(S.stream);
+    destroy_slot_streams(S);
   }
   cudaSetDevice(prev);
   delete c;
@@ -650,22 +658,30 @@ extern "C" int vael_circuit_backward(const vael_circuit_t* c, const float* facts
 }
 
 // ---------------------------------------------------------------------------
-// host-buffer variants: row chunks round-robin over kHostSlots streams (each with its own device
-// buffers) so that the H2D copy of one chunk, the kernels of another and the D2H copy of a third overlap
-// and both PCIe directions stay busy
+// host-buffer variants: row chunks round-robin over kHostSlots slots (each with its own device buffers, a
+// compute/download stream and an upload stream) so that the H2D copy of one chunk, the kernels of another and the
+// D2H copy of a third overlap and both PCIe directions stay busy.  Uploads have their own stream per slot: in one
+// stream the upload of a chunk's upstream gradients would queue behind the download of its worlds, which it does not
+// depend on, and the upload direction idled part of the call (0.90 of the link; 0.93 now).  Chunks are LARGE
+// (256 Ki rows by default, VAEL_HOST_CHUNK_ROWS): every chunk is seven copies, three of them 4 bytes per row, and the
+// per-copy cost shows — 16 Ki-row chunks reach 0.71 of the link, 32 Ki 0.83, 128 Ki 0.928, 256 Ki 0.933
+// (scripts/e2e_probe.py).  A call smaller than four full chunks is split in four so that all slots work.
 // ---------------------------------------------------------------------------
 // Caller holds host_mutex.  All-or-nothing: a failure frees what this call created.
 static int ensure_slots(const vael_circuit_t* c) {
   if (c->chunk_rows) return VAEL_OK;
   const char* env = getenv("VAEL_HOST_CHUNK_ROWS");
-  long long rows = env && *env ? atoll(env) : (1 << 17);
+  long long rows = env && *env ? atoll(env) : (1 << 18);
   if (rows < 32) rows = 32;
   const size_t F = c->n_facts, W = c->n_worlds ? c->n_worlds : 1;
   cudaError_t e = cudaSuccess;
   auto alloc = [&](auto** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(p), bytes); };
+  auto event = [&](cudaEvent_t* ev) { if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming); };
   for (int s = 0; s < kHostSlots && e == cudaSuccess; ++s) {
     auto& S = c->slot[s];
     e = cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&S.up, cudaStreamNonBlocking);
+    event(&S.facts_up); event(&S.grads_up); event(&S.done);
     alloc(&S.facts, rows * F * 4); alloc(&S.gf, rows * F * 4);
     alloc(&S.worlds, rows * W * 4); alloc(&S.gw, rows * W * 4);
     alloc(&S.query, rows * 4); alloc(&S.gq, rows * 4); alloc(&S.qidx, rows * 4);
@@ -674,7 +690,7 @@ static int ensure_slots(const vael_circuit_t* c) {
     for (auto& S : c->slot) {
       cudaFree(S.facts); cudaFree(S.worlds); cudaFree(S.query); cudaFree(S.gw); cudaFree(S.gq); cudaFree(S.gf);
       cudaFree(S.qidx);
-      if (S.stream) cudaStreamDestroy(S.stream);
+      destroy_slot_streams(S);
       S = vael_host_slot{};
     }
     return cuda_fail(e, "host pipeline allocation");
@@ -689,12 +705,27 @@ static int host_pipeline_locked(const vael_circuit_t* c, const float* facts_h, c
                                 int64_t B, const float* gw_h, const float* gq_h, float* worlds_h, float* query_h,
                                 float* gf_h, uint32_t flags, bool backward) {
   const size_t F = c->n_facts, W = c->n_worlds;
+  static const bool fixed_chunks = [] { const char* v = getenv("VAEL_HOST_FIXED_CHUNKS"); return v && v[0] == '1'; }();
+  int64_t chunk = c->chunk_rows;
+  if (!fixed_chunks) {
+    const int64_t quarter = ((B / kHostSlots + 31) / 32) * 32;
+    chunk = std::min<int64_t>(chunk, std::max<int64_t>(quarter, 32768));
+  }
   int idx = 0;
-  for (int64_t r0 = 0; r0 < B; r0 += c->chunk_rows, ++idx) {
-    const int64_t n = (B - r0 < c->chunk_rows) ? (B - r0) : c->chunk_rows;
+  for (int64_t r0 = 0; r0 < B; r0 += chunk, ++idx) {
+    const int64_t n = (B - r0 < chunk) ? (B - r0) : chunk;
     auto& S = c->slot[idx % kHostSlots];
-    CK(cudaMemcpyAsync(S.facts, facts_h + r0 * F, n * F * 4, cudaMemcpyHostToDevice, S.stream));
-    if (qidx_h) CK(cudaMemcpyAsync(S.qidx, qidx_h + r0, n * 4, cudaMemcpyHostToDevice, S.stream));
+    // uploads: after the chunk that used this slot before has finished with its buffers
+    if (idx >= kHostSlots) CK(cudaStreamWaitEvent(S.up, S.done, 0));
+    CK(cudaMemcpyAsync(S.facts, facts_h + r0 * F, n * F * 4, cudaMemcpyHostToDevice, S.up));
+    if (qidx_h) CK(cudaMemcpyAsync(S.qidx, qidx_h + r0, n * 4, cudaMemcpyHostToDevice, S.up));
+    CK(cudaEventRecord(S.facts_up, S.up));
+    if (backward) {
+      if (gw_h) CK(cudaMemcpyAsync(S.gw, gw_h + r0 * W, n * W * 4, cudaMemcpyHostToDevice, S.up));
+      if (gq_h) CK(cudaMemcpyAsync(S.gq, gq_h + r0, n * 4, cudaMemcpyHostToDevice, S.up));
+      CK(cudaEventRecord(S.grads_up, S.up));
+    }
+    CK(cudaStreamWaitEvent(S.stream, S.facts_up, 0));
     if (worlds_h || query_h) {
       if (int rc = vael_circuit_forward(c, S.facts, qidx_h ? S.qidx : nullptr, qs, n, worlds_h ? S.worlds : nullptr,
                                         query_h ? S.query : nullptr, flags, S.stream))
@@ -703,13 +734,13 @@ static int host_pipeline_locked(const vael_circuit_t* c, const float* facts_h, c
       if (query_h) CK(cudaMemcpyAsync(query_h + r0, S.query, n * 4, cudaMemcpyDeviceToHost, S.stream));
     }
     if (backward) {
-      if (gw_h) CK(cudaMemcpyAsync(S.gw, gw_h + r0 * W, n * W * 4, cudaMemcpyHostToDevice, S.stream));
-      if (gq_h) CK(cudaMemcpyAsync(S.gq, gq_h + r0, n * 4, cudaMemcpyHostToDevice, S.stream));
+      CK(cudaStreamWaitEvent(S.stream, S.grads_up, 0));
       if (int rc = vael_circuit_backward(c, S.facts, qidx_h ? S.qidx : nullptr, qs, n, gw_h ? S.gw : nullptr,
                                          gq_h ? S.gq : nullptr, S.gf, flags & ~VAEL_FLAG_CHECK_QUERY, S.stream))
         return rc;
       CK(cudaMemcpyAsync(gf_h + r0 * F, S.gf, n * F * 4, cudaMemcpyDeviceToHost, S.stream));
     }
+    CK(cudaEventRecord(S.done, S.stream));
   }
   return VAEL_OK;
 }
@@ -730,8 +761,10 @@ static int host_pipeline(const vael_circuit_t* c, const float* facts_h, const in
   // success or not, no copy may still be in flight when the caller gets its host buffers back
   cudaError_t first = cudaSuccess;
   for (int s = 0; s < kHostSlots; ++s) {
-    const cudaError_t e = cudaStreamSynchronize(c->slot[s].stream);
-    if (first == cudaSuccess) first = e;
+    for (cudaStream_t st : {c->slot[s].up, c->slot[s].stream}) {
+      const cudaError_t e = cudaStreamSynchronize(st);
+      if (first == cudaSuccess) first = e;
+    }
   }
   if (rc) return rc;
   if (first != cudaSuccess) return cuda_fail(first, "cudaStreamSynchronize");

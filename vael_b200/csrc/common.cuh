@@ -170,7 +170,9 @@ constexpr int kHostSlots = 4;  // stages of the host-buffer pipeline (one stream
 
 // Opaque handle behind vael_circuit_t (include/vael_b200.h)
 struct vael_host_slot {  // one stage of the host-buffer (e2e) pipeline
-  cudaStream_t stream;
+  cudaStream_t stream;       // kernels and device->host copies
+  cudaStream_t up;           // host->device copies: never queued behind a download of the same chunk
+  cudaEvent_t facts_up, grads_up, done;   // uploads landed (recorded on `up`), slot free again (on `stream`)
   float *facts, *worlds, *query, *gw, *gq, *gf;
   int32_t* qidx;
 };
