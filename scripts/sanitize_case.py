@@ -52,6 +52,7 @@ circuit_queries_all(dcm, f.detach())                       # member-list all-que
 z = torch.randn(37, 18, device=dev, requires_grad=True)
 facts_from_logits_clipped(z, 2, 1e-5, 0.9999).sum().backward()
 tabs = mario_tables(fam)
+os.environ["VAEL_GUMBEL_ROWS"] = "1"   # lane <-> row Gumbel kernels at these small batches too
 w_adm = torch.from_numpy(tabs[2].astype("float32")).to(dev)   # [24, 18] Herbrand table of the admissible worlds
 wh, idx, ys = gumbel_world(lw.detach().requires_grad_(True), w_adm, is_log=True, seed=3)   # lane <-> row, log domain
 wh.sum().backward()
@@ -60,6 +61,7 @@ pp = torch.softmax(torch.randn(45, 100, device=dev), 1).requires_grad_(True)
 for nz in (None, -torch.empty(45, 100, device=dev).exponential_().log()):
     wh, idx, ys = gumbel_world(pp, dense_path.herbrand_base(20).to(dev), seed=4, noise=nz)   # lane <-> row, padded lists
     (wh * torch.randn_like(wh)).sum().backward()
+os.environ["VAEL_GUMBEL_ROWS"] = "0"
 p81 = torch.softmax(torch.randn(33, 81, device=dev), 1).requires_grad_(True)                 # one warp per row
 wh, idx, ys = gumbel_world(p81, (torch.rand(81, 18, device=dev) < 0.3).float(), seed=1)
 wh.sum().backward()

@@ -73,11 +73,14 @@ def test_gumbel_world_matches_reference_golden(cuda_device):
     assert rel_err(gw.cpu().numpy(), ref, floor=1e-4 * np.abs(ref).max()) < 1e-4
 
 
-# (100, 20), (24, 18), (128, 32), (16, 5), (64, 7): lane <-> row kernels (gumbel_rows.cu); the rest: one warp per row
+# (100, 20), (24, 18), (128, 32), (16, 5), (64, 7): shapes the lane <-> row kernels (gumbel_rows.cu) take when
+# VAEL_GUMBEL_ROWS=1 forces them at this batch size; "0": the one-warp-per-row kernels for every shape
+@pytest.mark.parametrize("family", ["0", "1"])
 @pytest.mark.parametrize("W,H,is_log", [(100, 20, False), (24, 18, True), (81, 18, False), (1000, 30, False), (7, 3, True),
                                         (128, 32, False), (16, 5, True), (64, 7, False), (100, 33, False)])
-def test_gumbel_world_matches_oracle(cuda_device, W, H, is_log):
+def test_gumbel_world_matches_oracle(cuda_device, W, H, is_log, family, monkeypatch):
     from vael_b200.ops import gumbel_world
+    monkeypatch.setenv("VAEL_GUMBEL_ROWS", family)
     B = 193
     gen = torch.Generator().manual_seed(W)
     p = torch.softmax(2 * torch.randn(B, W, generator=gen), 1)
@@ -99,10 +102,10 @@ def test_gumbel_world_matches_oracle(cuda_device, W, H, is_log):
 
 
 @pytest.mark.parametrize("tau", [1.0, 0.4, 2.5])
-def test_gumbel_rows_kernels_equal_warp_per_row_kernels(cuda_device, tau, tmp_path):
+def test_gumbel_rows_kernels_equal_warp_per_row_kernels(cuda_device, tau, monkeypatch):
     """The two kernel families on the same inputs (real Herbrand base, injected noise, a temperature, a tail tile, views
     that are only 4-byte aligned): same worlds, y_soft within 1e-5, adjoints within 1e-5 of the largest entry."""
-    import subprocess, sys, os, json
+    from vael_b200 import _lib
     from vael_b200.ops import gumbel_world
     gen = torch.Generator().manual_seed(int(tau * 10))
     B, W, H = 32 * 9 + 5, 100, 20
@@ -121,36 +124,31 @@ def test_gumbel_rows_kernels_equal_warp_per_row_kernels(cuda_device, tau, tmp_pa
         (g,) = torch.autograd.grad((wh * up.cuda()).sum(), [sc])
         return wh.detach(), idx, ys, g
 
+    monkeypatch.setenv("VAEL_GUMBEL_ROWS", "1")
     a, b = run(0), run(1)
     for x, y in zip(a, b):
         assert torch.equal(x, y)
-    # the one-warp-per-row kernels on the same inputs: a child process with VAEL_GUMBEL_ROWS=0 (read once per process)
-    case, out = str(tmp_path / "case.pt"), str(tmp_path / "out.pt")
-    torch.save({"p": p, "noise": noise, "up": up, "tau": tau}, case)
-    code = (
-        "import torch, sys; sys.path.insert(0, %r)\n"
-        "from vael_b200.ops import gumbel_world\n"
-        "from oracle import dense_path\n"
-        "c = torch.load(%r)\n"
-        "sc = c['p'].cuda().requires_grad_(True)\n"
-        "wh, idx, ys = gumbel_world(sc, dense_path.herbrand_base(20).cuda(), tau=c['tau'], is_log=False, noise=c['noise'].cuda())\n"
-        "(g,) = torch.autograd.grad((wh * c['up'].cuda()).sum(), [sc])\n"
-        "torch.save({'wh': wh.detach().cpu(), 'idx': idx.cpu(), 'ys': ys.cpu(), 'g': g.cpu()}, %r)\n"
-    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), case, out)
-    env = dict(os.environ, VAEL_GUMBEL_ROWS="0")
-    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
-    o = torch.load(out)
-    assert torch.equal(a[1].cpu(), o["idx"])
-    np.testing.assert_allclose(a[2].cpu().numpy(), o["ys"].numpy(), rtol=1e-5, atol=1e-12)
-    np.testing.assert_allclose(a[0].cpu().numpy(), o["wh"].numpy(), atol=2.4e-7)
-    gm = o["g"].abs().max().item()
-    assert (a[3].cpu() - o["g"]).abs().max().item() <= 1e-5 * gm
+    monkeypatch.setenv("VAEL_GUMBEL_ROWS", "0")
+    o = run(0)
+    assert torch.equal(a[1], o[1])
+    np.testing.assert_allclose(a[2].cpu().numpy(), o[2].cpu().numpy(), rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(a[0].cpu().numpy(), o[0].cpu().numpy(), atol=2.4e-7)
+    gm = o[3].abs().max().item()
+    assert (a[3] - o[3]).abs().max().item() <= 1e-5 * gm
+    # the default: the lane <-> row kernels from 16 Ki rows up (same worlds as the forced run at a large batch)
+    monkeypatch.delenv("VAEL_GUMBEL_ROWS")
+    big = p.repeat(64, 1).cuda()
+    _, i_auto, _ = gumbel_world(big, hb, tau=tau, seed=3)
+    monkeypatch.setenv("VAEL_GUMBEL_ROWS", "1")
+    _, i_rows, _ = gumbel_world(big, hb, tau=tau, seed=3)
+    assert torch.equal(i_auto, i_rows)
 
 
-def test_gumbel_rows_philox_sampling_follows_world_distribution(cuda_device):
+def test_gumbel_rows_philox_sampling_follows_world_distribution(cuda_device, monkeypatch):
     """The lane <-> row kernel's own Philox stream (W = 100, the training shape): deterministic per seed, worlds
     distributed like P(w), y_soft a distribution whose arg-max is the sampled world."""
     from vael_b200.ops import gumbel_world
+    monkeypatch.setenv("VAEL_GUMBEL_ROWS", "1")
     W, B = 100, 600000
     p = torch.softmax(1.5 * torch.randn(1, W, generator=torch.Generator().manual_seed(5)), 1)
     scores = p.expand(B, W).contiguous().cuda()

@@ -10,7 +10,9 @@
 // loads and rewrites it IN PLACE — scores -> perturbed logits z -> exp2(z - max) -> y_soft — so max / arg-max / sum
 // are plain register chains, nothing W-sized lives in registers (the first version kept z[W] there: 190-255
 // registers, 5 warps per SM, one instruction every 5 cycles), and the finished tile leaves by one bulk store.
-// A tile buffer is single: ~12 resident warps per SM hide the load latency of one another.
+// A tile buffer is single: ~12 resident warps per SM hide the load latency of one another.  These are
+// THROUGHPUT kernels: the dispatcher takes them from 16 Ki rows up (below, a lane's ~4.6 k instructions are a latency
+// floor the one-warp-per-row kernels do not have).
 // Shapes: W a multiple of 4 whose tile fits (W <= 256), H <= 32; anything else stays on the one-warp-per-row
 // kernels.  The Herbrand table is ANY [W, H] float table (0/1 in VAEL): the forward copies row `arg` of a
 // shared-memory copy; the adjoint needs G_e = sum_h gh[h] H[e,h] and walks the non-zero columns of each world —
@@ -336,11 +338,20 @@ cudaError_t launch_rows(K kernel, const GumbelParams& P, const GrLayout& L, int 
 
 }  // namespace
 
+// Below ~16 Ki rows the one-warp-per-row kernels win: a lane here runs ~4.6 k instructions for its row whatever the
+// batch, a ~14 us floor (scripts/gumbel_small_batch.py: 4096 rows 14.1 / 13.3 us against 5.9 / 6.9 us; 16 Ki rows
+// 14.5 / 13.4 against 13.8 / 15.4; 256 Ki rows 76 / 84 against 174 / 214).  VAEL_GUMBEL_ROWS (read per call, so that
+// tests can flip it): 0 = never, 1 = whenever the shape allows, unset = from kRowsMinBatch rows up.
+constexpr long long kRowsMinBatch = 16384;
+
 bool gumbel_rows_ok(const GumbelParams& P, bool backward) {
-  static const bool off = [] { const char* v = getenv("VAEL_GUMBEL_ROWS"); return v != nullptr && v[0] == '0'; }();
-  if (off || P.W < 4 || (P.W & 3) != 0 || P.W > 256 || P.H < 1 || P.H > 32 || P.B < 1) return false;
+  const char* env = getenv("VAEL_GUMBEL_ROWS");
+  const bool never = env != nullptr && env[0] == '0', always = env != nullptr && env[0] == '1';
+  if (never || P.W < 4 || (P.W & 3) != 0 || P.W > 256 || P.H < 1 || P.H > 32 || P.B < 1) return false;
+  if (!always && P.B < kRowsMinBatch) return false;
   const GrLayout L = gr_layout(P.W, P.H, backward, !backward && P.noise != nullptr, backward && !P.is_log);
-  return gr_shape(L).nw * gr_shape(L).ctas >= 4;   // fewer resident warps than that: the one-warp-per-row kernels
+  const GrShape S = gr_shape(L);
+  return S.nw * S.ctas >= 4;   // fewer resident warps than that: the one-warp-per-row kernels
 }
 
 cudaError_t gumbel_rows_forward(const GumbelParams& P, int num_sms, cudaStream_t st) {
