@@ -146,11 +146,11 @@ __global__ void __launch_bounds__(128, FAST ? 6 : 1) fused_forward_kernel(const 
   const bool in_al = aligned16(P.logits);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < P.B; row += stride) {
-    float x[F], y[F], zs[2], f[F];
+    float x[F], y[F], rz[2], zs[2], f[F];
     load_row<F>(P.logits, row, x, in_al);
-    facts_row<2, N>(x, P.eps, y, zs);
+    facts_row<2, N>(x, P.eps, y, rz, zs);
 #pragma unroll
-    for (int c = 0; c < F; ++c) f[c] = (y[c] + P.eps) / zs[c / N];
+    for (int c = 0; c < F; ++c) f[c] = (y[c] + P.eps) * rz[c / N];
     if (P.facts != nullptr) store_row<F>(P.facts, row, f, aligned16(P.facts));
     uint32_t m[MW];
     fused_mask<MW>(m, P, row);
@@ -212,11 +212,11 @@ __global__ void __launch_bounds__(128, MINB) fused_backward_kernel(const FusedPa
   const bool in_al = aligned16(P.logits);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < P.B; row += stride) {
-    float x[F], y[F], zs[2], f[F];
+    float x[F], y[F], rz[2], zs[2], f[F];
     load_row<F>(P.logits, row, x, in_al);
-    facts_row<2, N>(x, P.eps, y, zs);
+    facts_row<2, N>(x, P.eps, y, rz, zs);
 #pragma unroll
-    for (int c = 0; c < F; ++c) f[c] = (y[c] + P.eps) / zs[c / N];
+    for (int c = 0; c < F; ++c) f[c] = (y[c] + P.eps) * rz[c / N];
     uint32_t m[MW];
     fused_mask<MW>(m, P, row);
     float df[F];
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(128, MINB) fused_backward_kernel(const FusedPa
     for (int g = 0; g < 2; ++g) {
       float dy[N], dot = 0.0f;
 #pragma unroll
-      for (int i = 0; i < N; ++i) { dy[i] = df[g * N + i] / zs[g]; dot = fmaf(y[g * N + i], dy[i], dot); }
+      for (int i = 0; i < N; ++i) { dy[i] = df[g * N + i] * rz[g]; dot = fmaf(y[g * N + i], dy[i], dot); }
 #pragma unroll
       for (int i = 0; i < N; ++i) dx[g * N + i] = y[g * N + i] * (dy[i] - dot);
     }

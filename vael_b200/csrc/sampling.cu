@@ -284,15 +284,15 @@ __global__ void __launch_bounds__(128) facts_tile_kernel(const float* __restrict
     const int rows = (int)min((long long)kWarp, B - sub * kWarp);
     lx.wait(s);
     if (BWD) lg.wait(s);
-    float x[F], y[F], zs[NG], gfr[BWD ? F : 1], o[F];
+    float x[F], y[F], rz[NG], gfr[BWD ? F : 1], o[F];
     tile_row_load<F>(lx.stage(s) + lane * F, x);
     if (BWD) tile_row_load<F>(lg.stage(s) + lane * F, gfr);
     __syncwarp();
     request(sub + kFactsStages * GW, s);
-    facts_row<NG, N>(x, eps, y, zs);
+    facts_row<NG, N>(x, eps, y, rz);
     if (!BWD) {
 #pragma unroll
-      for (int c = 0; c < F; ++c) o[c] = CLIP ? fminf(fmaxf(y[c], eps), hi) : (y[c] + eps) / zs[c / N];
+      for (int c = 0; c < F; ++c) o[c] = CLIP ? fminf(fmaxf(y[c], eps), hi) : (y[c] + eps) * rz[c / N];
     } else {
       // f = (y + eps) / Z with Z detached -> dL/dy_i = gf_i / Z (CLIP: gf_i where eps <= y_i <= hi, else 0);
       // softmax: dx_i = y_i (dy_i - sum_j y_j dy_j)
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(128) facts_tile_kernel(const float* __restrict
 #pragma unroll
         for (int i = 0; i < N; ++i) {
           const float yi = y[g * N + i];
-          dy[i] = CLIP ? ((yi >= eps && yi <= hi) ? gfr[g * N + i] : 0.0f) : gfr[g * N + i] / zs[g];
+          dy[i] = CLIP ? ((yi >= eps && yi <= hi) ? gfr[g * N + i] : 0.0f) : gfr[g * N + i] * rz[g];
           dot = fmaf(yi, dy[i], dot);
         }
 #pragma unroll
@@ -359,17 +359,19 @@ __global__ void __launch_bounds__(256) facts_forward_kernel(const float* __restr
     for (int i = 0; i < group; ++i) mx = fmaxf(mx, __ldg(x + i));
     float s = 0.0f;
     for (int i = 0; i < group; ++i) s += expf(__ldg(x + i) - mx);
+    const float rs = 1.0f / s;   // reciprocals per group, as facts_row
     if (hi > 0.0f) {  // clip mode
-      for (int i = 0; i < group; ++i) y[i] = fminf(fmaxf(expf(__ldg(x + i) - mx) / s, eps), hi);
+      for (int i = 0; i < group; ++i) y[i] = fminf(fmaxf(expf(__ldg(x + i) - mx) * rs, eps), hi);
       continue;
     }
     float zsum = 0.0f;
     for (int i = 0; i < group; ++i) {
-      const float v = expf(__ldg(x + i) - mx) / s + eps;
+      const float v = expf(__ldg(x + i) - mx) * rs + eps;
       y[i] = v;
       zsum += v;
     }
-    for (int i = 0; i < group; ++i) y[i] = y[i] / zsum;
+    const float rz = 1.0f / zsum;
+    for (int i = 0; i < group; ++i) y[i] = y[i] * rz;
   }
 }
 
@@ -386,26 +388,28 @@ __global__ void __launch_bounds__(256) facts_backward_kernel(const float* __rest
     for (int i = 0; i < group; ++i) mx = fmaxf(mx, __ldg(x + i));
     float s = 0.0f;
     for (int i = 0; i < group; ++i) s += expf(__ldg(x + i) - mx);
+    const float rs = 1.0f / s;
     if (hi > 0.0f) {  // clip mode: dy_i = gf_i where eps <= y_i <= hi, else 0
       float dotc = 0.0f;
       for (int i = 0; i < group; ++i) {
-        const float yi = expf(__ldg(x + i) - mx) / s;
+        const float yi = expf(__ldg(x + i) - mx) * rs;
         dotc = fmaf(yi, (yi >= eps && yi <= hi) ? __ldg(gf + i) : 0.0f, dotc);
       }
       for (int i = 0; i < group; ++i) {
-        const float yi = expf(__ldg(x + i) - mx) / s;
+        const float yi = expf(__ldg(x + i) - mx) * rs;
         gx[i] = yi * (((yi >= eps && yi <= hi) ? __ldg(gf + i) : 0.0f) - dotc);
       }
       continue;
     }
     float zsum = 0.0f;
-    for (int i = 0; i < group; ++i) zsum += expf(__ldg(x + i) - mx) / s + eps;
+    for (int i = 0; i < group; ++i) zsum += expf(__ldg(x + i) - mx) * rs + eps;
+    const float rz = 1.0f / zsum;
     // f = (y + eps) / Z with Z detached  ->  dL/dy_i = gf_i / Z ; softmax: dx_i = y_i (dy_i - sum_j y_j dy_j)
     float dot = 0.0f;
-    for (int i = 0; i < group; ++i) dot = fmaf(expf(__ldg(x + i) - mx) / s, __ldg(gf + i) / zsum, dot);
+    for (int i = 0; i < group; ++i) dot = fmaf(expf(__ldg(x + i) - mx) * rs, __ldg(gf + i) * rz, dot);
     for (int i = 0; i < group; ++i) {
-      const float yi = expf(__ldg(x + i) - mx) / s;
-      gx[i] = yi * (__ldg(gf + i) / zsum - dot);
+      const float yi = expf(__ldg(x + i) - mx) * rs;
+      gx[i] = yi * (__ldg(gf + i) * rz - dot);
     }
   }
 }

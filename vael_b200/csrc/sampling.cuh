@@ -57,8 +57,12 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 
+// One row of the facts head: per group softmax y, and rz[g] = 1 / sum_i (y_i + eps) (the detached normaliser of
+// models/vael.py:159-177, as a reciprocal).  Two divisions per GROUP — 1/s and 1/Z — and multiplications per element:
+// within 1.5 ulp of the reference's element-wise divisions, and ~290 fewer instructions per row of 2 x 10 logits
+// (the IEEE division is ~8 instructions; the stand-alone kernel was issue-limited at 0.66 of HBM with 40 of them).
 template <int NG, int N>
-__device__ __forceinline__ void facts_row(const float* x, float eps, float* y, float* zs) {
+__device__ __forceinline__ void facts_row(const float* x, float eps, float* y, float* rz, float* zs = nullptr) {
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
     float mx = x[g * N];
@@ -67,10 +71,12 @@ __device__ __forceinline__ void facts_row(const float* x, float eps, float* y, f
     float e[N], s = 0.0f;
 #pragma unroll
     for (int i = 0; i < N; ++i) { e[i] = expf(x[g * N + i] - mx); s += e[i]; }
+    const float rs = 1.0f / s;
     float zsum = 0.0f;
 #pragma unroll
-    for (int i = 0; i < N; ++i) { y[g * N + i] = e[i] / s; zsum += y[g * N + i] + eps; }
-    zs[g] = zsum;
+    for (int i = 0; i < N; ++i) { y[g * N + i] = e[i] * rs; zsum += y[g * N + i] + eps; }
+    rz[g] = 1.0f / zsum;
+    if (zs != nullptr) zs[g] = zsum;
   }
 }
 
