@@ -113,8 +113,7 @@ __global__ void __launch_bounds__(256, 2) gumbel_rows_forward_kernel(const Gumbe
         nz[0] = nv.x; nz[1] = nv.y; nz[2] = nv.z; nz[3] = nv.w;
       } else {
         const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)g, 1u), key);
-        nz[0] = log2_exp_variate(r.x); nz[1] = log2_exp_variate(r.y);
-        nz[2] = log2_exp_variate(r.z); nz[3] = log2_exp_variate(r.w);
+        log2_exp_variates4(r, nz);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {

@@ -44,8 +44,7 @@ namespace vael {
 __device__ __forceinline__ void noise_block(long long row, int blk, uint64_t seed, float* L4) {
   const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)blk, 0x5eedu),
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  L4[0] = log2_exp_variate(r.x); L4[1] = log2_exp_variate(r.y);
-  L4[2] = log2_exp_variate(r.z); L4[3] = log2_exp_variate(r.w);
+  log2_exp_variates4(r, L4);
 }
 
 template <int F>
@@ -115,16 +114,19 @@ __device__ __forceinline__ void perturbed_logits(const FusedParams& P, long long
   if (qsum != nullptr) *qsum = acc;
 }
 
-// FAST: s log p per column and the row's upper bound M of every perturbed logit (Philox noise only)
+// FAST: s log p per column, with the row's upper bound M of every perturbed logit (Philox noise only) already
+// subtracted from the first AD's columns: lps[i] + lps[N + k] - L / tau is then z - M <= 0, ready for exp2
 template <int N>
-__device__ __forceinline__ float scaled_logs_and_bound(const float* f, float inv_tau, float* lps) {
+__device__ __forceinline__ void scaled_logs_minus_bound(const float* f, float inv_tau, float* lps) {
   const float s = inv_tau * kLog2e;
 #pragma unroll
   for (int c = 0; c < 2 * N; ++c) lps[c] = s * __logf(f[c]);
   float m1 = lps[0], m2 = lps[N];
 #pragma unroll
   for (int i = 1; i < N; ++i) { m1 = fmaxf(m1, lps[i]); m2 = fmaxf(m2, lps[N + i]); }
-  return m1 + m2 - kLogE2Min * inv_tau;
+  const float M = m1 + m2 - kLogE2Min * inv_tau;
+#pragma unroll
+  for (int i = 0; i < N; ++i) lps[i] -= M;
 }
 
 template <int MW>
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(128, FAST ? 6 : 1) fused_forward_kernel(const 
     int arg;
     if constexpr (FAST) {
       float lps[F];
-      const float M = scaled_logs_and_bound<N>(f, inv_tau, lps);
+      scaled_logs_minus_bound<N>(f, inv_tau, lps);
       float mx = -INFINITY, sum = 0.0f, q = 0.0f, L4[4];
       arg = 0;
 #pragma unroll
@@ -166,12 +168,12 @@ __global__ void __launch_bounds__(128, FAST ? 6 : 1) fused_forward_kernel(const 
         const int i = e / N, k = e % N;
         if ((e & 3) == 0) noise_block(row, e >> 2, seed, L4);
         if (P.query != nullptr && ((m[e >> 5] >> (e & 31)) & 1u)) q = __fadd_rn(q, __fmul_rn(f[i], f[N + k]));
-        const float z = fmaf(L4[e & 3], -inv_tau, lps[i] + lps[N + k]);
+        const float z = fmaf(L4[e & 3], -inv_tau, lps[i] + lps[N + k]);   // perturbed logit minus M
         if (z > mx) { mx = z; arg = e; }
-        sum += fast_exp2(z - M);
+        sum += fast_exp2(z);
       }
       if (P.query != nullptr) P.query[row] = q;
-      ys = fast_exp2(mx - M) / sum;
+      ys = fast_exp2(mx) / sum;
     } else {
       float z[W], mx, q;
       perturbed_logits<N>(P, row, seed, f, m, inv_tau, z, mx, arg, &q);
@@ -223,27 +225,30 @@ __global__ void __launch_bounds__(128, MINB) fused_backward_kernel(const FusedPa
 #pragma unroll
     for (int c = 0; c < F; ++c) df[c] = 0.0f;
     if (P.grad_world_h != nullptr && FAST) {
-      float gh[F], lps[F], Pc[F], Ac[F];
+      // With p_e = exp2(z_e - M): P[c] = sum of p over the worlds of column c, and A[c] = sum of p_e G_e with
+      // G_e = gh[i] + gh[N + k] splits into gh[c] P[c] plus the cross term R[i] = sum_k p_ik gh[N + k] (resp.
+      // C[k] = sum_i p_ik gh[i]): two additions and two FMAs per world instead of the add, the product and four sums
+      float gh[F], lps[F], Pc[F], Xc[F];
       load_row<F>(P.grad_world_h, row, gh, aligned16(P.grad_world_h));
-      const float M = scaled_logs_and_bound<N>(f, inv_tau, lps);
+      scaled_logs_minus_bound<N>(f, inv_tau, lps);
 #pragma unroll
-      for (int c = 0; c < F; ++c) Pc[c] = Ac[c] = 0.0f;
+      for (int c = 0; c < F; ++c) Pc[c] = Xc[c] = 0.0f;
       float L4[4];
 #pragma unroll
       for (int e = 0; e < W; ++e) {
         const int i = e / N, k = e % N;
         if ((e & 3) == 0) noise_block(row, e >> 2, seed, L4);
-        const float pe = fast_exp2(fmaf(L4[e & 3], -inv_tau, lps[i] + lps[N + k]) - M);
-        const float t = pe * (gh[i] + gh[N + k]);
+        const float pe = fast_exp2(fmaf(L4[e & 3], -inv_tau, lps[i] + lps[N + k]));
         Pc[i] += pe; Pc[N + k] += pe;
-        Ac[i] += t; Ac[N + k] += t;
+        Xc[i] = fmaf(pe, gh[N + k], Xc[i]);
+        Xc[N + k] = fmaf(pe, gh[i], Xc[N + k]);
       }
       float S = 0.0f, D = 0.0f;
 #pragma unroll
-      for (int i = 0; i < N; ++i) { S += Pc[i]; D += Ac[i]; }
+      for (int i = 0; i < N; ++i) { S += Pc[i]; D += fmaf(gh[i], Pc[i], Xc[i]); }
       const float dot = D / S, scale = inv_tau / S;
 #pragma unroll
-      for (int c = 0; c < F; ++c) df[c] = fmaf(-dot, Pc[c], Ac[c]) * scale / f[c];
+      for (int c = 0; c < F; ++c) df[c] = fmaf(gh[c] - dot, Pc[c], Xc[c]) * scale / f[c];
     } else if (P.grad_world_h != nullptr) {
       float z[W], mx;
       int arg;

@@ -49,6 +49,22 @@ __device__ __forceinline__ float log2_exp_variate(uint32_t bits) {
   const float e2 = (v < 1.0f / 1024.0f) ? series : -__log2f(u);
   return __log2f(e2);
 }
+// The four variates of one Philox call.  The guard is taken per CALL, on the integers: the series is needed when one
+// of the four 23-bit numbers lies in the top 2^13 (v < 2^-10) — one call in 256 — and that rare path is a real branch
+// (the same values as four log2_exp_variate calls; 1.25 instead of 5 guard instructions per variate).
+__device__ __forceinline__ void log2_exp_variates4(uint4 r, float* L4) {
+  const uint32_t k0 = r.x >> 9, k1 = r.y >> 9, k2 = r.z >> 9, k3 = r.w >> 9;
+  if (max(max(k0, k1), max(k2, k3)) > 8388608u - 8192u - 1u) {
+    L4[0] = log2_exp_variate(r.x); L4[1] = log2_exp_variate(r.y);
+    L4[2] = log2_exp_variate(r.z); L4[3] = log2_exp_variate(r.w);
+    return;
+  }
+  constexpr float kScale = 1.0f / 8388608.0f;
+  L4[0] = __log2f(-__log2f((static_cast<float>(k0) + 0.5f) * kScale));
+  L4[1] = __log2f(-__log2f((static_cast<float>(k1) + 0.5f) * kScale));
+  L4[2] = __log2f(-__log2f((static_cast<float>(k2) + 0.5f) * kScale));
+  L4[3] = __log2f(-__log2f((static_cast<float>(k3) + 0.5f) * kScale));
+}
 // 2^x, x <= 0 (MUFU.EX2; 2 ulp): the softmax runs in the log2 domain, the log2(e) factor folded into 1/tau
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
