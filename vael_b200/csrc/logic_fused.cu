@@ -140,8 +140,10 @@ __device__ __forceinline__ void fused_mask(uint32_t* m, const FusedParams& P, lo
   }
 }
 
-template <int N, bool FAST>
-__global__ void __launch_bounds__(128, FAST ? 6 : 1) fused_forward_kernel(const FusedParams P) {
+// FMINB: resident CTAs per SM the register allocation is capped for (FAST: 6 -> 80 registers, the throughput shape;
+// 1 -> no cap: more of the 25 independent Philox chains in flight per lane, the latency shape for small batches)
+template <int N, bool FAST, int FMINB = (FAST ? 6 : 1)>
+__global__ void __launch_bounds__(128, FMINB) fused_forward_kernel(const FusedParams P) {
   constexpr int F = 2 * N, W = N * N, MW = (W + 31) / 32;
   const uint64_t seed = P.seed_dev ? *P.seed_dev : P.seed;
   const float inv_tau = 1.0f / P.tau;
@@ -329,9 +331,13 @@ static bool fused_fast_ok(const FusedParams& P) {
 
 template <bool BWD, bool FAST>
 static cudaError_t fused_launch(int n, const FusedParams& P, int grid, int block, cudaStream_t st) {
-  static const int minb = getenv("VAEL_FUSED_BWD_MINB") ? atoi(getenv("VAEL_FUSED_BWD_MINB")) : 4;
+  static const int minb_env = getenv("VAEL_FUSED_BWD_MINB") ? atoi(getenv("VAEL_FUSED_BWD_MINB")) : 0;
+  static const int fminb_env = getenv("VAEL_FUSED_FWD_MINB") ? atoi(getenv("VAEL_FUSED_FWD_MINB")) : 0;
+  const bool small = block == 32;   // fused_shape: fewer rows than one four-warp CTA per SM would take
+  const int minb = minb_env ? minb_env : (small ? 1 : 4), fminb = fminb_env ? fminb_env : (small ? 1 : 6);
   if (n == 10) {
-    if (BWD && FAST && minb == 4) fused_backward_kernel<10, FAST, 4><<<grid, block, 0, st>>>(P);
+    if (!BWD && FAST && fminb == 1) fused_forward_kernel<10, FAST, 1><<<grid, block, 0, st>>>(P);
+    else if (BWD && FAST && minb == 4) fused_backward_kernel<10, FAST, 4><<<grid, block, 0, st>>>(P);
     else if (BWD && FAST && minb == 5) fused_backward_kernel<10, FAST, 5><<<grid, block, 0, st>>>(P);
     else if (BWD && FAST && minb == 3) fused_backward_kernel<10, FAST, 3><<<grid, block, 0, st>>>(P);
     else if (BWD) fused_backward_kernel<10, FAST><<<grid, block, 0, st>>>(P);
