@@ -752,6 +752,10 @@ def secondary_probe(args, dev, rank, world, barrier, max_over_ranks, lib):
     # -- the training-mode logic path (models/vael.py:55-65): ONE fused kernel per direction against the three-stage
     # chain it replaces (facts head -> circuit -> Gumbel sampling), both with in-kernel Philox noise
     try:
+        out["stage_kernels"] = stage_kernels_probe(dev, rank, barrier, max_over_ranks, lib, peak)
+    except Exception as exc:   # noqa: BLE001
+        out["stage_kernels"] = {"error": repr(exc)[:300]}
+    try:
         out["logic_train_path"] = logic_path_probe(dev, rank, barrier, max_over_ranks, lib, peak)
     except Exception as exc:  # noqa: BLE001
         out["logic_train_path"] = {"error": repr(exc)[:300]}
@@ -764,6 +768,54 @@ def secondary_probe(args, dev, rank, world, barrier, max_over_ranks, lib):
                                  "rows_per_gpu": B2, "kernel_family": _lib.last_kernel(), "ms": a_ms,
                                  "bytes_per_row": 80 + 76, "GBs": B2 * 156 / a_ms / 1e6, "frac": B2 * 156 / a_ms / 1e6 / peak,
                                  "rows_per_sec": world * B2 / (a_ms * 1e-3)}
+    return out
+
+
+def stage_kernels_probe(dev, rank, barrier, max_over_ranks, lib, peak):
+    """The stand-alone kernels around the circuit (a14 facts head, a15/a16 Gumbel + Herbrand, a26 ELBO terms), each
+    alone at a streaming size, against the copy peak: algorithmic bytes per row / launch time."""
+    from vael_b200 import _lib, parallel
+    from vael_b200.ops import _p
+    sp = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device=dev).manual_seed(parallel.rank_seed(41, rank))
+    out = {"workload": "facts head [B,2x10] (fwd, adjoint), Gumbel-softmax(hard) + Herbrand [B,100] -> [B,20] (fwd with "
+                       "in-kernel Philox noise, adjoint), ELBO terms + gradients [B,1,28,56]; fp32, per-GPU rows fixed"}
+
+    def entry(ms, rows, bpr):
+        return {"ms": ms, "rows_per_gpu": rows, "bytes_per_row": bpr, "GBs": rows * bpr / ms / 1e6,
+                "frac": rows * bpr / ms / 1e6 / peak}
+
+    B = 1 << 21
+    x, gfa = torch.randn(B, 20, device=dev, generator=g), torch.randn(B, 20, device=dev, generator=g)
+    fo, gx = torch.empty(B, 20, device=dev), torch.empty(B, 20, device=dev)
+    f_ms, b_ms = _time_pair(lambda: _lib.check(lib.vael_facts_forward(_p(x), B, 2, 10, 1e-5, _p(fo), sp)),
+                            lambda: _lib.check(lib.vael_facts_backward(_p(x), _p(gfa), B, 2, 10, 1e-5, _p(gx), sp)),
+                            10, barrier, max_over_ranks)
+    out["facts_head"] = {"kernel": "facts_tile_kernel", "fwd": entry(f_ms, B, 160), "bwd": entry(b_ms, B, 240)}
+    del x, gfa, fo, gx
+    B = 1 << 20
+    p = torch.softmax(torch.randn(B, 100, device=dev, generator=g), 1)
+    hb = torch.cat([torch.eye(10).repeat_interleave(10, 0), torch.eye(10).repeat(10, 1)], 1).to(dev).contiguous()
+    ys, idx, wh = torch.empty(B, 100, device=dev), torch.empty(B, device=dev, dtype=torch.int32), torch.empty(B, 20, device=dev)
+    gh, gs = torch.randn(B, 20, device=dev, generator=g), torch.empty(B, 100, device=dev)
+    f_ms, b_ms = _time_pair(
+        lambda: _lib.check(lib.vael_gumbel_world_forward(_p(p), None, 7, B, 100, 0, 1.0, _p(hb), 20, _p(ys), _p(idx), _p(wh), sp)),
+        lambda: _lib.check(lib.vael_gumbel_world_backward(_p(p), _p(ys), _p(gh), B, 100, 0, 1.0, _p(hb), 20, _p(gs), sp)),
+        10, barrier, max_over_ranks)
+    out["gumbel_herbrand"] = {"kernel": "gumbel_rows_forward_kernel / gumbel_rows_backward_kernel (lane <-> row; from 16 Ki rows up)",
+                              "fwd": entry(f_ms, B, 884), "bwd": entry(b_ms, B, 1284),
+                              "bound": "forward: instruction issue (Philox4x32-10 + variate transforms); adjoint: resident warps"}
+    del p, ys, idx, wh, gh, gs
+    B = 65536
+    r, xi = torch.rand(B, 1, 28, 56, device=dev, generator=g), torch.rand(B, 1, 28, 56, device=dev, generator=g)
+    mu, lv = torch.randn(B, 23, device=dev, generator=g), torch.randn(B, 23, device=dev, generator=g)
+    q = torch.rand(B, device=dev, generator=g)
+    terms, gr, gm, glv, gq = torch.empty(4, device=dev), torch.empty_like(r), torch.empty_like(mu), torch.empty_like(lv), torch.empty_like(q)
+    ws = torch.zeros(int(lib.vael_elbo_workspace_bytes()), dtype=torch.uint8, device=dev)
+    e_ms, _ = _time_pair(lambda: _lib.check(lib.vael_elbo_terms(_p(r), _p(xi), B, 1568, _p(mu), _p(lv), 23, _p(q), 0.1, 1e-5, 1.0, 0,
+                                                                _p(terms), _p(gr), _p(gm), _p(glv), _p(gq), _p(ws), sp)),
+                         lambda: None, 10, barrier, max_over_ranks)
+    out["elbo_terms"] = {"kernel": "elbo_terms_kernel", "terms_and_grads": entry(e_ms, B, 1568 * 12)}
     return out
 
 
