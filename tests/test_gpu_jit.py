@@ -200,3 +200,36 @@ def test_jit_scope_and_fallback(cuda_device):
     assert _lib.last_kernel() == "generic-csr"
     w_ref, q_ref = fp_interp.forward(circ, f.cpu().numpy(), query=np.zeros(50, dtype=np.int64))
     np.testing.assert_array_equal(w.cpu().numpy(), w_ref)
+
+
+def test_jit_cubin_cache(cuda_device, tmp_path, monkeypatch):
+    """VAEL_JIT_CACHE_DIR: the first handle compiles and stores the cubin, the second loads it (no NVRTC run) and
+    computes the same bits; a cache file that does not load is dropped and rebuilt."""
+    import os
+    from vael_b200.mario_task import compile_mario_family
+    from vael_b200.ops import DeviceCircuit, circuit_forward
+    monkeypatch.setenv("VAEL_JIT_CACHE_DIR", str(tmp_path))
+    circ = compile_mario_family((3, 3)).circuit
+    f = torch.from_numpy(synthetic_facts(77, groups=(9, 9), seed=5)).cuda()
+    q = torch.arange(77, device="cuda") % circ.n_queries
+
+    def run():
+        dc = DeviceCircuit(circ, cuda_device)
+        ok, log = dc.jit_status()
+        assert ok, log
+        with torch.no_grad():
+            w, qq = circuit_forward(dc, f, q, force_jit=True)
+        return log, w, qq
+
+    log1, w1, q1 = run()
+    files = [p for p in os.listdir(tmp_path) if p.endswith(".cubin")]
+    assert len(files) == 1 and "from cache" not in log1, (files, log1)
+    log2, w2, q2 = run()
+    assert "from cache" in log2, log2
+    assert torch.equal(w1, w2) and torch.equal(q1, q2)
+    with open(tmp_path / files[0], "wb") as fh:
+        fh.write(b"not a cubin")
+    log3, w3, q3 = run()   # the unloadable file is dropped, the circuit compiled again and the cache rewritten
+    assert "from cache" not in log3 and "replaced" in log3, log3
+    assert torch.equal(w1, w3) and torch.equal(q1, q3)
+    assert os.path.getsize(tmp_path / files[0]) > 1000

@@ -19,6 +19,7 @@
 // Anything else, or a box without libnvrtc / libcuda, runs the interpreter: the JIT is an accelerator, never a
 // requirement (VAEL_JIT=0 switches it off).
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -49,6 +50,7 @@ struct JitApi {
   int (*nvrtcGetProgramLogSize)(nvrtcProgram, size_t*);
   int (*nvrtcGetProgramLog)(nvrtcProgram, char*);
   int (*nvrtcDestroyProgram)(nvrtcProgram*);
+  int (*nvrtcVersion)(int*, int*) = nullptr;   // optional: part of the cubin cache key
   int (*cuModuleLoadData)(CUmodule*, const void*);
   int (*cuModuleUnload)(CUmodule);
   int (*cuModuleGetFunction)(CUfunction*, CUmodule, const char*);
@@ -84,6 +86,7 @@ const JitApi& jit_api() {
     sym(rtc, "nvrtcGetProgramLog", api.nvrtcGetProgramLog);
     sym(rtc, "nvrtcDestroyProgram", api.nvrtcDestroyProgram);
     api.rtc_ok = all;
+    api.nvrtcVersion = reinterpret_cast<int (*)(int*, int*)>(dlsym(rtc, "nvrtcVersion"));
     if (!drv) { api.why = "libcuda not found"; return; }
     sym(drv, "cuModuleLoadData", api.cuModuleLoadData);
     sym(drv, "cuModuleUnload", api.cuModuleUnload);
@@ -917,6 +920,50 @@ std::string jit_source(const vael_circuit_desc_t* d) {
   return jit_eligible(d) ? source_for(d, &w, &wc) : std::string();
 }
 
+// ---- opt-in cubin cache ------------------------------------------------------
+static uint64_t fnv1a(const void* data, size_t n, uint64_t h = 1469598103934665603ull) {
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+static std::string jit_cache_path(const JitApi& A, const std::string& src) {
+  const char* dir = getenv("VAEL_JIT_CACHE_DIR");
+  if (dir == nullptr || *dir == 0) return std::string();
+  int ver[2] = {0, 0};
+  if (A.nvrtcVersion) A.nvrtcVersion(&ver[0], &ver[1]);
+  uint64_t h = fnv1a(src.data(), src.size());
+  h = fnv1a(ver, sizeof(ver), h);
+  static const char target[] = "sm_100a;c++17;fmad;lineinfo;abi2";
+  h = fnv1a(target, sizeof(target), h);
+  char name[64];
+  snprintf(name, sizeof(name), "/vael_jit_%016llx.cubin", static_cast<unsigned long long>(h));
+  return std::string(dir) + name;
+}
+static bool read_file(const std::string& path, std::vector<char>* out) {
+  FILE* fh = fopen(path.c_str(), "rb");
+  if (fh == nullptr) return false;
+  bool ok = false;
+  if (fseek(fh, 0, SEEK_END) == 0) {
+    const long n = ftell(fh);
+    if (n > 0 && fseek(fh, 0, SEEK_SET) == 0) {
+      out->resize(static_cast<size_t>(n));
+      ok = fread(out->data(), 1, static_cast<size_t>(n), fh) == static_cast<size_t>(n);
+    }
+  }
+  fclose(fh);
+  if (!ok) out->clear();
+  return ok;
+}
+// write to a temporary name and rename: a concurrent reader (another rank compiling the same circuit) sees either no
+// file or a complete one
+static void write_file_atomically(const std::string& path, const std::vector<char>& data) {
+  const std::string tmp = path + ".tmp" + std::to_string(static_cast<long long>(getpid()));
+  FILE* fh = fopen(tmp.c_str(), "wb");
+  if (fh == nullptr) return;
+  const bool ok = fwrite(data.data(), 1, data.size(), fh) == data.size();
+  if (fclose(fh) != 0 || !ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+}
+
 JitProgram* jit_create(const vael_circuit_desc_t* d) {
   JitProgram* J = new JitProgram();
   const JitApi& A = jit_api();
@@ -927,21 +974,41 @@ JitProgram* jit_create(const vael_circuit_desc_t* d) {
   if (const char* dump = getenv("VAEL_JIT_DUMP")) {
     if (FILE* fh = fopen(dump, "w")) { fputs(src.c_str(), fh); fclose(fh); }
   }
-  nvrtcProgram prog = nullptr;
-  if (A.nvrtcCreateProgram(&prog, src.c_str(), "vael_jit.cu", 0, nullptr, nullptr) != 0) { J->log = "nvrtcCreateProgram failed"; return J; }
-  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=true"};
-  const int rc = A.nvrtcCompileProgram(prog, 4, opts);
-  size_t logn = 0;
-  A.nvrtcGetProgramLogSize(prog, &logn);
-  if (logn > 1) { J->log.resize(logn); A.nvrtcGetProgramLog(prog, &J->log[0]); }
-  if (rc != 0) { A.nvrtcDestroyProgram(&prog); return J; }
-  size_t n = 0;
-  A.nvrtcGetCUBINSize(prog, &n);
-  std::vector<char> cubin(n);
-  A.nvrtcGetCUBIN(prog, cubin.data());
-  A.nvrtcDestroyProgram(&prog);
+  // Opt-in disk cache of the compiled cubin (VAEL_JIT_CACHE_DIR): NVRTC needs ~2 s for the 2-digit circuit's source
+  // and ~20 s for the 3-digit one's; the key is a hash of the generated source, the NVRTC version and the target.
+  std::vector<char> cubin;
+  const std::string cache_path = jit_cache_path(A, src);
+  auto compile = [&]() -> bool {
+    nvrtcProgram prog = nullptr;
+    if (A.nvrtcCreateProgram(&prog, src.c_str(), "vael_jit.cu", 0, nullptr, nullptr) != 0) { J->log = "nvrtcCreateProgram failed"; return false; }
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=true"};
+    const int rc = A.nvrtcCompileProgram(prog, 4, opts);
+    size_t logn = 0;
+    A.nvrtcGetProgramLogSize(prog, &logn);
+    J->log.clear();
+    if (logn > 1) { J->log.resize(logn); A.nvrtcGetProgramLog(prog, &J->log[0]); }
+    if (rc != 0) { A.nvrtcDestroyProgram(&prog); return false; }
+    size_t n = 0;
+    A.nvrtcGetCUBINSize(prog, &n);
+    cubin.resize(n);
+    A.nvrtcGetCUBIN(prog, cubin.data());
+    A.nvrtcDestroyProgram(&prog);
+    if (!cache_path.empty()) write_file_atomically(cache_path, cubin);   // best effort
+    return true;
+  };
+  const bool cached = !cache_path.empty() && read_file(cache_path, &cubin);
+  if (cached) J->log = "cubin from cache " + cache_path;
+  else if (!compile()) return J;
   cudaFree(nullptr);   // the runtime's primary context is current from here on
-  if (A.cuModuleLoadData(&J->mod, cubin.data()) != 0) { J->log += " cuModuleLoadData failed"; return J; }
+  if (A.cuModuleLoadData(&J->mod, cubin.data()) != 0) {
+    // a cache file that does not load (truncated, another toolkit's) is dropped and the circuit compiled afresh
+    if (!cached) { J->log += " cuModuleLoadData failed"; return J; }
+    remove(cache_path.c_str());
+    J->mod = nullptr;
+    if (!compile()) return J;
+    if (A.cuModuleLoadData(&J->mod, cubin.data()) != 0) { J->log += " cuModuleLoadData failed"; return J; }
+    J->log += " (unloadable cache file replaced)";
+  }
   auto get = [&](CUfunction* f, const char* name) { return A.cuModuleGetFunction(f, J->mod, name) == 0; };
   bool all = get(&J->fwd[0][0], "jit_fwd_00") && get(&J->fwd[1][0], "jit_fwd_10") && get(&J->qall[0], "jit_qall_0") &&
              get(&J->qall[1], "jit_qall_1") && get(&J->bwd[0], "jit_bwd_0") && get(&J->bwd[1], "jit_bwd_1");
