@@ -522,6 +522,12 @@ static bool make_map(CUtensorMap* map, const float* base, long long B, int W, in
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// the same map for the generated column-chunked kernels (circuit_jit.cu keeps the driver types out of its sources):
+// `map128` points at 128 bytes, 64-byte aligned
+bool make_row_box_map(void* map128, const float* base, long long B, int W, int C) {
+  return make_map(static_cast<CUtensorMap*>(map128), base, B, W, C);
+}
+
 static int adw_env(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;

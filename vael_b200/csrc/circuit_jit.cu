@@ -133,6 +133,15 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// 2-D tensor-map copies of a [32 rows, WC columns] box of a row-major [B,W] tensor (SASS UTMASTG / UTMALDG): rows
+// beyond B are clipped on the way out and zero-filled on the way in
+struct __align__(64) TensorMap { unsigned long long opaque[16]; };
+__device__ __forceinline__ void tma_store_2d(const TensorMap* tm, const void* src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(smem_u32(src)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const TensorMap* tm, int x, int y, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -622,6 +631,13 @@ WidePlan wide_plan(const vael_circuit_desc_t* d) {
   return P;
 }
 
+// store stages of the column-chunked forward: the box stores want few streams, each deep (the adw kernels' finding)
+static int wide_store_stages() {
+  const char* v = getenv("VAEL_JIT_WIDE_NSO");
+  const int n = (v && *v) ? atoi(v) : 4;
+  return std::max(2, std::min(6, n));
+}
+
 std::string generate_source_wide(const vael_circuit_desc_t* d, const WidePlan& PL) {
   const int N = d->n_nodes, F = d->n_facts, W = d->n_worlds, Q = d->n_queries, WC = PL.WC, NCH = PL.NCH;
   const int OC = std::max(WC, std::max(Q, 1));
@@ -630,7 +646,7 @@ std::string generate_source_wide(const vael_circuit_desc_t* d, const WidePlan& P
   std::ostringstream& o = g.o;
   o << kPrelude;
   o << "#define F " << F << "\n#define W " << W << "\n#define NQ " << Q << "\n#define WC " << WC << "\n#define NCH " << NCH
-    << "\n#define OC " << OC << "\n#define NST 2\n#define NSO 2\n#define NSG 2\n";
+    << "\n#define OC " << OC << "\n#define NST 2\n#define NSO 2\n#define NSF " << wide_store_stages() << "\n#define NSG 2\n";
   o << "#define FB ((32 * F * 4 + 127) / 128 * 128)\n#define OB ((32 * OC * 4 + 127) / 128 * 128)\n#define GB ((32 * WC * 4 + 127) / 128 * 128)\n";
   std::vector<char> out_cone(N, 0);
   for (int w = 0; w < W; ++w) out_cone[d->world_node[w]] = 1;
@@ -663,10 +679,10 @@ std::string generate_source_wide(const vael_circuit_desc_t* d, const WidePlan& P
   // ================================ forward ================================
   o << R"(
 template <bool NORM, bool QALL>
-__device__ __forceinline__ void fwd_body(const JitParams& P) {
+__device__ __forceinline__ void fwd_body(const JitParams& P, const TensorMap* tm_w) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  unsigned char* wb = smem + (size_t)warp * (128 + NST * FB + NSO * OB);
+  unsigned char* wb = smem + (size_t)warp * (128 + NST * FB + NSF * OB);
   uint64_t* bars = reinterpret_cast<uint64_t*>(wb);
   float* ostage = reinterpret_cast<float*>(wb + 128 + NST * FB);
   const long long n_sub = (P.B + 31) >> 5;
@@ -715,20 +731,22 @@ __device__ __forceinline__ void fwd_body(const JitParams& P) {
         if (PL.query_world[q] == w) o << "      qa" << q << " = v" << d->world_node[w] << ";\n";
     }
     o << "    }\n";
-    o << "    if (want_w) {\n      bulk_wait_read<NSO - 1>();   // this lane's row copy of two chunks ago has read its stage\n";
-    o << "      float* os = ostage + ((it * NCH + " << c << ") % NSO) * (OB / 4) + lane * WC;\n";
+    o << "    if (want_w) {\n      if (lane == 0) bulk_wait_read<NSF - 1>();   // the box store of NSF chunks ago has read its stage\n";
+    o << "      __syncwarp();\n";
+    o << "      float* ob = ostage + ((it * NCH + " << c << ") % NSF) * (OB / 4);\n      float* os = ob + lane * WC;\n";
     std::vector<std::string> e;
     for (int w = c0; w < c0 + WC; ++w) {
       const std::string v = "v" + std::to_string(d->world_node[w]);
       e.push_back("(NORM ? " + v + " / z : " + v + ")");
     }
     emit_row_stores(o, e, "os", "      ");
-    o << "      fence_proxy_async();\n      if (valid) bulk_s2g(P.worlds + row * W + " << c0 << ", os, WC * 4);\n      bulk_commit();\n    }\n";
+    o << "      fence_proxy_async();\n      __syncwarp();\n";
+    o << "      if (lane == 0) { tma_store_2d(tm_w, ob, " << c0 << ", (int)row0); bulk_commit(); }\n    }\n";
   }
   o << "    float qv = 0.0f;\n";
   for (int q = 0; q < Q; ++q) o << "    qv = (q == " << q << ") ? qa" << q << " : qv;\n";
-  o << "    if constexpr (QALL) {\n      if (lane == 0) bulk_wait_read<NSO - 1>();\n      __syncwarp();\n";
-  o << "      float* os = ostage + (it % NSO) * (OB / 4) + lane * NQ;\n";
+  o << "    if constexpr (QALL) {\n      if (lane == 0) bulk_wait_read<NSF - 1>();\n      __syncwarp();\n";
+  o << "      float* os = ostage + (it % NSF) * (OB / 4) + lane * NQ;\n";
   {
     std::vector<std::string> e;
     for (int q = 0; q < Q; ++q) e.push_back("(NORM ? qa" + std::to_string(q) + " / z : qa" + std::to_string(q) + ")");
@@ -736,17 +754,17 @@ __device__ __forceinline__ void fwd_body(const JitParams& P) {
   }
   o << R"(      fence_proxy_async();
       __syncwarp();
-      tile_store(P.queries_all + row0 * NQ, ostage + (it % NSO) * (OB / 4), rows * NQ, 32 * NQ, qall_al, lane);
+      tile_store(P.queries_all + row0 * NQ, ostage + (it % NSF) * (OB / 4), rows * NQ, 32 * NQ, qall_al, lane);
     }
     if (!QALL && P.query != nullptr && valid) P.query[row] = NORM ? qv / z : qv;
   }
   bulk_wait_all<0>();
   __syncwarp();
 }
-extern "C" __global__ void __launch_bounds__(256) jit_fwd_00(const JitParams P) { fwd_body<false, false>(P); }
-extern "C" __global__ void __launch_bounds__(256) jit_fwd_10(const JitParams P) { fwd_body<true, false>(P); }
-extern "C" __global__ void __launch_bounds__(256) jit_qall_0(const JitParams P) { fwd_body<false, true>(P); }
-extern "C" __global__ void __launch_bounds__(256) jit_qall_1(const JitParams P) { fwd_body<true, true>(P); }
+extern "C" __global__ void __launch_bounds__(256) jit_fwd_00(const JitParams P, const __grid_constant__ TensorMap tm) { fwd_body<false, false>(P, &tm); }
+extern "C" __global__ void __launch_bounds__(256) jit_fwd_10(const JitParams P, const __grid_constant__ TensorMap tm) { fwd_body<true, false>(P, &tm); }
+extern "C" __global__ void __launch_bounds__(256) jit_qall_0(const JitParams P, const __grid_constant__ TensorMap tm) { fwd_body<false, true>(P, &tm); }
+extern "C" __global__ void __launch_bounds__(256) jit_qall_1(const JitParams P, const __grid_constant__ TensorMap tm) { fwd_body<true, true>(P, &tm); }
 )";
 
   // ================================ backward ================================
@@ -759,7 +777,7 @@ extern "C" __global__ void __launch_bounds__(256) jit_qall_1(const JitParams P) 
   for (int n = 0; n < N; ++n) live[n] = out_cone[n] && has_leaf[n];
   o << R"(
 template <bool NORM>
-__device__ __forceinline__ void bwd_body(const JitParams& P) {
+__device__ __forceinline__ void bwd_body(const JitParams& P, const TensorMap* tm_g) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   unsigned char* wb = smem + (size_t)warp * (128 + NST * FB + NSG * GB + NSO * FB);
@@ -784,15 +802,16 @@ __device__ __forceinline__ void bwd_body(const JitParams& P) {
   auto request = [&](long long sub, int s) {
     if (sub < n_sub) ld.issue(s, P.facts + sub * 32 * F, (int)min(32LL, P.B - sub * 32) * F, 0, nullptr, 0, in_al, lane, 0.5f);
   };
-  // chunk ring: every lane copies its own row segment; the chunks of all tiles of this warp form one sequence gc
+  // chunk ring: one [32, WC] box of the upstream gradient per chunk (rows beyond B arrive as zeros); the chunks of all
+  // tiles of this warp form one sequence gc
   unsigned gc = 0;   // chunks consumed so far
   auto gissue = [&](long long sub, int c, unsigned k) {   // chunk c of tile `sub` as the k-th chunk of the sequence
     if (!has_gw || sub >= n_sub) return;
-    const int rows = (int)min(32LL, P.B - sub * 32);
-    __syncwarp();
-    if (lane == 0) mbar_arrive_expect_tx(&gbars[k % NSG], (uint32_t)rows * WC * 4u);
-    __syncwarp();
-    if (lane < rows) bulk_g2s(gstage + (k % NSG) * (GB / 4) + lane * WC, P.grad_worlds + (sub * 32 + lane) * W + c * WC, WC * 4u, &gbars[k % NSG]);
+    __syncwarp();   // every lane has read the stage this box lands in
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&gbars[k % NSG], 32u * WC * 4u);   // the box is always delivered whole
+      tma_load_2d(gstage + (k % NSG) * (GB / 4), tm_g, c * WC, (int)(sub * 32), &gbars[k % NSG]);
+    }
   };
 #pragma unroll
   for (int s = 0; s < NST; ++s) request(gw + s * GW, s);
@@ -875,8 +894,8 @@ __device__ __forceinline__ void bwd_body(const JitParams& P) {
   if (lane == 0) bulk_wait_all<0>();
   __syncwarp();
 }
-extern "C" __global__ void __launch_bounds__(256) jit_bwd_0(const JitParams P) { bwd_body<false>(P); }
-extern "C" __global__ void __launch_bounds__(256) jit_bwd_1(const JitParams P) { bwd_body<true>(P); }
+extern "C" __global__ void __launch_bounds__(256) jit_bwd_0(const JitParams P, const __grid_constant__ TensorMap tm) { bwd_body<false>(P, &tm); }
+extern "C" __global__ void __launch_bounds__(256) jit_bwd_1(const JitParams P, const __grid_constant__ TensorMap tm) { bwd_body<true>(P, &tm); }
 )";
   return o.str();
 }
@@ -893,6 +912,7 @@ struct JitProgram {
   int F = 0, W = 0, Q = 0, mask_words = 0;
   int fwd_warp_bytes = 0, bwd_warp_bytes = 0;
   bool wide = false;   // column-chunked world level: no EVIDENCE variant, the [B,W] tensors must be 16-byte aligned
+  int WC = 0;          // wide: columns per chunk = box width of the 2-D tensor-map copies
 };
 
 struct JitParamsHost {
@@ -1015,9 +1035,10 @@ JitProgram* jit_create(const vael_circuit_desc_t* d) {
   if (!J->wide) all = all && get(&J->fwd[0][1], "jit_fwd_01") && get(&J->fwd[1][1], "jit_fwd_11");
   if (!all) { J->log += " kernel lookup failed"; return J; }
   J->F = d->n_facts; J->W = d->n_worlds; J->Q = d->n_queries; J->mask_words = (d->n_worlds + 31) / 32;
+  J->WC = WC;
   auto pad = [](int b) { return (b + 127) / 128 * 128; };
   const int FB = pad(32 * J->F * 4), OB = pad(32 * std::max(std::max(WC, J->Q), 1) * 4), GB = pad(32 * WC * 4);
-  J->fwd_warp_bytes = 128 + 2 * FB + 2 * OB;
+  J->fwd_warp_bytes = 128 + 2 * FB + (J->wide ? wide_store_stages() : 2) * OB;
   J->bwd_warp_bytes = J->wide ? 128 + 2 * FB + 2 * GB + 2 * FB : 128 + 2 * (FB + GB) + 2 * FB;
   J->ok = true;
   return J;
@@ -1057,8 +1078,10 @@ void jit_destroy(JitProgram* J) {
 bool jit_ok(const JitProgram* J) { return J && J->ok; }
 const char* jit_log(const JitProgram* J) { return J ? J->log.c_str() : ""; }
 
+// `wide_tensor`: the [B,W] tensor a column-chunked (wide) kernel moves by 2-D tensor-map copies — worlds forward,
+// grad_worlds backward — or null when the call does not touch it
 static cudaError_t jit_launch(const JitProgram* J, CUfunction fn, int warp_bytes, int warps_per_sm, const GenCall& C, int num_sms,
-                              cudaStream_t st) {
+                              cudaStream_t st, const float* wide_tensor = nullptr) {
   const JitApi& A = jit_api();
   // one persistent CTA per SM holding `warps_per_sm` warps (the ad2 kernels' measured optimum: few, deep pipelines)
   int nw = std::max(1, std::min(8, warps_per_sm));
@@ -1073,7 +1096,9 @@ static cudaError_t jit_launch(const JitProgram* J, CUfunction fn, int warp_bytes
   P.facts = C.facts; P.qidx = C.qidx; P.qscalar = C.qscalar; P.B = C.B; P.qmask = C.qmask;
   P.worlds = C.worlds; P.query = C.query; P.queries_all = C.queries_all;
   P.grad_worlds = C.grad_worlds; P.grad_query = C.grad_query; P.grad_facts = C.grad_facts;
-  void* args[] = {&P};
+  struct alignas(64) TensorMapHost { unsigned long long opaque[16]; } map{};
+  if (J->wide && wide_tensor != nullptr && !make_row_box_map(&map, wide_tensor, C.B, J->W, J->WC)) return cudaErrorNotSupported;
+  void* args[] = {&P, &map};   // the narrow kernels take P only: the second entry is never read for them
   if (A.cuLaunchKernel(fn, (unsigned)grid, 1, 1, (unsigned)(nw * 32), 1, 1, (unsigned)smem, reinterpret_cast<CUstream>(st), args,
                        nullptr) != 0)
     return cudaErrorLaunchFailure;
@@ -1098,13 +1123,13 @@ cudaError_t jit_forward(const JitProgram* J, const GenCall& C, int num_sms, cuda
   // warps per SM (one persistent CTA), measured on B200 (scripts/gpu_r2j.sh): the write-dominated forward wants few
   // store streams in flight for 12.8 KB world tiles (5) and more for smaller tiles / column chunks (7)
   static const int forced = jit_env("VAEL_JIT_FWD_WARPS", 0);
-  const int wps = forced ? forced : ((!J->wide && J->W >= 96) ? 5 : 7);
+  const int wps = forced ? forced : (J->wide ? 2 : (J->W >= 96 ? 5 : 7));
   if (C.queries_all != nullptr) return jit_launch(J, J->qall[norm ? 1 : 0], J->fwd_warp_bytes, wps, C, num_sms, st);
-  return jit_launch(J, J->fwd[norm ? 1 : 0][evid ? 1 : 0], J->fwd_warp_bytes, wps, C, num_sms, st);
+  return jit_launch(J, J->fwd[norm ? 1 : 0][evid ? 1 : 0], J->fwd_warp_bytes, wps, C, num_sms, st, C.worlds);
 }
 cudaError_t jit_backward(const JitProgram* J, const GenCall& C, int num_sms, cudaStream_t st) {
   static const int wps = jit_env("VAEL_JIT_BWD_WARPS", 7);   // read-dominated: more loads in flight
-  return jit_launch(J, J->bwd[(C.flags & VAEL_FLAG_NORMALIZE) ? 1 : 0], J->bwd_warp_bytes, wps, C, num_sms, st);
+  return jit_launch(J, J->bwd[(C.flags & VAEL_FLAG_NORMALIZE) ? 1 : 0], J->bwd_warp_bytes, wps, C, num_sms, st, C.grad_worlds);
 }
 
 }  // namespace vael

@@ -133,6 +133,9 @@ struct GumbelParams {
 };
 cudaError_t gumbel_forward(const GumbelParams& P, int num_sms, cudaStream_t st);
 cudaError_t gumbel_backward(const GumbelParams& P, int num_sms, cudaStream_t st);
+// circuit_adw.cu: 2-D tensor map of a row-major [B,W] fp32 tensor with a [32 rows, C columns] box, written to the
+// 128 bytes (64-byte aligned) at `map128`; false when the driver entry point is missing or `base` is not 16-byte aligned
+bool make_row_box_map(void* map128, const float* base, long long B, int W, int C);
 // gumbel_rows.cu: lane <-> row kernels for W % 4 == 0, W <= 128, H <= 32 (the dispatchers above pick them)
 bool gumbel_rows_ok(const GumbelParams& P, bool backward);
 cudaError_t gumbel_rows_forward(const GumbelParams& P, int num_sms, cudaStream_t st);
