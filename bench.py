@@ -741,9 +741,18 @@ def secondary_probe(args, dev, rank, world, barrier, max_over_ranks, lib):
         qa_ms, _ = _time_pair(lambda: _lib.check(lib.vael_circuit_queries_all(dcm.handle, _p(pm), Bm, _p(qam), 0, sp)),
                               lambda: None, 10, barrier, max_over_ranks)
         out["mario_circuits"]["all_queries"] = {
-            "workload": "the four move queries + constraint of every row (member-list kernel; worlds not materialised)",
+            "workload": "the four move queries + constraint of every row (worlds not materialised): the circuit's generated "
+                        "kernel where NVRTC is available, else the hand-written member-list kernel",
             "kernel_family": _lib.last_kernel(), "ms": qa_ms, "bytes_per_row": 72 + 20, "GBs": Bm * 92 / qa_ms / 1e6,
             "frac": Bm * 92 / qa_ms / 1e6 / peak}
+        os.environ["VAEL_QUERIES_MEMBERLIST"] = "1"   # read per call: the hand-written kernel on the same rows
+        try:
+            ql_ms, _ = _time_pair(lambda: _lib.check(lib.vael_circuit_queries_all(dcm.handle, _p(pm), Bm, _p(qam), 0, sp)),
+                                  lambda: None, 10, barrier, max_over_ranks)
+            out["mario_circuits"]["all_queries"]["member_list_kernel"] = {
+                "kernel_family": _lib.last_kernel(), "ms": ql_ms, "GBs": Bm * 92 / ql_ms / 1e6, "frac": Bm * 92 / ql_ms / 1e6 / peak}
+        finally:
+            del os.environ["VAEL_QUERIES_MEMBERLIST"]
         del wm, gwm, la, gla, pm, qam
         torch.cuda.empty_cache()
     except Exception as exc:  # noqa: BLE001 - a secondary probe must not take the headline down

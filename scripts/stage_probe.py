@@ -105,6 +105,13 @@ if "generic" in which or "queries" in which:
         pm = torch.softmax(torch.randn(B, 2, 9, device=dev, generator=g), -1).clamp(1e-5, 0.9999).reshape(B, 18).contiguous()
         qa = torch.empty(B, 5, device=dev)
         timeit("mario_queries_all", lambda: ck(lib.vael_circuit_queries_all(dcm.handle, _p(pm), B, _p(qa), 0, sp)), B * (72 + 20))
+        if dcm.jit_status()[0]:   # the same call on the circuit's generated kernel (VAEL_FLAG_FORCE_JIT = 16)
+            timeit("mario_queries_all_generated", lambda: ck(lib.vael_circuit_queries_all(dcm.handle, _p(pm), B, _p(qa), 16, sp)), B * (72 + 20))
+        dc2q = DeviceCircuit(compile_addition_family(2, 10).circuit, dev)
+        qa2 = torch.empty(B, 19, device=dev)
+        timeit("ad2_queries_diag", lambda: ck(lib.vael_circuit_queries_all(dc2q.handle, _p(facts), B, _p(qa2), 0, sp)), B * 156)
+        if dc2q.jit_status()[0]:
+            timeit("ad2_queries_generated", lambda: ck(lib.vael_circuit_queries_all(dc2q.handle, _p(facts), B, _p(qa2), 16, sp)), B * 156)
         dc3 = DeviceCircuit(compile_addition_family(3, 10).circuit, dev)
         B3 = 1 << 20
         p3 = torch.softmax(3.0 * torch.randn(B3, 3, 10, device=dev, generator=g), -1).reshape(B3, 30).contiguous()

@@ -120,10 +120,11 @@ def test_queries_all(dc, addition_family, B, normalize):
 
 
 @pytest.mark.parametrize("B", [1, 97, 4001])
-def test_queries_all_overlapping_members_mario(cuda_device, B):
+def test_queries_all_overlapping_members_mario(cuda_device, B, monkeypatch):
     """Mario's five queries (four moves + `constraint`, which is the union of the moves: worlds belong to TWO
-    queries, and the member lists have ragged lengths) through the all-queries kernel (ad2<9,9>) and the generic
-    kernel: both bit-exact against the CSR-order fp32 oracle, with and without the normaliser."""
+    queries, and the member lists have ragged lengths) through the hand-written member-list kernel (ad2<9,9>), the
+    circuit's generated kernel (what the dispatcher prefers for member-list circuits) and the generic kernel: all
+    bit-exact against the CSR-order fp32 oracle, with and without the normaliser."""
     from vael_b200 import _lib
     from vael_b200.mario_task import compile_mario_family
     from vael_b200.ops import DeviceCircuit, circuit_queries_all
@@ -134,9 +135,14 @@ def test_queries_all_overlapping_members_mario(cuda_device, B):
     f = torch.from_numpy(p).cuda()
     for normalize in (False, True):
         ref = fp_interp.queries_all(circ, p, normalize=normalize)
+        monkeypatch.setenv("VAEL_QUERIES_MEMBERLIST", "1")
         out = circuit_queries_all(dcm, f, normalize=normalize)
         assert _lib.last_kernel() == "ad2-queries"
         np.testing.assert_array_equal(out.cpu().numpy(), ref)
+        monkeypatch.delenv("VAEL_QUERIES_MEMBERLIST")
+        out_j = circuit_queries_all(dcm, f, normalize=normalize)
+        assert _lib.last_kernel() == ("jit-straightline" if dcm.jit_status()[0] else "ad2-queries")
+        np.testing.assert_array_equal(out_j.cpu().numpy(), ref)
         out_g = circuit_queries_all(dcm, f, normalize=normalize, force_generic=True)
         assert _lib.last_kernel() == "generic-csr"
         np.testing.assert_array_equal(out_g.cpu().numpy(), ref)

@@ -62,7 +62,7 @@ def circuits(cuda_device):
 
 @pytest.mark.parametrize("name", ["2digit", "3digit", "mario", "admissible"])
 @pytest.mark.parametrize("path", ["default", "interpreter", "generated"])
-def test_circuit_entry_points_stay_inside_their_outputs(circuits, name, path):
+def test_circuit_entry_points_stay_inside_their_outputs(circuits, name, path, monkeypatch):
     from vael_b200 import circuit as cflags
     _lib, lib, _p, sp = _api()
     dc, groups = circuits[name]
@@ -90,10 +90,12 @@ def test_circuit_entry_points_stay_inside_their_outputs(circuits, name, path):
                 worlds.check(tag + " worlds"); gf.check(tag + " grad_facts")
                 query.check(tag + " query", written=bool(Q))
             if Q and name != "admissible":
-                qa = Guarded((B, Q), shift=shift)
-                _lib.check(lib.vael_circuit_queries_all(dc.handle, _p(facts), B, _p(qa.t), flags, sp))
-                torch.cuda.synchronize()
-                qa.check(f"{name}/{path} B={B} shift={shift} queries_all")
+                for keep in ("0", "1"):   # Mario, default path: the generated kernel / the hand-written member-list kernel
+                    monkeypatch.setenv("VAEL_QUERIES_MEMBERLIST", keep)
+                    qa = Guarded((B, Q), shift=shift)
+                    _lib.check(lib.vael_circuit_queries_all(dc.handle, _p(facts), B, _p(qa.t), flags, sp))
+                    torch.cuda.synchronize()
+                    qa.check(f"{name}/{path} B={B} shift={shift} queries_all memberlist={keep}")
 
 
 @pytest.mark.parametrize("n_groups,group,clip", [(2, 10, False), (3, 10, False), (2, 9, True), (1, 9, True), (4, 7, False)])

@@ -576,6 +576,21 @@ extern "C" int vael_circuit_queries_all(const vael_circuit_t* c, const float* fa
   if (flags & VAEL_FLAG_EVIDENCE) return fail(VAEL_E_INVALID, "EVIDENCE is meaningless for queries_all");
   if (B == 0) return VAEL_OK;
   if (!queries_all) return fail(VAEL_E_INVALID, "null output");
+  // Two-AD circuits whose queries are not the diagonals (Mario's overlapping, ragged member lists): the circuit's
+  // generated kernel folds the same products in the same order as straight-line code — 0.70 of HBM against the table-
+  // driven member-list kernel's 0.48 (scripts/stage_probe.py queries) — so it is preferred where it can be built
+  // (first use compiles it; VAEL_QUERIES_MEMBERLIST=1, read per call, keeps the hand-written kernel: tests, A/B timing).
+  if (pick_kernel(c, flags, nullptr) == 2 && !c->queries_diagonal && c->q_members_ok && c->n_queries <= kQMaxQueries) {
+    const char* keep = getenv("VAEL_QUERIES_MEMBERLIST");
+    if (!(keep && keep[0] == '1') && jit_can(jit_of(c), flags, nullptr)) {
+      GenCall G = make_call(c, facts, nullptr, -1, B, flags);
+      G.queries_all = queries_all;
+      CK(jit_forward(jit_of(c), G, c->num_sms, static_cast<cudaStream_t>(stream)));
+      g_last_kernel = "jit-straightline";
+      g_launches++;
+      return VAEL_OK;
+    }
+  }
   if (pick_kernel(c, flags, nullptr) == 2 && c->n_queries <= kQMaxQueries && (c->queries_diagonal || c->q_members_ok)) {
     Ad2QParams P{};
     P.facts = facts; P.B = B; P.n_queries = c->n_queries;
