@@ -52,6 +52,11 @@ __device__ __forceinline__ float log2_exp_variate(uint32_t bits) {
 // The four variates of one Philox call.  The guard is taken per CALL, on the integers: the series is needed when one
 // of the four 23-bit numbers lies in the top 2^13 (v < 2^-10) — one call in 256 — and that rare path is a real branch
 // (the same values as four log2_exp_variate calls; 1.25 instead of 5 guard instructions per variate).
+// (k + 1/2) 2^-23 for a 23-bit k without an int->float conversion (I2F shares the quarter-rate XU pipe with the
+// MUFU logarithms this routine is made of): [1,2) float with mantissa k, minus (1 - 2^-24) — exact, the same value
+__device__ __forceinline__ float unit_from_23_bits(uint32_t k) {
+  return __uint_as_float(0x3f800000u | k) - 0.99999994f;
+}
 __device__ __forceinline__ void log2_exp_variates4(uint4 r, float* L4) {
   const uint32_t k0 = r.x >> 9, k1 = r.y >> 9, k2 = r.z >> 9, k3 = r.w >> 9;
   if (max(max(k0, k1), max(k2, k3)) > 8388608u - 8192u - 1u) {
@@ -59,11 +64,10 @@ __device__ __forceinline__ void log2_exp_variates4(uint4 r, float* L4) {
     L4[2] = log2_exp_variate(r.z); L4[3] = log2_exp_variate(r.w);
     return;
   }
-  constexpr float kScale = 1.0f / 8388608.0f;
-  L4[0] = __log2f(-__log2f((static_cast<float>(k0) + 0.5f) * kScale));
-  L4[1] = __log2f(-__log2f((static_cast<float>(k1) + 0.5f) * kScale));
-  L4[2] = __log2f(-__log2f((static_cast<float>(k2) + 0.5f) * kScale));
-  L4[3] = __log2f(-__log2f((static_cast<float>(k3) + 0.5f) * kScale));
+  L4[0] = __log2f(-__log2f(unit_from_23_bits(k0)));
+  L4[1] = __log2f(-__log2f(unit_from_23_bits(k1)));
+  L4[2] = __log2f(-__log2f(unit_from_23_bits(k2)));
+  L4[3] = __log2f(-__log2f(unit_from_23_bits(k3)));
 }
 // 2^x, x <= 0 (MUFU.EX2; 2 ulp): the softmax runs in the log2 domain, the log2(e) factor folded into 1/tau
 __device__ __forceinline__ float fast_exp2(float x) {
