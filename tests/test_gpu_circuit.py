@@ -200,16 +200,16 @@ def test_unaligned_views_take_the_plain_copy_path(dc, addition_family):
     np.testing.assert_array_equal(q.cpu().numpy()[:, 0], q_ref)
 
 
-def test_full_size_properties_and_host_path(dc, addition_family):
-    """BASELINE.json microbenchmark scale (B = 2^21 + 3 rows, 0.8 GB of worlds; the oracle could not finish
-    this): size-independent properties of the reference's closed form (models/vael.py:208-225) — rows sum
+@pytest.mark.parametrize("B", [(1 << 21) + 3, 10_000_003])
+def test_full_size_properties_and_host_path(dc, addition_family, B):
+    """BASELINE.json microbenchmark scale (B = 2^21 + 3 and the full 1e7 rows of configs[3], 4 GB of worlds; the oracle
+    could not finish these): size-independent properties of the reference's closed form (models/vael.py:208-225) — rows sum
     to 1, world (j,k) = p1[j] * p2[k] bit for bit, query = sum of the member worlds, evidence rows
     renormalise to 1 and vanish off the evidence, the adjoint is linear and matches its closed form — and
     the C-ABI host-buffer path (copies inside) returns exactly what the device path does."""
     import ctypes as C
     from vael_b200 import _lib
     from vael_b200.ops import _p, circuit_forward
-    B = (1 << 21) + 3
     g = torch.Generator(device="cuda").manual_seed(0)
     p = torch.softmax(3 * torch.randn(B, 2, 10, device="cuda", generator=g), -1) + 1e-5
     facts = (p / p.sum(-1, keepdim=True)).reshape(B, 20).contiguous().requires_grad_(True)
