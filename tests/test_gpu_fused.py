@@ -174,14 +174,16 @@ def test_fused_logic_philox_mode(cuda_device, dc2):
     sd = torch.tensor([77], dtype=torch.int64, device="cuda")
     _, _, _, i4, _ = logic_train(dc2, logits, 9, seed_dev=sd)         # the device word overrides the host seed
     assert torch.equal(i1, i4)
-    # the single-pass production kernel (FAST) and the two-pass one (GENERAL, taken when y_soft is asked for) draw the
-    # same noise and form the same perturbed logits: identical worlds, for every tau the fast kernel accepts
+    # the production kernel (FAST: two uniforms pick the world, no per-world variates in the forward) and the two-pass
+    # one (GENERAL, taken when y_soft is asked for) make the same draws: identical worlds for every tau the fast kernel
+    # accepts, and the sampled world is the arg-max of the y_soft the GENERAL kernel builds around it
     for tau in (1.0, 0.5, 3.0):
         fa, qa, wha, ia, _ = logic_train(dc2, logits[:50000], 9, seed=5, tau=tau)
         fb, qb, whb, ib, ys = logic_train(dc2, logits[:50000], 9, seed=5, tau=tau, want_y_soft=True)
         assert torch.equal(ia, ib) and torch.equal(fa, fb) and torch.equal(qa, qb)
         assert torch.allclose(wha, whb, atol=2.4e-7, rtol=0)
         assert torch.allclose(ys.sum(1), torch.ones(50000, device="cuda"), atol=1e-5)
+        assert torch.equal(ys.argmax(1).int(), ib)
     facts = facts_from_logits(logits[:1], 2, 1e-5)
     p = circuit_forward(dc2, facts, None)[0][0].double().cpu()
     counts = torch.bincount(i1.long(), minlength=100).double().cpu()
@@ -208,6 +210,36 @@ def test_fused_logic_philox_mode(cuda_device, dc2):
                                               _stream_ptr()))
     (g_ref,) = torch.autograd.grad((worlds * gs).sum() + (q2 * gq).sum(), [lg2])
     assert rel_err(g_fused.cpu().numpy(), g_ref.cpu().numpy(), floor=1e-2 * g_ref.abs().max().item()) < 2e-4
+
+
+@pytest.mark.parametrize("tau", [1.0, 0.6, 2.0])
+def test_fused_philox_noise_has_the_law_of_gumbel_softmax(cuda_device, dc2, tau):
+    """The Philox mode draws the race times top-down (winner by inverse CDF, the others as winner + Exp / p): the
+    JOINT law of (sampled world, y_soft) must be that of F.gumbel_softmax.  Same row 300 000 times through the kernel's
+    own noise and through injected torch Gumbel noise (the reference's computation): world frequencies, E[y_soft],
+    E[y_soft^2], E[y_soft of the sampled world] and E[y_soft | world = w] for the likeliest worlds agree within
+    sampling error."""
+    from vael_b200.ops import logic_train
+    gen = torch.Generator().manual_seed(23)
+    row = 1.2 * torch.randn(1, 20, generator=gen)
+    B = 300000
+    logits = row.expand(B, 20).contiguous().cuda()
+    _, _, _, ia, ya = logic_train(dc2, logits, 9, seed=1234, tau=tau, want_y_soft=True)
+    noise = (-torch.empty(B, 100, device="cuda").exponential_().log())
+    _, _, _, ib, yb = logic_train(dc2, logits, 9, noise=noise, tau=tau, want_y_soft=True)
+    ya, yb = ya.double(), yb.double()
+    se = 5.0 / B ** 0.5                                   # five standard errors of a [0,1]-valued mean (sd <= 1/2 ... 1)
+    fa = torch.bincount(ia.long(), minlength=100).double() / B
+    fb = torch.bincount(ib.long(), minlength=100).double() / B
+    assert float((fa - fb).abs().max()) < 2 * se
+    assert float((ya.mean(0) - yb.mean(0)).abs().max()) < 2 * se
+    assert float(((ya ** 2).mean(0) - (yb ** 2).mean(0)).abs().max()) < 2 * se
+    sa = ya.gather(1, ia.long()[:, None]).mean().item(); sb = yb.gather(1, ib.long()[:, None]).mean().item()
+    assert abs(sa - sb) < 2 * se, (sa, sb)
+    for w in torch.topk(fb, 3).indices.tolist():           # conditional on the sampled world (n ~ B f_w rows each)
+        ca, cb = ya[ia == w].mean(0), yb[ib == w].mean(0)
+        n = min(int((ia == w).sum()), int((ib == w).sum()))
+        assert float((ca - cb).abs().max()) < 2 * 5.0 / n ** 0.5, (w, n)
 
 
 def test_model_forward_fused_equals_stagewise(cuda_device):

@@ -35,16 +35,52 @@
 // instead of 157 / 255: 2-3x the resident warps), and the adjoint needs the per-column sums of p and p G only
 // (a[c] = A[c] - (sum p G / sum p) P[c]).
 #include <cstdlib>
+#include <type_traits>
 
 #include "params.cuh"
 #include "sampling.cuh"
 
 namespace vael {
 
-__device__ __forceinline__ void noise_block(long long row, int blk, uint64_t seed, float* L4) {
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)blk, 0x5eedu),
-                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  log2_exp_variates4(r, L4);
+// ---- in-kernel noise (Philox mode): exponential races, drawn top-down ------------------------------------------------
+// F.gumbel_softmax perturbs logit_w = log p_w with g_w = -log E_w, E_w ~ Exp(1): the perturbed logit is -log t_w with
+// t_w = E_w / p_w, the sampled world is the arg-MIN of the race times t_w and y_soft_w is proportional to t_w^(-1/tau).
+// The times can be drawn in another order with the same joint law (the Gumbel-max trick read backwards, Maddison et al.
+// 2014): the winner w* ~ Categorical(p) — for the product distribution p_w = p1[i] p2[k] that is one inverse-CDF
+// draw per annotated disjunction —, its time t* ~ Exp(1) / sum_w p_w, and by memorylessness every other
+// t_w = t* + E'_w / p_w with fresh E'_w ~ Exp(1).  The FORWARD then needs two uniforms per row instead of W
+// variates (the straight-through forward value (1 - y) + y of the selected component is 1 up to one ulp and is
+// written as 1); only the adjoint, which needs every y_soft_w, walks the W worlds.  Counters: block e / 4 of a row
+// holds the variates of worlds 4 (e / 4) .. + 3, block ceil(W / 4) the row's three draws; key = seed.
+__device__ __forceinline__ uint4 philox_block(long long row, int blk, uint64_t seed) {
+  return philox4x32_10(make_uint4((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)blk, 0x5eedu),
+                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+
+struct RowDraw {
+  int arg;       // the sampled world i* N + k*
+  float t_min;   // its race time, in units of ln 2 (t / ln 2): every other world's is t_min + E2'_w / p_w
+};
+template <int N>
+__device__ __forceinline__ RowDraw draw_world(const float* f, long long row, uint64_t seed) {
+  const uint4 r = philox_block(row, (N * N + 3) / 4, seed);
+  float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) { s1 += f[i]; s2 += f[N + i]; }
+  // inverse CDF per annotated disjunction: the number of proper prefix sums the target has reached
+  const float ta = unit_from_23_bits(r.x >> 9) * s1, tb = unit_from_23_bits(r.y >> 9) * s2;
+  int ia = 0, ka = 0;
+  float c1 = 0.0f, c2 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < N - 1; ++i) {
+    c1 += f[i]; c2 += f[N + i];
+    ia += (ta >= c1) ? 1 : 0;
+    ka += (tb >= c2) ? 1 : 0;
+  }
+  RowDraw d;
+  d.arg = ia * N + ka;
+  d.t_min = exp2_variate(r.z) / (s1 * s2);
+  return d;
 }
 
 template <int F>
@@ -75,27 +111,27 @@ __device__ __forceinline__ void store_row(float* __restrict__ base, long long ro
 }
 
 // GENERAL: perturbed logits z[e] of one row in the log2 domain (up to a row constant), their maximum and arg-max; the
-// query sum under mask `m` when `qsum` is non-null.  Noise: injected (`noise` [B,W], z = s (log p + g)) or Philox
-// (one call per four consecutive worlds, counter = (row, e / 4), key = seed; z = s log p - L / tau).
+// query sum under mask `m` when `qsum` is non-null.  Noise: injected (`noise` [B,W], z = s (log p + g): the reference's
+// computation on the caller's Gumbel variates) or Philox (race times drawn top-down, z = -log2(t) / tau).
 template <int N>
 __device__ __forceinline__ void perturbed_logits(const FusedParams& P, long long row, uint64_t seed, const float* f,
                                                  const uint32_t* m, float inv_tau, float* z, float& mx, int& arg,
                                                  float* qsum) {
   constexpr int W = N * N;
-  const float s = inv_tau * kLog2e;
-  float lps[2 * N];
-#pragma unroll
-  for (int c = 0; c < 2 * N; ++c) lps[c] = s * __logf(f[c]);   // absolute error of the log <= 3e-6: noise-level
-  const bool nz_al = P.noise != nullptr && (W % 4 == 0) && aligned16(P.noise);
-  mx = -INFINITY;
-  arg = 0;
   float acc = 0.0f;
-  float g4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (P.noise != nullptr) {
+    const float s = inv_tau * kLog2e;
+    float lps[2 * N];
 #pragma unroll
-  for (int e = 0; e < W; ++e) {
-    const int i = e / N, k = e % N;
-    if ((e & 3) == 0) {
-      if (P.noise != nullptr) {
+    for (int c = 0; c < 2 * N; ++c) lps[c] = s * __logf(f[c]);   // absolute error of the log <= 3e-6: noise-level
+    const bool nz_al = (W % 4 == 0) && aligned16(P.noise);
+    mx = -INFINITY;
+    arg = 0;
+    float g4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int e = 0; e < W; ++e) {
+      const int i = e / N, k = e % N;
+      if ((e & 3) == 0) {
         if (nz_al) {
           const float4 t = __ldg(reinterpret_cast<const float4*>(P.noise + row * W + e));
           g4[0] = t.x; g4[1] = t.y; g4[2] = t.z; g4[3] = t.w;
@@ -103,30 +139,29 @@ __device__ __forceinline__ void perturbed_logits(const FusedParams& P, long long
 #pragma unroll
           for (int u = 0; u < 4; ++u) g4[u] = (e + u < W) ? __ldg(P.noise + row * W + e + u) : 0.0f;
         }
-      } else {
-        noise_block(row, e >> 2, seed, g4);
       }
+      if (qsum != nullptr && ((m[e >> 5] >> (e & 31)) & 1u)) acc = __fadd_rn(acc, __fmul_rn(f[i], f[N + k]));
+      z[e] = fmaf(g4[e & 3], s, lps[i] + lps[N + k]);
+      if (z[e] > mx) { mx = z[e]; arg = e; }
     }
-    if (qsum != nullptr && ((m[e >> 5] >> (e & 31)) & 1u)) acc = __fadd_rn(acc, __fmul_rn(f[i], f[N + k]));
-    z[e] = (P.noise != nullptr) ? fmaf(g4[e & 3], s, lps[i] + lps[N + k]) : fmaf(g4[e & 3], -inv_tau, lps[i] + lps[N + k]);
-    if (z[e] > mx) { mx = z[e]; arg = e; }
+  } else {
+    const RowDraw d = draw_world<N>(f, row, seed);
+    float r1[N], r2[N], E4[4];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { r1[i] = 1.0f / f[i]; r2[i] = 1.0f / f[N + i]; }
+#pragma unroll
+    for (int e = 0; e < W; ++e) {
+      const int i = e / N, k = e % N;
+      if ((e & 3) == 0) exp2_variates4(philox_block(row, e >> 2, seed), E4);
+      if (qsum != nullptr && ((m[e >> 5] >> (e & 31)) & 1u)) acc = __fadd_rn(acc, __fmul_rn(f[i], f[N + k]));
+      float t = fmaf(E4[e & 3], r1[i] * r2[k], d.t_min);
+      t = (e == d.arg) ? d.t_min : t;
+      z[e] = -inv_tau * __log2f(t);
+    }
+    arg = d.arg;
+    mx = -inv_tau * __log2f(d.t_min);   // = z[arg]: every other race time is t_min plus something non-negative
   }
   if (qsum != nullptr) *qsum = acc;
-}
-
-// FAST: s log p per column, with the row's upper bound M of every perturbed logit (Philox noise only) already
-// subtracted from the first AD's columns: lps[i] + lps[N + k] - L / tau is then z - M <= 0, ready for exp2
-template <int N>
-__device__ __forceinline__ void scaled_logs_minus_bound(const float* f, float inv_tau, float* lps) {
-  const float s = inv_tau * kLog2e;
-#pragma unroll
-  for (int c = 0; c < 2 * N; ++c) lps[c] = s * __logf(f[c]);
-  float m1 = lps[0], m2 = lps[N];
-#pragma unroll
-  for (int i = 1; i < N; ++i) { m1 = fmaxf(m1, lps[i]); m2 = fmaxf(m2, lps[N + i]); }
-  const float M = m1 + m2 - kLogE2Min * inv_tau;
-#pragma unroll
-  for (int i = 0; i < N; ++i) lps[i] -= M;
 }
 
 template <int MW>
@@ -161,21 +196,16 @@ __global__ void __launch_bounds__(128, FMINB) fused_forward_kernel(const FusedPa
     float ys;   // y_soft of the selected world
     int arg;
     if constexpr (FAST) {
-      float lps[F];
-      scaled_logs_minus_bound<N>(f, inv_tau, lps);
-      float mx = -INFINITY, sum = 0.0f, q = 0.0f, L4[4];
-      arg = 0;
+      // two uniforms pick the world; no variate is drawn per world (the adjoint draws them)
+      arg = draw_world<N>(f, row, seed).arg;
+      if (P.query != nullptr) {
+        float q = 0.0f;
 #pragma unroll
-      for (int e = 0; e < W; ++e) {
-        const int i = e / N, k = e % N;
-        if ((e & 3) == 0) noise_block(row, e >> 2, seed, L4);
-        if (P.query != nullptr && ((m[e >> 5] >> (e & 31)) & 1u)) q = __fadd_rn(q, __fmul_rn(f[i], f[N + k]));
-        const float z = fmaf(L4[e & 3], -inv_tau, lps[i] + lps[N + k]);   // perturbed logit minus M
-        if (z > mx) { mx = z; arg = e; }
-        sum += fast_exp2(z);
+        for (int e = 0; e < W; ++e)
+          if ((m[e >> 5] >> (e & 31)) & 1u) q = __fadd_rn(q, __fmul_rn(f[e / N], f[N + e % N]));
+        P.query[row] = q;
       }
-      if (P.query != nullptr) P.query[row] = q;
-      ys = fast_exp2(mx) / sum;
+      ys = 1.0f;   // stands for any y_soft: (1 - y) + y is written as 1 (the reference's value is 1 or 1 - 2^-24)
     } else {
       float z[W], mx, q;
       perturbed_logits<N>(P, row, seed, f, m, inv_tau, z, mx, arg, &q);
@@ -227,24 +257,35 @@ __global__ void __launch_bounds__(128, MINB) fused_backward_kernel(const FusedPa
 #pragma unroll
     for (int c = 0; c < F; ++c) df[c] = 0.0f;
     if (P.grad_world_h != nullptr && FAST) {
-      // With p_e = exp2(z_e - M): P[c] = sum of p over the worlds of column c, and A[c] = sum of p_e G_e with
-      // G_e = gh[i] + gh[N + k] splits into gh[c] P[c] plus the cross term R[i] = sum_k p_ik gh[N + k] (resp.
-      // C[k] = sum_i p_ik gh[i]): two additions and two FMAs per world instead of the add, the product and four sums
-      float gh[F], lps[F], Pc[F], Xc[F];
+      // Softmax weights q_e = t_e^(-1/tau) of the race times (no maximum to subtract: t_e >= t_min > 0 and, for
+      // tau >= 0.5, t^(-1/tau) stays inside fp32).  P[c] = sum of q over the worlds of column c, and A[c] = sum of
+      // q_e G_e with G_e = gh[i] + gh[N + k] splits into gh[c] P[c] plus the cross term X[i] = sum_k q_ik gh[N + k]
+      // (resp. X[N + k] = sum_i q_ik gh[i]): two additions and two FMAs per world.
+      float gh[F], r1[N], r2[N], Pc[F], Xc[F];
       load_row<F>(P.grad_world_h, row, gh, aligned16(P.grad_world_h));
-      scaled_logs_minus_bound<N>(f, inv_tau, lps);
+      const RowDraw d = draw_world<N>(f, row, seed);
+#pragma unroll
+      for (int i = 0; i < N; ++i) { r1[i] = 1.0f / f[i]; r2[i] = 1.0f / f[N + i]; }
 #pragma unroll
       for (int c = 0; c < F; ++c) Pc[c] = Xc[c] = 0.0f;
-      float L4[4];
+      float E4[4];
+      auto walk = [&](auto tau_is_one) {
 #pragma unroll
-      for (int e = 0; e < W; ++e) {
-        const int i = e / N, k = e % N;
-        if ((e & 3) == 0) noise_block(row, e >> 2, seed, L4);
-        const float pe = fast_exp2(fmaf(L4[e & 3], -inv_tau, lps[i] + lps[N + k]));
-        Pc[i] += pe; Pc[N + k] += pe;
-        Xc[i] = fmaf(pe, gh[N + k], Xc[i]);
-        Xc[N + k] = fmaf(pe, gh[i], Xc[N + k]);
-      }
+        for (int e = 0; e < W; ++e) {
+          const int i = e / N, k = e % N;
+          if ((e & 3) == 0) exp2_variates4(philox_block(row, e >> 2, seed), E4);
+          float t = fmaf(E4[e & 3], r1[i] * r2[k], d.t_min);
+          t = (e == d.arg) ? d.t_min : t;
+          float qe;
+          if constexpr (decltype(tau_is_one)::value) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(qe) : "f"(t));
+          else qe = fast_exp2(-inv_tau * __log2f(t));
+          Pc[i] += qe; Pc[N + k] += qe;
+          Xc[i] = fmaf(qe, gh[N + k], Xc[i]);
+          Xc[N + k] = fmaf(qe, gh[i], Xc[N + k]);
+        }
+      };
+      if (inv_tau == 1.0f) walk(std::true_type{});
+      else walk(std::false_type{});
       float S = 0.0f, D = 0.0f;
 #pragma unroll
       for (int i = 0; i < N; ++i) { S += Pc[i]; D += fmaf(gh[i], Pc[i], Xc[i]); }

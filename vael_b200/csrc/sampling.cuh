@@ -69,6 +69,23 @@ __device__ __forceinline__ void log2_exp_variates4(uint4 r, float* L4) {
   L4[2] = __log2f(-__log2f(unit_from_23_bits(k2)));
   L4[3] = __log2f(-__log2f(unit_from_23_bits(k3)));
 }
+// The exponential variates themselves, base 2: E2 = -log2(U) = E / ln 2, E ~ Exp(1), four per Philox call, with the
+// same per-call guard (series of -log(1 - v) where the fast logarithm's absolute error would be a large relative one).
+__device__ __forceinline__ float exp2_variate(uint32_t bits) {
+  const float u = unit_from_23_bits(bits >> 9);
+  const float v = 1.0f - u;
+  const float series = v * fmaf(v, fmaf(v, 0.48089835f, 0.72134752f), 1.44269504f);   // (v + v^2/2 + v^3/3) / ln 2
+  return (v < 1.0f / 1024.0f) ? series : -__log2f(u);
+}
+__device__ __forceinline__ void exp2_variates4(uint4 r, float* E4) {
+  const uint32_t k0 = r.x >> 9, k1 = r.y >> 9, k2 = r.z >> 9, k3 = r.w >> 9;
+  if (max(max(k0, k1), max(k2, k3)) > 8388608u - 8192u - 1u) {
+    E4[0] = exp2_variate(r.x); E4[1] = exp2_variate(r.y); E4[2] = exp2_variate(r.z); E4[3] = exp2_variate(r.w);
+    return;
+  }
+  E4[0] = -__log2f(unit_from_23_bits(k0)); E4[1] = -__log2f(unit_from_23_bits(k1));
+  E4[2] = -__log2f(unit_from_23_bits(k2)); E4[3] = -__log2f(unit_from_23_bits(k3));
+}
 // 2^x, x <= 0 (MUFU.EX2; 2 ulp): the softmax runs in the log2 domain, the log2(e) factor folded into 1/tau
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
