@@ -871,8 +871,8 @@ def logic_path_probe(dev, rank, barrier, max_over_ranks, lib, peak, Bl=1 << 20):
                               "rows_per_sec": Bl / (f_ms * 1e-3)},
                       "bwd": {"ms": b_ms, "bytes_per_row": bb, "GBs": Bl * bb / b_ms / 1e6, "frac_hbm": Bl * bb / b_ms / 1e6 / peak,
                               "rows_per_sec": Bl / (b_ms * 1e-3)},
-                      "bound": "FP32/SFU issue (about 5.5 k instructions per row: 25 Philox4x32-10 calls, 100 Gumbel "
-                               "transforms, 100 expf, 20 logf), not HBM"},
+                      "bound": "forward: HBM (the world is drawn top-down: two uniforms per row, ~550 instructions); adjoint: "
+                               "FP32/SFU issue (25 Philox4x32-10 calls, 100 lg2 + 100 rcp per row)"},
             "three_stage_kernels": {"fwd": {"ms": sf_ms, "bytes_per_row": sfb, "GBs": Bl * sfb / sf_ms / 1e6},
                                     "bwd": {"ms": sb_ms, "bytes_per_row": sbb, "GBs": Bl * sbb / sb_ms / 1e6}},
             "speedup": {"fwd": sf_ms / f_ms, "bwd": sb_ms / b_ms}}

@@ -231,8 +231,11 @@ VAEL_API int vael_gumbel_world_backward(const float* scores, const float* y_soft
  * VAELModel.forward between the MLP and the decoder (models/vael.py:55-65) for the two-digit program family:
  * compute_facts_probability (:159-177) -> problog_inference (:200-225) -> log + F.gumbel_softmax(hard) (:61-62)
  * -> herbrand with define_herbrand_base (:82-84, :179-187).  No [B,W] tensor touches memory; the adjoint redraws
- * the Gumbel noise from the same counters (Philox4x32-10 keyed by `seed`, or by the device word `seed_dev` when
- * given — a CUDA graph can refresh it per replay) instead of saving it.  Covers circuits of fast_kind 2 whose two
+ * the noise from the same counters (Philox4x32-10 keyed by `seed`, or by the device word `seed_dev` when
+ * given — a CUDA graph can refresh it per replay) instead of saving it.  With `noise` == NULL the race times behind
+ * the Gumbel-max trick are drawn top-down (sampled world by inverse CDF, the others as winner + Exp / p): the same
+ * joint law of (world, y_soft) as F.gumbel_softmax, two uniforms per row in the forward; the straight-through forward
+ * value (1 - y) + y of the selected component (1 or 1 - 2^-24 in the reference) is then written as 1.  Covers circuits of fast_kind 2 whose two
  * annotated disjunctions have 9 or 10 values each (vael_logic_fused_supported); the Herbrand base is the
  * reference's: row i*N+k = [onehot(i), onehot(k)].
  *   logits   [B,2N]  MLP outputs                     noise  [B,W] injected Gumbel noise or NULL

@@ -11,29 +11,25 @@
 // y_soft[B,W] to HBM and reads them back: 1.5 KB per row forward, 2.3 KB backward.  Here nothing [B,W]-shaped
 // exists in memory: 252 B per row forward (logits, query index in; facts, query, world index, world_h out),
 // 248 B backward (logits, query index, grad_world_h, grad_query in; grad_logits out).  The backward RE-DRAWS the
-// Gumbel noise from the same Philox counters instead of saving it, and recomputes the softmax.
+// noise from the same Philox counters instead of saving it, and recomputes the softmax.
 //
-// lane <-> row, everything in registers (the W = N*N perturbed logits are a fully unrolled register array), no
-// shared memory, no barriers; rows are fetched with 128-bit loads (a row is 2N contiguous floats).  The kernel is
-// bound by FP32 / SFU issue, not by HBM: per row W x (a quarter Philox4x32-10 call, the Gumbel transform,
-// one exp2) plus the facts head — about 5 k instructions against 252 B.
+// lane <-> row, everything in registers, no shared memory, no barriers; rows are fetched with 128-bit loads (a row is
+// 2N contiguous floats).
 //
 // Arithmetic notes.  facts: the same facts_row as the stand-alone kernel (bit-identical).  worlds and query:
 // __fmul_rn products folded in world order under the per-row query mask (bit-identical to ad2_forward_kernel).
-// logit(w) = log p1[i] + log p2[k] (2N fast logarithms instead of W accurate ones; absolute error <= 3e-6, far
-// below the Gumbel noise it is added to; y_soft agrees with the reference's to ~1e-5 relative), softmax as
-// exp2 in the log2 domain.  Ties of the arg-max go to the lowest world index.
+// Ties of the arg-max go to the lowest world index.
 // Adjoint: with y = softmax((logit + g)/tau), G_e = gh[i] + gh[N+k], d logit_e = y_e (G_e - sum y G) / tau;
 // d/d p1[i] of sum_e d logit_e log(p1[i] p2[k]) = (sum_k d logit_ik) / p1[i] — no division per world;
 // the query adds gq [e in query] p2[k] (resp. p1[i]); then the facts-head adjoint (detached normaliser).
 //
-// Two variants per direction.  GENERAL keeps the W perturbed logits in registers (two passes: max, then exp) and takes
-// any noise source and any tau.  FAST is the production path (in-kernel Philox noise, tau >= 0.5): Philox-drawn Gumbel
-// variates are bounded, so M = max_i log p1[i] + max_k log p2[k] + (largest variate) bounds every perturbed logit of
-// the row from above BEFORE any of them is drawn, and the largest one sits at most 57 binades below M — the softmax is
-// a single pass of exp2(z - M) with no running maximum, nothing W-sized lives in registers (70 / ~130 registers
-// instead of 157 / 255: 2-3x the resident warps), and the adjoint needs the per-column sums of p and p G only
-// (a[c] = A[c] - (sum p G / sum p) P[c]).
+// Two variants per direction.  GENERAL keeps the W perturbed logits in registers (two passes: max, then exp2 in the
+// log2 domain) and takes any noise source, any tau, and produces y_soft: with INJECTED noise it is the reference's
+// computation on the caller's Gumbel variates (logit(w) = log p1[i] + log p2[k]: 2N fast logarithms instead of W,
+// absolute error <= 3e-6, y_soft within 1e-5 relative of the reference's).  FAST is the production path (in-kernel
+// Philox noise, tau >= 0.5, no y_soft): the race times behind the Gumbel-max trick are drawn TOP-DOWN (see
+// draw_world below), so the forward draws two uniforms per row and touches no world but the query's members, and the
+// adjoint needs per-column sums of the softmax weights only — nothing W-sized lives in registers.
 #include <cstdlib>
 #include <type_traits>
 
