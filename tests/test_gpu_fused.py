@@ -225,7 +225,7 @@ def test_fused_philox_noise_has_the_law_of_gumbel_softmax(cuda_device, dc2, tau)
     B = 300000
     logits = row.expand(B, 20).contiguous().cuda()
     _, _, _, ia, ya = logic_train(dc2, logits, 9, seed=1234, tau=tau, want_y_soft=True)
-    noise = (-torch.empty(B, 100, device="cuda").exponential_().log())
+    noise = -torch.empty(B, 100, device="cuda").exponential_(generator=torch.Generator(device="cuda").manual_seed(77)).log()
     _, _, _, ib, yb = logic_train(dc2, logits, 9, noise=noise, tau=tau, want_y_soft=True)
     ya, yb = ya.double(), yb.double()
     se = 5.0 / B ** 0.5                                   # five standard errors of a [0,1]-valued mean (sd <= 1/2 ... 1)
