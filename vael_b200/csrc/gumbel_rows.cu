@@ -56,12 +56,6 @@ __host__ __device__ inline GrLayout gr_layout(int W, int H, bool bwd, bool noise
   return L;
 }
 
-__device__ __forceinline__ float fast_log2(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
 template <bool NOISE>
 __global__ void __launch_bounds__(256, 2) gumbel_rows_forward_kernel(const GumbelParams P) {
   extern __shared__ __align__(128) uint8_t gr_smem[];
@@ -117,7 +111,7 @@ __global__ void __launch_bounds__(256, 2) gumbel_rows_forward_kernel(const Gumbe
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float l = k * (is_log ? sc[u] : fast_log2(sc[u]));
+        const float l = k * (is_log ? sc[u] : fast_lg2(sc[u]));
         // injected g: z = l + log2(e)/tau g; Philox: z = l - L / tau (+ a row constant nobody sees)
         z[u] = NOISE ? fmaf(nz[u], sc_log, l) : fmaf(nz[u], -inv_tau, l);
         if (z[u] > mx) { mx = z[u]; arg = 4 * g + u; }

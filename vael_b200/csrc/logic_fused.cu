@@ -144,7 +144,7 @@ __device__ __forceinline__ void perturbed_logits(const FusedParams& P, long long
     const RowDraw d = draw_world<N>(f, row, seed);
     float r1[N], r2[N], E4[4];
 #pragma unroll
-    for (int i = 0; i < N; ++i) { r1[i] = 1.0f / f[i]; r2[i] = 1.0f / f[N + i]; }
+    for (int i = 0; i < N; ++i) { r1[i] = fast_rcp(f[i]); r2[i] = fast_rcp(f[N + i]); }
 #pragma unroll
     for (int e = 0; e < W; ++e) {
       const int i = e / N, k = e % N;
@@ -152,10 +152,10 @@ __device__ __forceinline__ void perturbed_logits(const FusedParams& P, long long
       if (qsum != nullptr && ((m[e >> 5] >> (e & 31)) & 1u)) acc = __fadd_rn(acc, __fmul_rn(f[i], f[N + k]));
       float t = fmaf(E4[e & 3], r1[i] * r2[k], d.t_min);
       t = (e == d.arg) ? d.t_min : t;
-      z[e] = -inv_tau * __log2f(t);
+      z[e] = -inv_tau * fast_lg2(t);
     }
     arg = d.arg;
-    mx = -inv_tau * __log2f(d.t_min);   // = z[arg]: every other race time is t_min plus something non-negative
+    mx = -inv_tau * fast_lg2(d.t_min);   // = z[arg]: every other race time is t_min plus something non-negative
   }
   if (qsum != nullptr) *qsum = acc;
 }
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(128, MINB) fused_backward_kernel(const FusedPa
       load_row<F>(P.grad_world_h, row, gh, aligned16(P.grad_world_h));
       const RowDraw d = draw_world<N>(f, row, seed);
 #pragma unroll
-      for (int i = 0; i < N; ++i) { r1[i] = 1.0f / f[i]; r2[i] = 1.0f / f[N + i]; }
+      for (int i = 0; i < N; ++i) { r1[i] = fast_rcp(f[i]); r2[i] = fast_rcp(f[N + i]); }
 #pragma unroll
       for (int c = 0; c < F; ++c) Pc[c] = Xc[c] = 0.0f;
       float E4[4];
@@ -273,8 +273,8 @@ __global__ void __launch_bounds__(128, MINB) fused_backward_kernel(const FusedPa
           float t = fmaf(E4[e & 3], r1[i] * r2[k], d.t_min);
           t = (e == d.arg) ? d.t_min : t;
           float qe;
-          if constexpr (decltype(tau_is_one)::value) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(qe) : "f"(t));
-          else qe = fast_exp2(-inv_tau * __log2f(t));
+          if constexpr (decltype(tau_is_one)::value) qe = fast_rcp(t);
+          else qe = fast_exp2(-inv_tau * fast_lg2(t));
           Pc[i] += qe; Pc[N + k] += qe;
           Xc[i] = fmaf(qe, gh[N + k], Xc[i]);
           Xc[N + k] = fmaf(qe, gh[i], Xc[N + k]);
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(128, MINB) fused_backward_kernel(const FusedPa
       for (int i = 0; i < N; ++i) { S += Pc[i]; D += fmaf(gh[i], Pc[i], Xc[i]); }
       const float dot = D / S, scale = inv_tau / S;
 #pragma unroll
-      for (int c = 0; c < F; ++c) df[c] = fmaf(gh[c] - dot, Pc[c], Xc[c]) * scale / f[c];
+      for (int c = 0; c < F; ++c) df[c] = fmaf(gh[c] - dot, Pc[c], Xc[c]) * scale * (c < N ? r1[c] : r2[c - N]);
     } else if (P.grad_world_h != nullptr) {
       float z[W], mx;
       int arg;

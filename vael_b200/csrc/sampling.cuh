@@ -18,6 +18,21 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
+// log2 / reciprocal of a NORMAL positive float: the bare MUFU instruction.  __log2f / __logf / 1.0f/x without
+// -use_fast_math wrap it in a denormal-range check and rescale (4-5 instructions; profiles/r02i: 6.5 instructions per
+// variate where 3 were expected); every argument below is a normal number by construction.
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLn2f = 0.6931471805599453f;
+
 // Gumbel(0,1) = -log(E), E ~ Exp(1) = -log(U)  (torch: -empty.exponential_().log())
 // U = (k + 1/2) 2^-23 with k the top 23 random bits: exact in fp32 and strictly inside (0,1), so E > 0 without a
 // clamp.  The noise only has to be Gumbel-distributed, not bit-reproducible against a CPU libm, so the logarithms are
@@ -28,8 +43,8 @@ __device__ __forceinline__ float gumbel_from_bits(uint32_t bits) {
   const float u = (static_cast<float>(bits >> 9) + 0.5f) * (1.0f / 8388608.0f);
   const float v = 1.0f - u;
   const float e_series = v * fmaf(v, fmaf(v, 0.33333334f, 0.5f), 1.0f);   // v + v^2/2 + v^3/3, |rel err| < v^3/4
-  const float e = (v < 1.0f / 1024.0f) ? e_series : -__logf(u);
-  return -__logf(e);
+  const float e = (v < 1.0f / 1024.0f) ? e_series : -kLn2f * fast_lg2(u);
+  return -kLn2f * fast_lg2(e);
 }
 
 constexpr float kLog2e = 1.4426950408889634f;
@@ -42,15 +57,20 @@ constexpr float kLogE2Min = -23.5f, kLogE2Max = 4.6f;
 //     log2(e)/tau (log p + g) = s log p - L / tau + const,    s = log2(e) / tau
 // (the constant shifts every world of the row alike: arg-max and softmax do not see it).  Same accuracy guard as
 // gumbel_from_bits: for U -> 1 the series of -log(1 - v) replaces the fast logarithm.
+// v = 1 - U below which the series replaces the fast logarithm (lg2.approx: absolute error 2^-22 on [0.5, 1), i.e. a
+// relative error of E = -log U of at most 0.3 % at the switch-over, one variate in 16 384), and the same bound on the
+// 23-bit integer for the per-call test
+constexpr float kSeriesBelow = 1.0f / 16384.0f;
+constexpr uint32_t kSeriesFromK = 8388608u - 512u;
 __device__ __forceinline__ float log2_exp_variate(uint32_t bits) {
   const float u = (static_cast<float>(bits >> 9) + 0.5f) * (1.0f / 8388608.0f);
   const float v = 1.0f - u;
   const float series = v * fmaf(v, fmaf(v, 0.48089835f, 0.72134752f), 1.44269504f);   // (v + v^2/2 + v^3/3) / ln 2
-  const float e2 = (v < 1.0f / 1024.0f) ? series : -__log2f(u);
-  return __log2f(e2);
+  const float e2 = (v < kSeriesBelow) ? series : -fast_lg2(u);
+  return fast_lg2(e2);
 }
 // The four variates of one Philox call.  The guard is taken per CALL, on the integers: the series is needed when one
-// of the four 23-bit numbers lies in the top 2^13 (v < 2^-10) — one call in 256 — and that rare path is a real branch
+// of the four 23-bit numbers lies in the top 2^9 (v < 2^-14) — one call in 4096 — and that rare path is a real branch
 // (the same values as four log2_exp_variate calls; 1.25 instead of 5 guard instructions per variate).
 // (k + 1/2) 2^-23 for a 23-bit k without an int->float conversion (I2F shares the quarter-rate XU pipe with the
 // MUFU logarithms this routine is made of): [1,2) float with mantissa k, minus (1 - 2^-24) — exact, the same value
@@ -59,15 +79,15 @@ __device__ __forceinline__ float unit_from_23_bits(uint32_t k) {
 }
 __device__ __forceinline__ void log2_exp_variates4(uint4 r, float* L4) {
   const uint32_t k0 = r.x >> 9, k1 = r.y >> 9, k2 = r.z >> 9, k3 = r.w >> 9;
-  if (max(max(k0, k1), max(k2, k3)) > 8388608u - 8192u - 1u) {
+  if (max(max(k0, k1), max(k2, k3)) >= kSeriesFromK) {
     L4[0] = log2_exp_variate(r.x); L4[1] = log2_exp_variate(r.y);
     L4[2] = log2_exp_variate(r.z); L4[3] = log2_exp_variate(r.w);
     return;
   }
-  L4[0] = __log2f(-__log2f(unit_from_23_bits(k0)));
-  L4[1] = __log2f(-__log2f(unit_from_23_bits(k1)));
-  L4[2] = __log2f(-__log2f(unit_from_23_bits(k2)));
-  L4[3] = __log2f(-__log2f(unit_from_23_bits(k3)));
+  L4[0] = fast_lg2(-fast_lg2(unit_from_23_bits(k0)));
+  L4[1] = fast_lg2(-fast_lg2(unit_from_23_bits(k1)));
+  L4[2] = fast_lg2(-fast_lg2(unit_from_23_bits(k2)));
+  L4[3] = fast_lg2(-fast_lg2(unit_from_23_bits(k3)));
 }
 // The exponential variates themselves, base 2: E2 = -log2(U) = E / ln 2, E ~ Exp(1), four per Philox call, with the
 // same per-call guard (series of -log(1 - v) where the fast logarithm's absolute error would be a large relative one).
@@ -75,16 +95,16 @@ __device__ __forceinline__ float exp2_variate(uint32_t bits) {
   const float u = unit_from_23_bits(bits >> 9);
   const float v = 1.0f - u;
   const float series = v * fmaf(v, fmaf(v, 0.48089835f, 0.72134752f), 1.44269504f);   // (v + v^2/2 + v^3/3) / ln 2
-  return (v < 1.0f / 1024.0f) ? series : -__log2f(u);
+  return (v < kSeriesBelow) ? series : -fast_lg2(u);
 }
 __device__ __forceinline__ void exp2_variates4(uint4 r, float* E4) {
   const uint32_t k0 = r.x >> 9, k1 = r.y >> 9, k2 = r.z >> 9, k3 = r.w >> 9;
-  if (max(max(k0, k1), max(k2, k3)) > 8388608u - 8192u - 1u) {
+  if (max(max(k0, k1), max(k2, k3)) >= kSeriesFromK) {
     E4[0] = exp2_variate(r.x); E4[1] = exp2_variate(r.y); E4[2] = exp2_variate(r.z); E4[3] = exp2_variate(r.w);
     return;
   }
-  E4[0] = -__log2f(unit_from_23_bits(k0)); E4[1] = -__log2f(unit_from_23_bits(k1));
-  E4[2] = -__log2f(unit_from_23_bits(k2)); E4[3] = -__log2f(unit_from_23_bits(k3));
+  E4[0] = -fast_lg2(unit_from_23_bits(k0)); E4[1] = -fast_lg2(unit_from_23_bits(k1));
+  E4[2] = -fast_lg2(unit_from_23_bits(k2)); E4[3] = -fast_lg2(unit_from_23_bits(k3));
 }
 // 2^x, x <= 0 (MUFU.EX2; 2 ulp): the softmax runs in the log2 domain, the log2(e) factor folded into 1/tau
 __device__ __forceinline__ float fast_exp2(float x) {
