@@ -147,7 +147,7 @@ def test_fused_logic_entry_points_stay_inside_their_outputs(circuits, inject):
     _lib, lib, _p, sp = _api()
     dc, _ = circuits["2digit"]
     gen = torch.Generator().manual_seed(3)
-    for B in BATCHES:
+    for B in BATCHES + (20001,):   # 20001 rows: the tile-pipeline forward of streaming batches (ragged last tile)
         for shift in (0, 1):
             x = (2 * torch.randn(B, 20, generator=gen)).cuda()
             qidx = torch.arange(B, device="cuda", dtype=torch.int32) % 19

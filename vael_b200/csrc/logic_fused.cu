@@ -232,6 +232,89 @@ __global__ void __launch_bounds__(128, FMINB) fused_forward_kernel(const FusedPa
   }
 }
 
+// The FAST forward for streaming batches: the same row computation, with the three 80-byte-per-row streams (logits in;
+// facts and world_h out) moved as [32, 2N] tiles by bulk copies through warp-private rings (WarpTileLoader) instead of
+// per-lane 128-bit global accesses.  The per-thread kernel above touches 20 different 128-byte lines with every
+// warp-wide row access: L1/TEX 70 % busy, the limiter at 0.64 of HBM (profiles/r02i_fused_topdown_ncu.md).
+constexpr int kFusedTileStages = 2;
+template <int F>
+__host__ __device__ constexpr int fused_tile_bytes() { return (kWarp * F * 4 + 127) / 128 * 128; }
+template <int F>
+__host__ __device__ constexpr int fused_warp_bytes() { return 128 + 3 * kFusedTileStages * fused_tile_bytes<F>(); }
+
+template <int N>
+__global__ void __launch_bounds__(128) fused_forward_tiles_kernel(const FusedParams P) {
+  constexpr int F = 2 * N, W = N * N, MW = (W + 31) / 32, FT = kWarp * F, TB = fused_tile_bytes<F>();
+  extern __shared__ __align__(128) uint8_t fused_smem[];
+  const uint64_t seed = P.seed_dev ? *P.seed_dev : P.seed;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  uint8_t* wb = fused_smem + (size_t)warp * fused_warp_bytes<F>();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wb);
+  float* istage = reinterpret_cast<float*>(wb + 128);
+  float* fstage = istage + kFusedTileStages * (TB / 4);
+  float* hstage = fstage + kFusedTileStages * (TB / 4);
+  const long long n_sub = (P.B + kWarp - 1) / kWarp;
+  const long long gw = (long long)blockIdx.x * nwarps + warp, GW = (long long)gridDim.x * nwarps;
+  if (gw >= n_sub) return;
+  const bool in_al = aligned16(P.logits);
+  const bool f_al = P.facts != nullptr && aligned16(P.facts), h_al = P.world_h != nullptr && aligned16(P.world_h);
+  const int n_out = (P.facts != nullptr ? 1 : 0) + (P.world_h != nullptr ? 1 : 0);
+  WarpTileLoader<kFusedTileStages> lx;
+  lx.init(istage, bars, TB / 4, lane);
+  auto request = [&](long long sub, int s) {
+    if (sub < n_sub) lx.issue(s, P.logits + sub * FT, (int)min((long long)kWarp, P.B - sub * kWarp) * F, in_al, lane, 0.0f);
+  };
+#pragma unroll
+  for (int s = 0; s < kFusedTileStages; ++s) request(gw + s * GW, s);
+  long long it = 0;
+  for (long long sub = gw; sub < n_sub; sub += GW, ++it) {
+    const int s = (int)(it % kFusedTileStages);
+    const int rows = (int)min((long long)kWarp, P.B - sub * kWarp);
+    const long long row = sub * kWarp + lane;
+    const bool valid = lane < rows;
+    lx.wait(s);
+    float x[F], y[F], rz[2], f[F];
+    tile_row_load<F>(lx.stage(s) + lane * F, x);
+    __syncwarp();
+    request(sub + kFusedTileStages * GW, s);
+    facts_row<2, N>(x, P.eps, y, rz);
+#pragma unroll
+    for (int c = 0; c < F; ++c) f[c] = (y[c] + P.eps) * rz[c / N];
+    uint32_t m[MW];
+#pragma unroll
+    for (int i = 0; i < MW; ++i) m[i] = 0u;
+    if (valid) fused_mask<MW>(m, P, row);
+    const int arg = draw_world<N>(f, row, seed).arg;
+    if (P.query != nullptr) {
+      float q = 0.0f;
+#pragma unroll
+      for (int e = 0; e < W; ++e)
+        if ((m[e >> 5] >> (e & 31)) & 1u) q = __fadd_rn(q, __fmul_rn(f[e / N], f[N + e % N]));
+      if (valid) P.query[row] = q;
+    }
+    if (P.world_idx != nullptr && valid) P.world_idx[row] = arg;
+    // the stores of two tiles ago have read their stages (n_out bulk groups per tile)
+    if (lane == 0) {
+      if (n_out == 2) bulk_wait_read<2>();
+      else if (n_out == 1) bulk_wait_read<1>();
+    }
+    __syncwarp();
+    if (P.facts != nullptr) tile_row_store<F>(fstage + s * (TB / 4) + lane * F, f);
+    if (P.world_h != nullptr) {
+      const int ia = arg / N, ka = arg - ia * N;
+      float h[F];
+#pragma unroll
+      for (int c = 0; c < F; ++c) h[c] = (c == ia || c == N + ka) ? 1.0f : 0.0f;   // (1 - y) + y written as 1
+      tile_row_store<F>(hstage + s * (TB / 4) + lane * F, h);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (P.facts != nullptr) warp_tile_store(P.facts + sub * FT, fstage + s * (TB / 4), rows * F, FT, f_al, lane);
+    if (P.world_h != nullptr) warp_tile_store(P.world_h + sub * FT, hstage + s * (TB / 4), rows * F, FT, h_al, lane);
+  }
+  if (lane == 0) bulk_wait_all<0>();
+}
+
 // MINB: resident CTAs per SM the register allocation is capped for (4 -> 128 registers with a few spilled words,
 // 1 -> 168 registers, no spills); VAEL_FUSED_BWD_MINB picks, the default is the measured optimum
 template <int N, bool FAST, int MINB = 1>
@@ -388,9 +471,28 @@ static cudaError_t fused_launch(int n, const FusedParams& P, int grid, int block
   return cudaGetLastError();
 }
 
+template <int N>
+static cudaError_t fused_forward_tiles(const FusedParams& P, int num_sms, cudaStream_t st) {
+  static const int nw_env = getenv("VAEL_FUSED_TILE_WARPS") ? atoi(getenv("VAEL_FUSED_TILE_WARPS")) : 0;
+  // measured on B200 (1 Mi rows): 2 warps per CTA 0.0586 ms, 3 0.0622, 4 0.0625; the per-thread kernel 0.0651
+  const int nw = nw_env ? max(1, min(4, nw_env)) : 2, smem = nw * fused_warp_bytes<2 * N>();
+  const long long n_sub = (P.B + kWarp - 1) / kWarp;
+  const int ctas = max(1, min(16, (227 * 1024) / (smem + 1024)));
+  const int grid = (int)max(1LL, min((n_sub + nw - 1) / nw, (long long)num_sms * ctas));
+  cudaError_t e = cudaFuncSetAttribute(fused_forward_tiles_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  fused_forward_tiles_kernel<N><<<grid, nw * 32, smem, st>>>(P);
+  return cudaGetLastError();
+}
+
 cudaError_t fused_forward(int n, const FusedParams& P, int num_sms, cudaStream_t st) {
   int grid, block;
   const bool fast = fused_fast_ok(P);
+  static const bool no_tiles = getenv("VAEL_FUSED_NO_TILES") != nullptr;   // A-B timing
+  if (fast && !no_tiles && P.B > (long long)num_sms * 128) {   // streaming batches: tiles by bulk copies
+    if (n == 10) return fused_forward_tiles<10>(P, num_sms, st);
+    if (n == 9) return fused_forward_tiles<9>(P, num_sms, st);
+  }
   fused_shape(P.B, num_sms, fast ? 6 : 3, &grid, &block);   // resident CTAs per SM by registers: 80 / 157
   return fast ? fused_launch<false, true>(n, P, grid, block, st) : fused_launch<false, false>(n, P, grid, block, st);
 }

@@ -220,29 +220,6 @@ cudaError_t gumbel_backward(const GumbelParams& P, int num_sms, cudaStream_t st)
 // CLIP: out = clamp(softmax, eps, hi) instead of (softmax + eps) / sum — MarioVAELModel's facts
 // (models/vael.py:319-322: Softmax then torch.clip(min=1e-5, max=0.9999)); its gradient passes where
 // eps <= softmax <= hi (torch.clip's rule) and is zero elsewhere.
-// row of K floats of a [32, K] shared-memory tile <-> registers, with the widest access the row pitch allows
-// (pitches of 80 / 120 / 72 / 36 bytes: 128 / 64 / 64 / 32-bit accesses are conflict-free per quarter / half warp)
-template <int K>
-__device__ __forceinline__ void tile_row_load(const float* row, float* x) {
-  constexpr int V = (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1);
-#pragma unroll
-  for (int c = 0; c < K; c += V) {
-    if constexpr (V == 4) { const float4 t = *reinterpret_cast<const float4*>(row + c); x[c] = t.x; x[c + 1] = t.y; x[c + 2] = t.z; x[c + 3] = t.w; }
-    else if constexpr (V == 2) { const float2 t = *reinterpret_cast<const float2*>(row + c); x[c] = t.x; x[c + 1] = t.y; }
-    else x[c] = row[c];
-  }
-}
-template <int K>
-__device__ __forceinline__ void tile_row_store(float* row, const float* x) {
-  constexpr int V = (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1);
-#pragma unroll
-  for (int c = 0; c < K; c += V) {
-    if constexpr (V == 4) *reinterpret_cast<float4*>(row + c) = make_float4(x[c], x[c + 1], x[c + 2], x[c + 3]);
-    else if constexpr (V == 2) *reinterpret_cast<float2*>(row + c) = make_float2(x[c], x[c + 1]);
-    else row[c] = x[c];
-  }
-}
-
 constexpr int kFactsStages = 2;
 template <int F, bool BWD>
 __host__ __device__ constexpr int facts_warp_bytes() {

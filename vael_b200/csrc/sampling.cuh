@@ -114,6 +114,29 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 
+// row of K floats of a [32, K] shared-memory tile <-> registers, with the widest access the row pitch allows
+// (pitches of 80 / 120 / 72 / 36 bytes: 128 / 64 / 64 / 32-bit accesses are conflict-free per quarter / half warp)
+template <int K>
+__device__ __forceinline__ void tile_row_load(const float* row, float* x) {
+  constexpr int V = (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1);
+#pragma unroll
+  for (int c = 0; c < K; c += V) {
+    if constexpr (V == 4) { const float4 t = *reinterpret_cast<const float4*>(row + c); x[c] = t.x; x[c + 1] = t.y; x[c + 2] = t.z; x[c + 3] = t.w; }
+    else if constexpr (V == 2) { const float2 t = *reinterpret_cast<const float2*>(row + c); x[c] = t.x; x[c + 1] = t.y; }
+    else x[c] = row[c];
+  }
+}
+template <int K>
+__device__ __forceinline__ void tile_row_store(float* row, const float* x) {
+  constexpr int V = (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1);
+#pragma unroll
+  for (int c = 0; c < K; c += V) {
+    if constexpr (V == 4) *reinterpret_cast<float4*>(row + c) = make_float4(x[c], x[c + 1], x[c + 2], x[c + 3]);
+    else if constexpr (V == 2) *reinterpret_cast<float2*>(row + c) = make_float2(x[c], x[c + 1]);
+    else row[c] = x[c];
+  }
+}
+
 // One row of the facts head: per group softmax y (exponentials as ex2.approx of the log2-scaled, non-positive
 // argument: 2 instructions instead of expf's ~10, relative error ~1e-6 on the terms that matter — the bar against the
 // reference's softmax is 1e-5), and rz[g] = 1 / sum_i (y_i + eps) (the detached normaliser of
