@@ -596,6 +596,28 @@ int l2_hint_env() {
   return h;
 }
 
+constexpr long long kOnceMinRows = 1 << 18;   // from this batch up the non-persistent grids below are used
+
+// ONE tile per warp, CTAs of a few warps, as many CTAs as there are tiles (no persistent loop): the write front of a
+// non-persistent grid advances compactly through memory, and write-dominated streams run measurably faster that way
+// (scripts/micro/storebench.cu, 12.8 KB tiles + 2.5 KB loads: 6.7 TB/s against 6.1 TB/s for persistent warps striding
+// over the tiles; pure stores 7.5 against 6.3)
+template <int NA, int NB, bool NORM, bool EVID>
+static cudaError_t launch_fwd_once(const Ad2Params& P, int nw, cudaStream_t st) {
+  using Sh = Ad2Shape<NA, NB>;
+  constexpr int PER_WARP = Sh::FACT_BYTES + Sh::OUT_BYTES + 128;
+  cudaError_t e = cudaFuncSetAttribute(ad2_forward_kernel<NA, NB, NORM, EVID, 1, 1>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, nw * PER_WARP);
+  if (e != cudaSuccess) return e;
+  const long long n_sub = (P.B + kWarp - 1) / kWarp;
+  const long long grid = (n_sub + nw - 1) / nw;
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+  Ad2Params Q = P;
+  Q.l2_hint = l2_hint_env();
+  ad2_forward_kernel<NA, NB, NORM, EVID, 1, 1><<<(unsigned)grid, nw * 32, nw * PER_WARP, st>>>(Q);
+  return cudaGetLastError();
+}
+
 template <int NA, int NB, bool NORM, bool EVID, int S, int SO, bool STG = false>
 static cudaError_t launch_fwd_cfg(const Ad2Params& P, int num_sms, cudaStream_t st) {
   using Sh = Ad2Shape<NA, NB>;
@@ -622,6 +644,12 @@ template <int NA, int NB, bool NORM, bool EVID>
 static cudaError_t launch_fwd_t(const Ad2Params& P, int num_sms, cudaStream_t st) {
   // pipeline depth (load stages S, store stages SO) — tunable for experiments, default 2/2
   static const int cfg = env_int("VAEL_AD2_FWD_STAGES", 22);
+  // streaming batches: one tile per warp, three warps per CTA (B = 2^23: 0.606 ms against 0.686 ms for the persistent
+  // pipeline below; 1 / 2 / 4 / 6 / 8 warps: 0.611 / 0.610 / 0.613 / 0.640 / 0.797).  Small batches keep the
+  // persistent kernel (B = 1e5: 11.3 us against 12.6).  VAEL_AD2_FWD_ONCE: 0 = never, n > 0 = always with n warps.
+  static const int once_env = env_int("VAEL_AD2_FWD_ONCE", -1);
+  if (once_env > 0 || (once_env < 0 && P.B >= kOnceMinRows))
+    return launch_fwd_once<NA, NB, NORM, EVID>(P, once_env > 0 ? min(8, once_env) : 3, st);
   if constexpr (!NORM && !EVID) {
     if (cfg == 23) return launch_fwd_cfg<NA, NB, NORM, EVID, 2, 3>(P, num_sms, st);
     if (cfg == 33) return launch_fwd_cfg<NA, NB, NORM, EVID, 3, 3>(P, num_sms, st);
@@ -632,7 +660,27 @@ static cudaError_t launch_fwd_t(const Ad2Params& P, int num_sms, cudaStream_t st
 }
 
 template <int NA, int NB, bool NORM>
+static cudaError_t launch_bwd_once(const Ad2Params& P, int nw, cudaStream_t st) {
+  using Sh = Ad2Shape<NA, NB>;
+  constexpr int PER_WARP = (Sh::FACT_BYTES + Sh::OUT_BYTES) + Sh::FACT_BYTES + 128;
+  cudaError_t e = cudaFuncSetAttribute(ad2_backward_kernel<NA, NB, NORM, 1, 1>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, nw * PER_WARP);
+  if (e != cudaSuccess) return e;
+  const long long n_sub = (P.B + kWarp - 1) / kWarp;
+  const long long grid = (n_sub + nw - 1) / nw;
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+  Ad2Params Q = P;
+  Q.l2_hint = l2_hint_env();
+  ad2_backward_kernel<NA, NB, NORM, 1, 1><<<(unsigned)grid, nw * 32, nw * PER_WARP, st>>>(Q);
+  return cudaGetLastError();
+}
+
+template <int NA, int NB, bool NORM>
 static cudaError_t launch_bwd_t(const Ad2Params& P, int num_sms, cudaStream_t st) {
+  // as the forward: 0.660 ms against 0.757 ms at B = 2^23 (2 / 3 / 4 / 6 / 8 warps: 0.660 / 0.660 / 0.660 / 0.661 / 0.726)
+  static const int once_env = env_int("VAEL_AD2_BWD_ONCE", -1);
+  if (once_env > 0 || (once_env < 0 && P.B >= kOnceMinRows))
+    return launch_bwd_once<NA, NB, NORM>(P, once_env > 0 ? min(8, once_env) : 4, st);
   constexpr int S = 2, SO = 2;
   using Sh = Ad2Shape<NA, NB>;
   constexpr int PER_WARP = S * (Sh::FACT_BYTES + Sh::OUT_BYTES) + SO * Sh::FACT_BYTES + 128;
