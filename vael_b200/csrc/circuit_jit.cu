@@ -295,6 +295,17 @@ void emit_row_stores(std::ostringstream& o, const std::vector<std::string>& e, c
   }
 }
 
+// Grid shape of the generated kernels.  Default: NON-persistent — one tile per warp, a few warps per CTA, as many CTAs
+// as tiles, single-buffered stages: the access front of such a grid advances compactly through memory and DRAM
+// streams run 10-15 % faster than with persistent warps striding over the tiles (scripts/micro/storebench.cu; the
+// hand-written two-AD kernels: 0.69 -> 0.61 ms and 0.76 -> 0.66 ms).  VAEL_JIT_PERSISTENT=1: the earlier shape (one
+// persistent CTA per SM, double-buffered stages), for A-B timing.
+static bool jit_persistent() {
+  static const bool v = [] { const char* e = getenv("VAEL_JIT_PERSISTENT"); return e != nullptr && e[0] == '1'; }();
+  return v;
+}
+static int jit_stages() { return jit_persistent() ? 2 : 1; }
+
 std::string generate_source(const vael_circuit_desc_t* d) {
   const int N = d->n_nodes, F = d->n_facts, W = d->n_worlds, Q = d->n_queries, MW = (W + 31) / 32;
   const int OC = std::max(std::max(W, Q), 1);
@@ -306,7 +317,7 @@ std::string generate_source(const vael_circuit_desc_t* d) {
   std::ostringstream& o = g.o;
   o << kPrelude;
   o << "#define F " << F << "\n#define W " << W << "\n#define NQ " << Q << "\n#define MW " << MW << "\n#define OC " << OC << "\n";
-  o << "#define NST 2\n#define NSO 2\n";
+  o << "#define NST " << jit_stages() << "\n#define NSO " << jit_stages() << "\n";
   o << "#define FB ((32 * F * 4 + 127) / 128 * 128)\n#define OB ((32 * OC * 4 + 127) / 128 * 128)\n#define GB ((32 * W * 4 + 127) / 128 * 128)\n";
 
   // which nodes only the normaliser needs (emitted inside `if constexpr (NORM)`)
@@ -646,7 +657,7 @@ std::string generate_source_wide(const vael_circuit_desc_t* d, const WidePlan& P
   std::ostringstream& o = g.o;
   o << kPrelude;
   o << "#define F " << F << "\n#define W " << W << "\n#define NQ " << Q << "\n#define WC " << WC << "\n#define NCH " << NCH
-    << "\n#define OC " << OC << "\n#define NST 2\n#define NSO 2\n#define NSF " << wide_store_stages() << "\n#define NSG 2\n";
+    << "\n#define OC " << OC << "\n#define NST " << jit_stages() << "\n#define NSO " << jit_stages() << "\n#define NSF " << wide_store_stages() << "\n#define NSG 2\n";
   o << "#define FB ((32 * F * 4 + 127) / 128 * 128)\n#define OB ((32 * OC * 4 + 127) / 128 * 128)\n#define GB ((32 * WC * 4 + 127) / 128 * 128)\n";
   std::vector<char> out_cone(N, 0);
   for (int w = 0; w < W; ++w) out_cone[d->world_node[w]] = 1;
@@ -1038,8 +1049,9 @@ JitProgram* jit_create(const vael_circuit_desc_t* d) {
   J->WC = WC;
   auto pad = [](int b) { return (b + 127) / 128 * 128; };
   const int FB = pad(32 * J->F * 4), OB = pad(32 * std::max(std::max(WC, J->Q), 1) * 4), GB = pad(32 * WC * 4);
-  J->fwd_warp_bytes = 128 + 2 * FB + (J->wide ? wide_store_stages() : 2) * OB;
-  J->bwd_warp_bytes = J->wide ? 128 + 2 * FB + 2 * GB + 2 * FB : 128 + 2 * (FB + GB) + 2 * FB;
+  const int ST = jit_stages();
+  J->fwd_warp_bytes = 128 + ST * FB + (J->wide ? wide_store_stages() : ST) * OB;
+  J->bwd_warp_bytes = J->wide ? 128 + ST * FB + 2 * GB + ST * FB : 128 + ST * (FB + GB) + ST * FB;
   J->ok = true;
   return J;
 }
@@ -1091,7 +1103,9 @@ static cudaError_t jit_launch(const JitProgram* J, CUfunction fn, int warp_bytes
   if (A.cuFuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, smem) != 0) return cudaErrorInvalidValue;
   const int ctas_per_sm = std::max(1, std::min(4, (227 * 1024) / (smem + 1024)));
   const long long n_sub = (C.B + 31) / 32;
-  const long long grid = std::max(1LL, std::min((n_sub + nw - 1) / nw, (long long)num_sms * ctas_per_sm));
+  long long grid = std::max(1LL, (n_sub + nw - 1) / nw);
+  if (jit_persistent()) grid = std::min(grid, (long long)num_sms * ctas_per_sm);
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
   JitParamsHost P{};
   P.facts = C.facts; P.qidx = C.qidx; P.qscalar = C.qscalar; P.B = C.B; P.qmask = C.qmask;
   P.worlds = C.worlds; P.query = C.query; P.queries_all = C.queries_all;
@@ -1123,12 +1137,12 @@ cudaError_t jit_forward(const JitProgram* J, const GenCall& C, int num_sms, cuda
   // warps per SM (one persistent CTA), measured on B200 (scripts/gpu_r2j.sh): the write-dominated forward wants few
   // store streams in flight for 12.8 KB world tiles (5) and more for smaller tiles / column chunks (7)
   static const int forced = jit_env("VAEL_JIT_FWD_WARPS", 0);
-  const int wps = forced ? forced : (J->wide ? 2 : (J->W >= 96 ? 5 : 7));
+  const int wps = forced ? forced : (jit_persistent() ? (J->wide ? 2 : (J->W >= 96 ? 5 : 7)) : (J->wide ? 2 : 3));
   if (C.queries_all != nullptr) return jit_launch(J, J->qall[norm ? 1 : 0], J->fwd_warp_bytes, wps, C, num_sms, st);
   return jit_launch(J, J->fwd[norm ? 1 : 0][evid ? 1 : 0], J->fwd_warp_bytes, wps, C, num_sms, st, C.worlds);
 }
 cudaError_t jit_backward(const JitProgram* J, const GenCall& C, int num_sms, cudaStream_t st) {
-  static const int wps = jit_env("VAEL_JIT_BWD_WARPS", 7);   // read-dominated: more loads in flight
+  static const int wps = jit_env("VAEL_JIT_BWD_WARPS", jit_persistent() ? 7 : 4);   // persistent: more loads in flight
   return jit_launch(J, J->bwd[(C.flags & VAEL_FLAG_NORMALIZE) ? 1 : 0], J->bwd_warp_bytes, wps, C, num_sms, st, C.grad_worlds);
 }
 
