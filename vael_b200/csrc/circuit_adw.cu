@@ -533,6 +533,19 @@ static int adw_env(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
+// Non-persistent grids (one tile per warp, as many CTAs as tiles) stream faster than persistent warps striding over
+// the tiles (circuit_ad2.cu, scripts/micro/storebench.cu).  Measured here (3-digit circuit, 524 288 rows): forward
+// 5.81 TB/s against 5.61 persistent; the adjoint, with its three-stage chunk ring, runs 6.38 persistent against 5.92
+// non-persistent and stays persistent.  VAEL_ADW_FWD_ONCE / VAEL_ADW_BWD_ONCE override (0 / 1).
+static bool adw_fwd_once() {
+  static const bool v = adw_env("VAEL_ADW_FWD_ONCE", 1) != 0;
+  return v;
+}
+static bool adw_bwd_once() {
+  static const bool v = adw_env("VAEL_ADW_BWD_ONCE", 0) != 0;
+  return v;
+}
+
 template <int NP, int NA, int NB, bool NORM, bool EVID, int S, int SO, int IC>
 static cudaError_t launch_fwd_cfg(const AdwParams& P0, int num_sms, cudaStream_t st) {
   using Sh = AdwShape<NP, NA, NB>;
@@ -548,7 +561,9 @@ static cudaError_t launch_fwd_cfg(const AdwParams& P0, int num_sms, cudaStream_t
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, nw * PER_WARP);
   if (e != cudaSuccess) return e;
   const long long n_sub = (P.B + kWarp - 1) / kWarp;
-  const long long grid = min((n_sub + nw - 1) / nw, (long long)num_sms);
+  long long grid = (n_sub + nw - 1) / nw;
+  if (!adw_fwd_once()) grid = min(grid, (long long)num_sms);
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
   kern<<<(unsigned)grid, nw * 32, nw * PER_WARP, st>>>(map, P);
   return cudaGetLastError();
 }
@@ -576,13 +591,15 @@ static cudaError_t launch_bwd_cfg(const AdwParams& P0, int num_sms, cudaStream_t
   alignas(64) CUtensorMap map;
   memset(&map, 0, sizeof(map));
   if (P.grad_worlds != nullptr && !make_map(&map, P.grad_worlds, P.B, Sh::W, Sh::C)) return cudaErrorNotSupported;
-  int nw = max(1, min(8, adw_env("VAEL_ADW_BWD_WARPS", (227 * 1024 - 1024) / PER_WARP)));
+  int nw = max(1, min(8, adw_env("VAEL_ADW_BWD_WARPS", adw_bwd_once() ? 2 : (227 * 1024 - 1024) / PER_WARP)));
   while (nw > 1 && nw * PER_WARP > 227 * 1024) --nw;
   auto kern = adw_backward_kernel<NP, NA, NB, NORM, S>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, nw * PER_WARP);
   if (e != cudaSuccess) return e;
   const long long n_sub = (P.B + kWarp - 1) / kWarp;
-  const long long grid = min((n_sub + nw - 1) / nw, (long long)num_sms);
+  long long grid = (n_sub + nw - 1) / nw;
+  if (!adw_bwd_once()) grid = min(grid, (long long)num_sms);
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
   kern<<<(unsigned)grid, nw * 32, nw * PER_WARP, st>>>(map, P);
   return cudaGetLastError();
 }
