@@ -716,7 +716,7 @@ static cudaError_t launch_queries(const Ad2QParams& P, bool norm, int num_sms, c
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, nw * per_warp);
     if (e != cudaSuccess) return e;
     const long long n_sub = (P.B + kWarp - 1) / kWarp;
-    const long long grid = min((n_sub + nw - 1) / nw, (long long)num_sms * 4);
+    const long long grid = tile_grid(n_sub, nw, (long long)num_sms * 4);
     kern<<<(unsigned)grid, nw * 32, nw * per_warp, st>>>(P);
     return cudaGetLastError();
   }
@@ -729,7 +729,7 @@ static cudaError_t launch_queries(const Ad2QParams& P, bool norm, int num_sms, c
   if (e != cudaSuccess) return e;
   const long long n_sub = (P.B + kWarp - 1) / kWarp;
   const int ctas_per_sm = max(1, min(8, (227 * 1024) / (smem_bytes + 1024)));
-  const long long grid = min((n_sub + nw - 1) / nw, (long long)num_sms * ctas_per_sm);
+  const long long grid = tile_grid(n_sub, nw, (long long)num_sms * ctas_per_sm);
   kern<<<(unsigned)grid, nw * 32, smem_bytes, st>>>(P);
   return cudaGetLastError();
 }

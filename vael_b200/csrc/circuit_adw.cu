@@ -697,7 +697,7 @@ cudaError_t adw_queries_diag(int np, int na, int nb, const float* facts, long lo
   const int nw = 4;
   auto kern = norm ? adw_queries_diag_kernel<10, 10, 10, true> : adw_queries_diag_kernel<10, 10, 10, false>;
   const long long n_sub = (B + kWarp - 1) / kWarp;
-  const long long grid = min((n_sub + nw - 1) / nw, (long long)num_sms * 4);
+  const long long grid = tile_grid(n_sub, nw, (long long)num_sms * 4);
   kern<<<(unsigned)grid, nw * 32, nw * PER_WARP, st>>>(facts, B, queries_all);
   return cudaGetLastError();
 }

@@ -1093,7 +1093,7 @@ const char* jit_log(const JitProgram* J) { return J ? J->log.c_str() : ""; }
 // `wide_tensor`: the [B,W] tensor a column-chunked (wide) kernel moves by 2-D tensor-map copies — worlds forward,
 // grad_worlds backward — or null when the call does not touch it
 static cudaError_t jit_launch(const JitProgram* J, CUfunction fn, int warp_bytes, int warps_per_sm, const GenCall& C, int num_sms,
-                              cudaStream_t st, const float* wide_tensor = nullptr) {
+                              cudaStream_t st, const float* wide_tensor = nullptr, bool resident_only = false) {
   const JitApi& A = jit_api();
   // one persistent CTA per SM holding `warps_per_sm` warps (the ad2 kernels' measured optimum: few, deep pipelines)
   int nw = std::max(1, std::min(8, warps_per_sm));
@@ -1104,7 +1104,7 @@ static cudaError_t jit_launch(const JitProgram* J, CUfunction fn, int warp_bytes
   const int ctas_per_sm = std::max(1, std::min(4, (227 * 1024) / (smem + 1024)));
   const long long n_sub = (C.B + 31) / 32;
   long long grid = std::max(1LL, (n_sub + nw - 1) / nw);
-  if (jit_persistent()) grid = std::min(grid, (long long)num_sms * ctas_per_sm);
+  if (jit_persistent() || resident_only) grid = std::min(grid, (long long)num_sms * ctas_per_sm);
   if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
   JitParamsHost P{};
   P.facts = C.facts; P.qidx = C.qidx; P.qscalar = C.qscalar; P.B = C.B; P.qmask = C.qmask;
@@ -1138,7 +1138,9 @@ cudaError_t jit_forward(const JitProgram* J, const GenCall& C, int num_sms, cuda
   // store streams in flight for 12.8 KB world tiles (5) and more for smaller tiles / column chunks (7)
   static const int forced = jit_env("VAEL_JIT_FWD_WARPS", 0);
   const int wps = forced ? forced : (jit_persistent() ? (J->wide ? 2 : (J->W >= 96 ? 5 : 7)) : (J->wide ? 2 : 3));
-  if (C.queries_all != nullptr) return jit_launch(J, J->qall[norm ? 1 : 0], J->fwd_warp_bytes, wps, C, num_sms, st);
+  // all-queries: small result tiles ([32, Q]) — a resident grid of many warps measures better than one tile per warp
+  if (C.queries_all != nullptr)
+    return jit_launch(J, J->qall[norm ? 1 : 0], J->fwd_warp_bytes, forced ? forced : 8, C, num_sms, st, nullptr, true);
   return jit_launch(J, J->fwd[norm ? 1 : 0][evid ? 1 : 0], J->fwd_warp_bytes, wps, C, num_sms, st, C.worlds);
 }
 cudaError_t jit_backward(const JitProgram* J, const GenCall& C, int num_sms, cudaStream_t st) {

@@ -296,7 +296,7 @@ static cudaError_t lt_launch(K kern, int per_warp, long long B, int num_sms, cud
   if (e != cudaSuccess) return e;
   const int ctas_per_sm = max(1, min(8, (227 * 1024) / (smem + 1024)));
   const long long n_sub = (B + kWarp - 1) / kWarp;
-  const long long grid = max(1LL, min((n_sub + nw - 1) / nw, (long long)num_sms * ctas_per_sm));
+  const long long grid = tile_grid(n_sub, nw, (long long)num_sms * ctas_per_sm);
   kern<<<(unsigned)grid, nw * 32, smem, st>>>(args...);
   return cudaGetLastError();
 }

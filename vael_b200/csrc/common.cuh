@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 
 #include <mutex>
 #include <vector>
@@ -157,6 +158,21 @@ __device__ __forceinline__ void warp_tile_store(float* gdst, const float* stage,
     for (int i = lane; i < n; i += 32) gdst[i] = stage[i];
     if (lane == 0) bulk_commit();   // keep the group count in step with the bulk path
   }
+}
+
+// Grid of a warp-tile kernel (warp w of the grid takes tiles w, w + GW, ...).  The kernels that move LARGE tiles (the
+// [32, W] world tiles of circuit_ad2.cu / circuit_adw.cu / circuit_jit.cu) launch non-persistent grids — one tile per
+// warp, as many CTAs as tiles: 10-15 % faster DRAM streams (scripts/micro/storebench.cu).  The kernels built on
+// WarpTileLoader move small tiles and / or pay a per-CTA prologue (tables staged in shared memory), and measured the
+// other way (scripts/gpu_r3t.sh: literal-table kernels 0.070 / 0.095 ms persistent against 0.143 / 0.159 ms, lane <->
+// row Gumbel 0.229 / 0.264 against 0.269 / 0.379, facts head and all-queries kernels within 5 % either way): they keep
+// the resident-CTAs-only grid.  VAEL_ONCE_TILES=1 flips them (A-B timing).
+inline long long tile_grid(long long n_sub, int warps_per_cta, long long resident_ctas) {
+  static const bool once = [] { const char* e = getenv("VAEL_ONCE_TILES"); return e != nullptr && e[0] == '1'; }();
+  long long grid = (n_sub + warps_per_cta - 1) / warps_per_cta;
+  if (!once) grid = grid < resident_ctas ? grid : resident_ctas;
+  if (grid < 1) grid = 1;
+  return grid > 0x7fffffffLL ? 0x7fffffffLL : grid;
 }
 
 __host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

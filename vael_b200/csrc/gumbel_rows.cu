@@ -327,7 +327,7 @@ cudaError_t launch_rows(K kernel, const GumbelParams& P, const GrLayout& L, int 
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S.smem);
   if (e != cudaSuccess) return e;
   const long long n_sub = (P.B + kWarp - 1) / kWarp;
-  const int grid = (int)max(1LL, min((n_sub + S.nw - 1) / S.nw, (long long)num_sms * S.ctas));
+  const int grid = (int)tile_grid(n_sub, S.nw, (long long)num_sms * S.ctas);
   kernel<<<grid, S.nw * 32, S.smem, st>>>(P);
   return cudaGetLastError();
 }

@@ -478,7 +478,7 @@ static cudaError_t fused_forward_tiles(const FusedParams& P, int num_sms, cudaSt
   const int nw = nw_env ? max(1, min(4, nw_env)) : 2, smem = nw * fused_warp_bytes<2 * N>();
   const long long n_sub = (P.B + kWarp - 1) / kWarp;
   const int ctas = max(1, min(16, (227 * 1024) / (smem + 1024)));
-  const int grid = (int)max(1LL, min((n_sub + nw - 1) / nw, (long long)num_sms * ctas));
+  const int grid = (int)tile_grid(n_sub, nw, (long long)num_sms * ctas);
   cudaError_t e = cudaFuncSetAttribute(fused_forward_tiles_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   fused_forward_tiles_kernel<N><<<grid, nw * 32, smem, st>>>(P);

@@ -303,7 +303,7 @@ static cudaError_t launch_facts_tile(const float* logits, const float* gf, long 
   const int smem = nw * facts_warp_bytes<NG * N, BWD>();
   const long long n_sub = (B + kWarp - 1) / kWarp;
   const int ctas = max(1, min(8, (227 * 1024) / (smem + 1024)));
-  const int grid = (int)max(1LL, min((n_sub + nw - 1) / nw, (long long)num_sms * ctas));
+  const int grid = (int)tile_grid(n_sub, nw, (long long)num_sms * ctas);
   cudaError_t e = cudaFuncSetAttribute(facts_tile_kernel<NG, N, BWD, CLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   facts_tile_kernel<NG, N, BWD, CLIP><<<grid, nw * 32, smem, st>>>(logits, gf, B, eps, hi, out);
