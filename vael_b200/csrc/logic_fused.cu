@@ -435,11 +435,15 @@ __global__ void __launch_bounds__(128, MINB) fused_backward_kernel(const FusedPa
 bool fused_supported(int na, int nb) { return na == nb && (na == 10 || na == 9); }
 
 // one row per thread.  Small batches (the B = 32 .. 4096 training configurations) use one-warp CTAs so that the
-// rows spread over as many SMs as possible — a row is a ~5 k-instruction serial chain; large batches use
-// four-warp CTAs, a few per SM, grid-striding.
+// rows spread over as many SMs as possible — a row is a long serial chain; large batches use four-warp CTAs.
 static void fused_shape(long long B, int num_sms, int ctas_per_sm, int* grid, int* block) {
   *block = (B <= (long long)num_sms * 128) ? 32 : 128;
-  *grid = (int)max(1LL, min((B + *block - 1) / *block, (long long)num_sms * ctas_per_sm * (128 / *block)));
+  // one row per thread, as many CTAs as rows need: no grid-stride loop (adjoint 0.216 -> 0.197 ms per Mi rows, forward
+  // 0.063 -> 0.059; VAEL_FUSED_PERSISTENT=1 restores the resident-CTAs-only grid)
+  static const bool persistent = getenv("VAEL_FUSED_PERSISTENT") != nullptr;
+  long long g = (B + *block - 1) / *block;
+  if (persistent) g = min(g, (long long)num_sms * ctas_per_sm * (128 / *block));
+  *grid = (int)max(1LL, min(g, 0x7fffffffLL));
 }
 
 // FAST needs bounded (Philox) noise and a tau that keeps the softmax terms inside fp32's range; y_soft is a
