@@ -225,6 +225,16 @@ def test_full_size_properties_and_host_path(dc, addition_family, B):
         we, _ = circuit_forward(dc, facts.detach(), qi, evidence=True)
     assert torch.allclose(we.sum(1), torch.ones(B, device="cuda"), atol=1e-5)
     assert float((we * (1 - wq.T[qi])).abs().max()) == 0.0
+    # NORMALIZE at this size (the non-persistent kernels of streaming batches): Z = prod_AD (sum p + (1 - sum p)) is 1
+    # up to rounding, so the normalised outputs are the plain ones within an ulp or two, and so is the adjoint
+    fn = facts.detach().clone().requires_grad_(True)
+    wn, qn = circuit_forward(dc, fn, qi, normalize=True)
+    assert torch.allclose(wn.detach(), w.detach(), rtol=5e-7, atol=0) and torch.allclose(qn.detach(), q.detach(), rtol=5e-7, atol=0)
+    gwn = torch.randn(B, 100, device="cuda", generator=g)
+    (gn,) = torch.autograd.grad((wn * gwn).sum() + qn.sum(), [fn])
+    (gp,) = torch.autograd.grad((w * gwn).sum() + q.sum(), [facts], retain_graph=True)
+    assert torch.allclose(gn, gp, rtol=1e-4, atol=1e-4 * float(gp.abs().max()))
+    del fn, wn, qn, gwn, gn, gp
     gw = torch.randn(B, 100, device="cuda", generator=g)
     (g1,) = torch.autograd.grad((w * gw).sum(), [facts], retain_graph=True)
     (g2,) = torch.autograd.grad((w * (3 * gw)).sum(), [facts], retain_graph=True)
@@ -313,3 +323,32 @@ def test_admissible_worlds_literal_table_kernel(cuda_device, B):
     assert odd.fast_kind == 0
     long_col = rng.integers(0, 2, size=(40, 18)); long_col[:, 0] = 1
     assert DeviceCircuit(circuit_from_world_table(long_col), cuda_device).fast_kind == 0
+
+
+@pytest.mark.parametrize("name", ["addition", "mario"])
+def test_streaming_batch_kernels_agree_with_interpreter(cuda_device, addition_family, name):
+    """From 2^18 rows up the two-AD kernels run on non-persistent grids (one tile per warp, single-buffered stages) and
+    so do the generated kernels: at B = 2^18 + 77 (ragged last tile) all three paths — structured, generated, CSR
+    interpreter — give the same bits forward (worlds, per-row query, NORMALIZE too) and the same adjoint to 1e-6 of its
+    largest entry."""
+    from vael_b200.mario_task import compile_mario_family
+    from vael_b200.ops import DeviceCircuit, circuit_forward
+    circ, groups = (addition_family.circuit, (10, 10)) if name == "addition" else (compile_mario_family((3, 3)).circuit, (9, 9))
+    dc = DeviceCircuit(circ, cuda_device)
+    B = (1 << 18) + 77
+    g = torch.Generator(device="cuda").manual_seed(9)
+    n = groups[0]
+    p = torch.softmax(2 * torch.randn(B, 2, n, device="cuda", generator=g), -1).clamp(1e-5, 0.9999)
+    qi = torch.randint(0, circ.n_queries, (B,), device="cuda", generator=g)
+    gw = torch.randn(B, circ.n_worlds, device="cuda", generator=g)
+    paths = [dict(), dict(force_generic=True)] + ([dict(force_jit=True)] if dc.jit_status()[0] else [])
+    for normalize in (False, True):
+        res = []
+        for kw in paths:
+            f = p.reshape(B, 2 * n).clone().requires_grad_(True)
+            w, q = circuit_forward(dc, f, qi, normalize=normalize, **kw)
+            (gf,) = torch.autograd.grad((w * gw).sum() + 2 * q.sum(), [f])
+            res.append((w.detach(), q.detach(), gf))
+        for w, q, gf in res[1:]:
+            assert torch.equal(w, res[0][0]) and torch.equal(q, res[0][1])
+            assert float((gf - res[0][2]).abs().max()) <= 1e-6 * float(res[0][2].abs().max())
