@@ -335,7 +335,7 @@ def test_streaming_batch_kernels_agree_with_interpreter(cuda_device, addition_fa
     from vael_b200.ops import DeviceCircuit, circuit_forward
     circ, groups = (addition_family.circuit, (10, 10)) if name == "addition" else (compile_mario_family((3, 3)).circuit, (9, 9))
     dc = DeviceCircuit(circ, cuda_device)
-    B = (1 << 18) + 77
+    B = (1 << 18) + 77 if name == "addition" else (1 << 16) + 77   # Mario: the adjoint alone is non-persistent here
     g = torch.Generator(device="cuda").manual_seed(9)
     n = groups[0]
     p = torch.softmax(2 * torch.randn(B, 2, n, device="cuda", generator=g), -1).clamp(1e-5, 0.9999)
