@@ -434,8 +434,8 @@ def test_mnist_model_checks_the_worlds_queries_matrix():
 
 def test_generated_circuit_kernels_compile_for_sm100a(addition_family):
     """circuit_jit.cu: the straight-line source generated for a circuit compiles with NVRTC for sm_100a (no GPU
-    needed: the module is not loaded); circuits outside the generator's scope are reported as such.  (The 3-digit
-    circuit — column-chunked variant, 9 k lines of source — compiles too but takes 20 s: covered by the GPU tests.)"""
+    needed: the module is not loaded); circuits outside the generator's scope are reported as such.  The 3-digit
+    circuit takes the column-chunked variant (2-D tensor-map box copies, 9 k lines of source, ~20 s of NVRTC)."""
     import ctypes
     from vael_b200 import _lib
     from vael_b200.mario_task import compile_mario_family
@@ -444,7 +444,8 @@ def test_generated_circuit_kernels_compile_for_sm100a(addition_family):
     buf = ctypes.create_string_buffer(1 << 16)
     from vael_b200.mario_task import admissible_circuit, mario_tables
     adm = admissible_circuit(mario_tables(compile_mario_family((3, 3)))[2])        # log semiring: out of scope
-    for circ, want in ((addition_family.circuit, 0), (compile_mario_family((3, 3)).circuit, 0), (adm, 1)):
+    wide = compile_addition_family(3, 10).circuit
+    for circ, want in ((addition_family.circuit, 0), (compile_mario_family((3, 3)).circuit, 0), (adm, 1), (wide, 0)):
         d = _lib.make_desc(circ)
         rc = lib.vael_jit_compile_check(ctypes.byref(d), buf, len(buf))
         if rc == 2:
