@@ -15,6 +15,8 @@
 // flight per thread), the KL and query terms are grid-stride loops over their [B,L] / [B] elements.  Per-CTA
 // partial sums go to a workspace in fp64 and the last CTA to finish adds them in index order, so the
 // result is deterministic.
+#include <cstdlib>
+
 #include "params.cuh"
 
 namespace vael {
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(256) elbo_terms_kernel(const ElboParams P) {
   }
 }
 
-constexpr int kElboMaxGrid = 2048;
+constexpr int kElboMaxGrid = 8192;
 size_t elbo_workspace_bytes() { return 16 + (size_t)kElboMaxGrid * 3 * sizeof(double); }
 
 cudaError_t elbo_terms(ElboParams P, void* workspace, int num_sms, cudaStream_t st) {
@@ -170,7 +172,10 @@ cudaError_t elbo_terms(ElboParams P, void* workspace, int num_sms, cudaStream_t 
   P.partials = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(workspace) + 16);
   // enough CTAs to fill the chip, never more than one per 1024 float4s of the pixel stream
   const long long work = max(1LL, (P.B * P.D) / 4096);
-  const int grid = (int)max(1LL, min(work, (long long)min(kElboMaxGrid, num_sms * 8)));
+  static const int grid_env = getenv("VAEL_ELBO_GRID") ? atoi(getenv("VAEL_ELBO_GRID")) : 0;   // experiments
+  // more, shorter contiguous spans stream faster (B = 65 536: 1184 CTAs 5.89 TB/s, 2048 6.14, 4096 6.21, 8192 6.28)
+  const int cap = grid_env > 0 ? min(kElboMaxGrid, grid_env) : kElboMaxGrid;
+  const int grid = (int)max(1LL, min(work, (long long)cap));
   if (P.rec_loss == VAEL_REC_MSE) elbo_terms_kernel<VAEL_REC_MSE><<<grid, 256, 0, st>>>(P);
   else if (P.rec_loss == VAEL_REC_BCE) elbo_terms_kernel<VAEL_REC_BCE><<<grid, 256, 0, st>>>(P);
   else elbo_terms_kernel<VAEL_REC_LAPLACE><<<grid, 256, 0, st>>>(P);
